@@ -1,0 +1,356 @@
+"""caesar.jl_b200 -- host-side mirror (Python, because Julia is absent from this image) of the Julia API that
+Caesar.jl's belief hot path sits behind: `manikde!`, `manifoldProduct`, `mmd`, `sample`, `getPoints`, `getBW`,
+evaluation of a ManifoldKernelDensity, and the ScatterAlignPose2/3 factor plugin.  Every operator is a thin call
+into libcaesar_b200.so through the C ABI of include/caesar_b200.h -- the same entry points the Julia shim
+(caesar.jl_b200/julia/CaesarB200.jl) binds with `ccall`.  No arithmetic of the hot path happens in Python and
+there is no CPU fallback.
+
+Reference interfaces mirrored (R: = /root/reference/):
+  manikde!(M, pts; bw)                 call sites R:ext/Images/ScatterAlignPose2.jl:105-106, R:test/testScatterAlignPose2.jl:187
+  manifoldProduct(ff, M; Niter, N)     call sites R:ext/services/additional.jl:24, R:docs/src/principles/multiplyingDensities.md:25
+  mmd(M, a, b, N, M, threads; bw)      call site  R:ext/Images/ScatterAlignPose2.jl:179
+  mmd(mkdA, mkdB), isapprox(;mmd_tol)  call sites R:test/ICRA2022_tests/insufficient_data.jl:53, R:test/testScatterAlignPose2.jl:81-82
+  (mkd)(pts)                           call sites R:test/ICRA2022_tests/multihypo_corners.jl:66-90
+  sample(mkd, n)                       call sites R:ext/Images/ScatterAlignPose2.jl:140-141,172-173
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import CB2_FP32, CB2_FP64, CB2Error, Density, ProductDesc, f64, ptr, circ_arr
+
+# variable types -> per-coordinate topology: 1 = circular (wrap to (-pi, pi])
+MANIFOLDS = {
+    "ContinuousScalar": (0,), "Circular": (1,), "Point2": (0, 0), "Point3": (0, 0, 0), "Position3": (0, 0, 0),
+    "Pose2": (0, 0, 1), "Pose3": (0, 0, 0, 1, 1, 1),
+    "TranslationGroup(2)": (0, 0), "TranslationGroup(3)": (0, 0, 0),
+    "SpecialEuclidean(2)": (0, 0, 1), "SpecialEuclidean(3)": (0, 0, 0, 1, 1, 1),
+}
+
+
+def _topology(M, d=None):
+    if M is None:
+        return tuple([0] * d)
+    if isinstance(M, str):
+        key = M.replace("RoME.", "").replace("IncrementalInference.", "")
+        if key not in MANIFOLDS:
+            raise KeyError(f"unknown variable type / manifold {M!r}")
+        return MANIFOLDS[key]
+    return tuple(int(bool(c)) for c in M)
+
+
+class Context:
+    """One library context = one GPU (one process per GPU).  precision: 'fp32' (default) or 'fp64'."""
+
+    def __init__(self, device=0, precision="fp32"):
+        self._h = C.c_void_p()
+        prec = {"fp32": CB2_FP32, "fp64": CB2_FP64, CB2_FP32: CB2_FP32, CB2_FP64: CB2_FP64}[precision]
+        L = _capi.lib()
+        rc = L.cb2_create(int(device), prec, C.byref(self._h))
+        if rc != 0:
+            raise CB2Error(rc, L.cb2_last_error(None).decode())
+        self.device = int(device)
+        self.precision = "fp64" if prec == CB2_FP64 else "fp32"
+
+    def check(self, rc):
+        if rc != 0:
+            raise CB2Error(rc, _capi.lib().cb2_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _capi.lib().cb2_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(_capi.lib().cb2_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def synchronize(self):
+        self.check(_capi.lib().cb2_synchronize(self._h))
+
+    @property
+    def kernel_launches(self):
+        return int(_capi.lib().cb2_kernel_launches(self._h))
+
+    @property
+    def sm_count(self):
+        return int(_capi.lib().cb2_device_sm_count(self._h))
+
+    def stage_ms(self, name):
+        return float(_capi.lib().cb2_last_stage_ms(self._h, name.encode()))
+
+
+_default_ctx = {}
+
+
+def context(device=0, precision="fp32"):
+    key = (int(device), precision)
+    if key not in _default_ctx:
+        _default_ctx[key] = Context(device, precision)
+    return _default_ctx[key]
+
+
+class ManifoldKernelDensity:
+    """Equally (or explicitly) weighted Gaussian-kernel density on a product of lines and circles.
+    pts: N x d coordinates (row = point; memory-identical to Julia's d x N column-major matrix)."""
+
+    def __init__(self, manifold, pts, bw, weights=None, partial=None, infoPerCoord=None):
+        self.pts = f64(np.atleast_2d(pts))
+        self.N, self.d = self.pts.shape
+        self.manifold = manifold
+        self.circular = _topology(manifold, self.d)
+        if len(self.circular) != self.d:
+            raise ValueError(f"manifold {manifold!r} has {len(self.circular)} coordinates, points have {self.d}")
+        self.bw = f64(np.broadcast_to(np.asarray(bw, dtype=np.float64), (self.d,)))
+        self.weights = None if weights is None else f64(weights)
+        self.partial = partial
+        self.infoPerCoord = np.ones(self.d) if infoPerCoord is None else f64(infoPerCoord)
+
+    def __call__(self, q, logp=False, ctx=None):
+        return evaluate(self, q, logp=logp, ctx=ctx)
+
+    def _density(self):
+        return Density(self.N, self.pts.ctypes.data, self.bw.ctypes.data,
+                       self.weights.ctypes.data if self.weights is not None else None)
+
+
+MKD = ManifoldKernelDensity
+
+
+def getPoints(mkd):
+    return mkd.pts
+
+
+def getBW(mkd):
+    return mkd.bw
+
+
+def Npts(mkd):
+    return mkd.N
+
+
+def Ndim(mkd):
+    return mkd.d
+
+
+def kde_bandwidth(pts, manifold=None, ctx=None):
+    """Leave-one-out likelihood cross-validation bandwidth, one sigma per coordinate (what `manikde!` computes
+    when `bw` is not given)."""
+    ctx = ctx or context()
+    pts = f64(np.atleast_2d(pts))
+    N, d = pts.shape
+    circ = circ_arr(_topology(manifold, d), d)
+    out = np.zeros(d)
+    ctx.check(_capi.lib().cb2_kde_bw_loo(ctx._h, ptr(pts), d, N, ptr(circ), ptr(out)))
+    return out
+
+
+def kde_bandwidth_batch(pts_list, manifold=None, ctx=None):
+    ctx = ctx or context()
+    arrs = [f64(np.atleast_2d(p)) for p in pts_list]
+    d = arrs[0].shape[1]
+    B = len(arrs)
+    circ = circ_arr(_topology(manifold, d), d)
+    mus = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+    Ns = np.array([a.shape[0] for a in arrs], dtype=np.int32)
+    out = np.zeros((B, d))
+    ctx.check(_capi.lib().cb2_kde_bw_loo_batch(ctx._h, C.cast(mus, C.c_void_p), ptr(Ns), B, d, ptr(circ), ptr(out)))
+    return out
+
+
+def manikde(manifold, pts, bw=None, weights=None, partial=None, infoPerCoord=None, ctx=None):
+    """`manikde!(M, pts; bw)`: bandwidth by LOO cross-validation on the device unless given."""
+    pts = f64(np.atleast_2d(pts))
+    if bw is None:
+        bw = kde_bandwidth(pts, manifold, ctx=ctx)
+    return ManifoldKernelDensity(manifold, pts, bw, weights, partial, infoPerCoord)
+
+
+def mmd(a, b, bw=None, ctx=None):
+    """`mmd(M, a, b, N, M; bw)` on point arrays, or `mmd(mkdA, mkdB; bw=[0.001])` on two beliefs.
+    Biased V-statistic MMD^2 with k = exp(-bw |p - q|^2)."""
+    ctx = ctx or context()
+    if isinstance(a, ManifoldKernelDensity):
+        a, b = a.pts, b.pts
+        bw = 0.001 if bw is None else bw
+    if bw is None:
+        raise ValueError("bw is required for point arrays")
+    bw = float(np.ravel(bw)[0])
+    a, b = f64(np.atleast_2d(a)), f64(np.atleast_2d(b))
+    if a.shape[1] != b.shape[1]:
+        raise ValueError("dimension mismatch")
+    out = C.c_double()
+    ctx.check(_capi.lib().cb2_mmd(ctx._h, ptr(a), a.shape[0], ptr(b), b.shape[0], a.shape[1], bw, C.byref(out)))
+    return out.value
+
+
+def mmd_sums(a, b, bw, rows_a=None, rows_b=None, ctx=None):
+    """Raw pair sums {aa, ab, bb} over row ranges (the unit a row-sharded multi-GPU mmd all-reduces)."""
+    ctx = ctx or context()
+    a, b = f64(np.atleast_2d(a)), f64(np.atleast_2d(b))
+    ra = rows_a or (0, a.shape[0])
+    rb = rows_b or (0, b.shape[0])
+    out = np.zeros(3)
+    ctx.check(_capi.lib().cb2_mmd_sums(ctx._h, ptr(a), a.shape[0], ptr(b), b.shape[0], a.shape[1], float(bw),
+                                       ra[0], ra[1], rb[0], rb[1], ptr(out)))
+    return out
+
+
+def mmd_combine(sums, N, M):
+    return sums[0] / (N * N) - 2.0 * sums[1] / (N * M) + sums[2] / (M * M)
+
+
+def isapprox(a, b, mmd_tol=1e-2, ctx=None):
+    return mmd(a, b, ctx=ctx) < mmd_tol
+
+
+def mmd_se_batch(a, b, bw, coords, backward=True, grad=True, ctx=None):
+    """mmd(a, T(c_k) b) (or T(c_k)^-1 b when backward) for K coordinate vectors, with analytic gradients."""
+    ctx = ctx or context()
+    a, b = f64(np.atleast_2d(a)), f64(np.atleast_2d(b))
+    c = f64(np.atleast_2d(coords))
+    K, nc = c.shape
+    dim = a.shape[1]
+    if nc != (3 if dim == 2 else 6):
+        raise ValueError(f"coords must have {3 if dim == 2 else 6} columns for dim={dim}")
+    vals = np.zeros(K)
+    grads = np.zeros((K, nc)) if grad else None
+    ctx.check(_capi.lib().cb2_mmd_se_batch(ctx._h, ptr(a), a.shape[0], ptr(b), b.shape[0], dim, float(bw), ptr(c), K,
+                                           int(backward), ptr(vals), ptr(grads)))
+    return (vals, grads) if grad else vals
+
+
+def evaluate(mkd, q, logp=False, ctx=None):
+    ctx = ctx or context()
+    q = f64(np.atleast_2d(q))
+    if q.shape[1] != mkd.d:
+        if q.shape[0] == mkd.d:  # Julia passes d x Q
+            q = f64(q.T)
+        else:
+            raise ValueError("query dimension mismatch")
+    out = np.zeros(q.shape[0])
+    w = mkd.weights
+    ctx.check(_capi.lib().cb2_kde_eval(ctx._h, ptr(mkd.pts), ptr(mkd.bw), ptr(w), mkd.d, mkd.N, ptr(q), q.shape[0],
+                                       int(logp), ptr(out)))
+    return out
+
+
+def sample(mkd, n=1, seed=0, stream=0, ctx=None):
+    """`sample(mkd, n)` -> (points, ): kernel ~ weights, plus bandwidth-scaled Gaussian noise."""
+    ctx = ctx or context()
+    out = np.zeros((int(n), mkd.d))
+    circ = circ_arr(mkd.circular, mkd.d)
+    ctx.check(_capi.lib().cb2_kde_sample(ctx._h, ptr(mkd.pts), ptr(mkd.bw), ptr(mkd.weights), mkd.d, mkd.N, ptr(circ),
+                                         int(n), int(seed), int(stream), ptr(out)))
+    return (out,)
+
+
+def _pack_products(groups, Nouts, niter, streams, sample_offsets, want_labels, want_bw, d):
+    B = len(groups)
+    descs = (ProductDesc * B)()
+    keep = []
+    outs, labels, bws = [], [], []
+    for b, dens in enumerate(groups):
+        D = len(dens)
+        arr = (Density * D)(*[m._density() for m in dens])
+        keep.append(arr)
+        o = np.zeros((Nouts[b], d))
+        lab = np.zeros((Nouts[b], D), dtype=np.int32) if want_labels else None
+        bw = np.zeros(d) if want_bw else None
+        outs.append(o); labels.append(lab); bws.append(bw)
+        descs[b].dens = arr
+        descs[b].D = D
+        descs[b].Nout = int(Nouts[b])
+        descs[b].niter = int(niter)
+        descs[b].stream = int(streams[b])
+        descs[b].sample_offset = int(sample_offsets[b])
+        descs[b].pts_out = o.ctypes.data
+        descs[b].labels_out = lab.ctypes.data if lab is not None else None
+        descs[b].bw_out = bw.ctypes.data if bw is not None else None
+    return descs, keep, outs, labels, bws
+
+
+def manifoldProducts(groups, manifold=None, N=None, Niter=1, seed=0, streams=None, sample_offsets=None,
+                     return_labels=False, bw="loo", ctx=None):
+    """Batched `manifoldProduct`: one device pass over B independent products (all variables of a Gibbs sweep /
+    all ready cliques).  groups: list of lists of ManifoldKernelDensity over the same variable type.
+    Returns a list of ManifoldKernelDensity (bw='loo': fresh LOO bandwidth as upstream; bw=None: skip)."""
+    ctx = ctx or context()
+    B = len(groups)
+    if B == 0:
+        return []
+    first = groups[0][0]
+    d = first.d
+    manifold = manifold if manifold is not None else first.manifold
+    topo = _topology(manifold, d)
+    for g in groups:
+        for m in g:
+            if m.d != d or tuple(m.circular) != tuple(topo):
+                raise ValueError("all messages of a batch must share the variable type")
+    Nouts = [int(N) if N is not None else max(m.N for m in g) for g in groups]
+    streams = list(range(B)) if streams is None else streams
+    sample_offsets = [0] * B if sample_offsets is None else sample_offsets
+    # upstream early-out: a product of one density is that density
+    results = [None] * B
+    multi = [b for b in range(B) if len(groups[b]) > 1]
+    for b in range(B):
+        if len(groups[b]) == 1:
+            results[b] = (groups[b][0], None)
+    if multi:
+        want_bw = bw == "loo"
+        descs, keep, outs, labels, bws = _pack_products([groups[b] for b in multi], [Nouts[b] for b in multi], Niter,
+                                                        [streams[b] for b in multi], [sample_offsets[b] for b in multi],
+                                                        return_labels, want_bw, d)
+        circ = circ_arr(topo, d)
+        ctx.check(_capi.lib().cb2_product_batch(ctx._h, descs, len(multi), ptr(circ), d, int(seed)))
+        for i, b in enumerate(multi):
+            bwv = bws[i] if want_bw else (bw if bw is not None else np.full(d, np.nan))
+            results[b] = (ManifoldKernelDensity(manifold, outs[i], bwv), labels[i])
+    if return_labels:
+        return results
+    return [r[0] for r in results]
+
+
+def manifoldProduct(ff, manifold=None, Niter=1, N=None, seed=0, stream=0, return_labels=False, bw="loo", ctx=None):
+    """`manifoldProduct(ff, M; Niter=1, N)`: Gibbs-sampled product of the beliefs in `ff`."""
+    r = manifoldProducts([list(ff)], manifold, N, Niter, seed, [stream], None, return_labels, bw, ctx)
+    return r[0]
+
+
+def product_points(dens, circular, Nout, seed=0, niter=1, stream=0, sample_offset=0, ctx=None):
+    """Raw single product: dens = list of (pts, bw[, w]).  Returns (pts Nout x d, labels Nout x D)."""
+    ctx = ctx or context()
+    ms = [ManifoldKernelDensity(circular, x[0], x[1], x[2] if len(x) > 2 else None) for x in dens]
+    d = ms[0].d
+    descs, keep, outs, labels, _ = _pack_products([ms], [Nout], niter, [stream], [sample_offset], True, False, d)
+    circ = circ_arr(ms[0].circular, d)
+    ctx.check(_capi.lib().cb2_product_batch(ctx._h, descs, 1, ptr(circ), d, int(seed)))
+    return outs[0], labels[0]
+
+
+def tree_levels(pts, bw, w=None, ctx=None):
+    """Level hierarchy of one message as built on the device (parity tests)."""
+    ctx = ctx or context()
+    m = ManifoldKernelDensity(None, pts, bw, w)
+    den = m._density()
+    depth, cnt = C.c_int32(), C.c_int32()
+    perm = np.zeros(m.N, dtype=np.int32)
+    L = _capi.lib()
+    ctx.check(L.cb2_tree_debug(ctx._h, C.byref(den), m.d, 0, C.byref(depth), C.byref(cnt), ptr(perm), None, None, None))
+    levels = []
+    for l in range(depth.value + 1):
+        ctx.check(L.cb2_tree_debug(ctx._h, C.byref(den), m.d, l, C.byref(depth), C.byref(cnt), None, None, None, None))
+        mean, var, wt = np.zeros((cnt.value, m.d)), np.zeros((cnt.value, m.d)), np.zeros(cnt.value)
+        ctx.check(L.cb2_tree_debug(ctx._h, C.byref(den), m.d, l, C.byref(depth), C.byref(cnt), None, ptr(mean), ptr(var), ptr(wt)))
+        levels.append((mean, var, wt))
+    return depth.value, perm, levels
+
+
+from .factors import ScatterAlign, ScatterAlignPose2, ScatterAlignPose3, CalcFactor, preambleCache, getSample  # noqa: E402
+from .serialization import packDistribution, unpackDistribution  # noqa: E402

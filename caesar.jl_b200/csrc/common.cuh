@@ -1,0 +1,140 @@
+// common.cuh -- context, error plumbing, device helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <mutex>
+#include "../../include/caesar_b200.h"
+
+#define CB2_LOG2E 1.4426950408889634074
+#define CB2_TWO_PI 6.283185307179586476925286766559
+
+struct cb2_arena {  // grow-only device scratch; reset at the start of each public call
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+};
+
+struct cb2_pending {  // one submitted async product batch: what to copy back at cb2_wait
+  cudaEvent_t done = nullptr;
+  std::vector<void*> host_dst;
+  std::vector<const void*> pinned_src;
+  std::vector<size_t> bytes;
+  void* pinned_block = nullptr;
+  void* dev_block = nullptr;
+};
+
+struct cb2_ctx {
+  int device = 0;
+  int precision = CB2_FP32;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cb2_arena arena;       // device scratch
+  char* pinned = nullptr;  // pinned host staging
+  size_t pinned_cap = 0;
+  uint64_t launches = 0;
+  std::string err;
+  std::mutex mu;
+  std::map<std::string, double> stage_ms;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::map<int64_t, cb2_pending> pending;
+  int64_t next_ticket = 1;
+};
+
+int cb2_fail(cb2_ctx* ctx, int code, const char* fmt, ...);
+
+#define CB2_CUDA(ctx, call)                                                                         \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return cb2_fail(ctx, e__ == cudaErrorMemoryAllocation ? CB2_ERR_NOMEM : CB2_ERR_CUDA,         \
+                      "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define CB2_CHECK_LAUNCH(ctx, name)                                                                     \
+  do {                                                                                                  \
+    (ctx)->launches++;                                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                                               \
+    if (e__ != cudaSuccess)                                                                             \
+      return cb2_fail(ctx, CB2_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__));     \
+  } while (0)
+
+#define CB2_REQUIRE(ctx, cond, ...)                                  \
+  do {                                                               \
+    if (!(cond)) return cb2_fail(ctx, CB2_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// device scratch: 256-byte aligned bump allocation out of the context arena
+int cb2_arena_reserve(cb2_ctx* ctx, size_t bytes);  // ensure capacity (may reallocate: only call when off==0)
+void* cb2_arena_alloc(cb2_ctx* ctx, size_t bytes);  // nullptr when out of reserved space
+int cb2_pinned_reserve(cb2_ctx* ctx, size_t bytes);
+void cb2_resolve_product_stages(cb2_ctx* ctx);  // product.cu: turns recorded events into stage_ms
+
+static inline size_t cb2_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// uniform in (0,1): float path keeps 24 bits (exactly representable, shared with the oracle's ubits=24),
+// double path keeps 53 bits (oracle's ubits=53)
+template <typename T> __device__ __forceinline__ T u01(uint32_t x0, uint32_t x1);
+template <> __device__ __forceinline__ float u01<float>(uint32_t x0, uint32_t) {
+  return ((float)(x0 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+template <> __device__ __forceinline__ double u01<double>(uint32_t x0, uint32_t x1) {
+  uint64_t v = (((uint64_t)x0 << 32) | x1) >> 11;
+  return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ double fast_exp2(double x) { return exp2(x); }
+__device__ __forceinline__ float fast_log2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ double fast_log2(double x) { return log2(x); }
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
+
+// wrap to [-pi, pi]
+__device__ __forceinline__ float wrap_pi(float x) { return x - 6.2831853071795864769f * rintf(x * 0.15915494309189533577f); }
+__device__ __forceinline__ double wrap_pi(double x) { return x - CB2_TWO_PI * rint(x / CB2_TWO_PI); }
+
+__device__ __forceinline__ float rint_t(float x) { return rintf(x); }
+__device__ __forceinline__ double rint_t(double x) { return rint(x); }
+__device__ __forceinline__ float atan2_t(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double atan2_t(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

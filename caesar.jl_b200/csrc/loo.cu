@@ -1,0 +1,300 @@
+// loo.cu -- per-dimension leave-one-out likelihood cross-validation bandwidth (K4): what upstream
+// `manikde!(M, pts)` does when no bandwidth is given (call site R:test/testScatterAlignPose2.jl:187).
+//
+// A "problem" is one coordinate of one density: N scalars.  The golden-section search state of every problem
+// lives on the device; each iteration is two launches for the whole batch (no host round trip):
+//   loo_rows_kernel   : for every active problem, sum_i log( sum_{j != i} exp2(-(x_i-x_j)^2 c(h)) ), one CTA per
+//                       (problem, block of 1024 rows), rows in registers, columns broadcast from shared memory
+//   golden_step_kernel: one thread per problem folds the row-block partials in fixed order, turns them into
+//                       the objective value and advances that problem's bracket.
+// The bracket and the update rule follow Ihler's `ksize(..., 'lcv')` / `golden` as restated in oracle/cb2_oracle.c.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kRI = 4;
+constexpr int kCT = 1024;
+constexpr double kTol = 1e-2;
+
+struct LooProblem {
+  const double* x;  // first scalar of this coordinate
+  int stride;       // distance between consecutive points (= d)
+  int N;
+  int circular;
+  int part0;        // first slot in the row-block partial array
+  int nrb;
+};
+
+struct LooState {
+  double x0, x1, x2, x3, f1, f2;
+  double h_eval;  // bandwidth to evaluate in the next rows pass
+  int phase;      // 0: evaluating x1, 1: evaluating x2, 2: iterating (evaluating the new interior point), 3: done
+  int slot;       // which of (x1,x2) h_eval belongs to while iterating
+  double result;
+};
+
+// one thread per problem: bracket from the smallest neighbour gap and the data range
+__global__ void loo_init_kernel(const LooProblem* __restrict__ probs, int P, LooState* __restrict__ st,
+                                double* __restrict__ sortbuf) {
+  int p = blockIdx.x;
+  if (p >= P) return;
+  const LooProblem pr = probs[p];
+  // block-wide min gap: every thread scans a slice for its nearest right neighbour (O(N^2 / threads), N <= 16K)
+  __shared__ double smin[kThreads], slo[kThreads], shi[kThreads];
+  double mn = 1e300, lo = 1e300, hi = -1e300;
+  for (int i = threadIdx.x; i < pr.N; i += blockDim.x) {
+    double xi = pr.x[(size_t)i * pr.stride];
+    lo = fmin(lo, xi); hi = fmax(hi, xi);
+    double best = 1e300;
+    for (int j = 0; j < pr.N; ++j) {
+      double xj = pr.x[(size_t)j * pr.stride];
+      double g = xj - xi;
+      // nearest neighbour at or to the right (ties broken by index so duplicates give gap 0 once)
+      if ((g > 0 || (g == 0 && j > i)) && g < best) best = g;
+    }
+    mn = fmin(mn, best);
+  }
+  smin[threadIdx.x] = mn; slo[threadIdx.x] = lo; shi[threadIdx.x] = hi;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      smin[threadIdx.x] = fmin(smin[threadIdx.x], smin[threadIdx.x + o]);
+      slo[threadIdx.x] = fmin(slo[threadIdx.x], slo[threadIdx.x + o]);
+      shi[threadIdx.x] = fmax(shi[threadIdx.x], shi[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    LooState s;
+    double m = smin[0] < 1e-6 ? 1e-6 : smin[0];
+    double range = shi[0] - slo[0];
+    if (!(range >= 1e-6)) {
+      s.phase = 3; s.result = 1e-6; s.h_eval = 1.0;
+      s.x0 = s.x1 = s.x2 = s.x3 = s.f1 = s.f2 = 0; s.slot = 0;
+      st[p] = s;
+      return;
+    }
+    const double C = (3.0 - sqrt(5.0)) / 2.0;
+    double ax = 2.0 * m / (1.0 + sqrt(5.0)), bx = m, cx = 2.0 * range;
+    s.x0 = ax; s.x3 = cx;
+    if (fabs(cx - bx) > fabs(bx - ax)) { s.x1 = bx; s.x2 = bx + C * (cx - bx); }
+    else { s.x2 = bx; s.x1 = bx - C * (bx - ax); }
+    s.f1 = s.f2 = 0; s.phase = 0; s.slot = 1; s.h_eval = s.x1; s.result = 0;
+    st[p] = s;
+  }
+  (void)sortbuf;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict__ st, const int2* __restrict__ cta_map,
+                double* __restrict__ partial) {
+  const int2 cm = cta_map[blockIdx.x];  // (problem, row block)
+  const LooState s = st[cm.x];
+  if (s.phase == 3) return;
+  const LooProblem pr = probs[cm.x];
+  __shared__ T sx[kCT];
+  __shared__ double sred[kThreads / 32];
+  const int tid = threadIdx.x;
+  // exponent in base 2: (x_i - x_j)^2 * 0.5*log2e/h^2 -> pre-scale the coordinates by sc
+  const double sc = sqrt(0.5 * CB2_LOG2E) / s.h_eval;
+  const double x_first = pr.x[0];  // common shift keeps FP32 differences accurate
+  const T period = (T)(CB2_TWO_PI * sc);
+  const T inv_period = (T)(1.0 / (CB2_TWO_PI * sc));
+  T xi[kRI], acc[kRI];
+  int rowi[kRI];
+  const int rbase = cm.y * (kThreads * kRI);
+#pragma unroll
+  for (int r = 0; r < kRI; ++r) {
+    int row = rbase + r * kThreads + tid;
+    rowi[r] = row;
+    int rr = row < pr.N ? row : 0;
+    xi[r] = (T)((pr.x[(size_t)rr * pr.stride] - x_first) * sc);
+    acc[r] = T(0);
+  }
+  for (int cs = 0; cs < pr.N; cs += kCT) {
+    __syncthreads();
+    for (int j = tid; j < kCT; j += kThreads) {
+      int col = cs + j;
+      sx[j] = col < pr.N ? (T)((pr.x[(size_t)col * pr.stride] - x_first) * sc) : T(1e18);
+    }
+    __syncthreads();
+    // the diagonal (j == i) only meets this sub-tile if it overlaps the CTA's rows
+    const bool has_diag = cs < rbase + kThreads * kRI && cs + kCT > rbase;
+    if (has_diag || pr.circular) {
+      for (int j = 0; j < kCT; ++j) {
+        T q = sx[j];
+#pragma unroll
+        for (int r = 0; r < kRI; ++r) {
+          T df = xi[r] - q;
+          if (pr.circular) df = df - period * rint_t(df * inv_period);
+          T kv = fast_exp2(-(df * df));
+          acc[r] += (cs + j == rowi[r]) ? T(0) : kv;
+        }
+      }
+    } else {
+#pragma unroll 8
+      for (int j = 0; j < kCT; ++j) {
+        T q = sx[j];
+#pragma unroll
+        for (int r = 0; r < kRI; ++r) {
+          T df = xi[r] - q;
+          acc[r] += fast_exp2(-(df * df));
+        }
+      }
+    }
+  }
+  double v = 0;
+#pragma unroll
+  for (int r = 0; r < kRI; ++r)
+    if (rowi[r] < pr.N) {
+      double a = (double)acc[r];
+      v += log(a > 2.2250738585072014e-308 ? a : 2.2250738585072014e-308);
+    }
+  v = warp_sum(v);
+  if ((tid & 31) == 0) sred[tid >> 5] = v;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sred[w];
+    partial[pr.part0 + cm.y] = t;
+  }
+}
+
+__global__ void golden_step_kernel(const LooProblem* __restrict__ probs, int P, const double* __restrict__ partial,
+                                   LooState* __restrict__ st, int* __restrict__ n_active) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  LooState s = st[p];
+  if (s.phase == 3) return;
+  const LooProblem pr = probs[p];
+  double t = 0;
+  for (int b = 0; b < pr.nrb; ++b) t += partial[pr.part0 + b];
+  const double h = s.h_eval;
+  // nll(h) = -(1/N) sum_i [ log(sum_{j!=i} k_ij) - 0.5 log(2 pi h^2) - log(N-1) ]
+  const double f = -(t / pr.N - 0.5 * log(CB2_TWO_PI * h * h) - log((double)(pr.N - 1)));
+  const double C = (3.0 - sqrt(5.0)) / 2.0, R = 1.0 - C;
+  if (s.phase == 0) { s.f1 = f; s.phase = 1; s.h_eval = s.x2; }
+  else {
+    if (s.phase == 1) { s.f2 = f; s.phase = 2; }
+    else if (s.slot == 2) s.f2 = f;
+    else s.f1 = f;
+    if (fabs(s.x3 - s.x0) > kTol * (fabs(s.x1) + fabs(s.x2))) {
+      if (s.f2 < s.f1) { s.x0 = s.x1; s.x1 = s.x2; s.x2 = R * s.x1 + C * s.x3; s.f1 = s.f2; s.h_eval = s.x2; s.slot = 2; }
+      else { s.x3 = s.x2; s.x2 = s.x1; s.x1 = R * s.x2 + C * s.x0; s.f2 = s.f1; s.h_eval = s.x1; s.slot = 1; }
+    } else {
+      s.result = s.f1 < s.f2 ? s.x1 : s.x2;
+      s.phase = 3;
+    }
+  }
+  st[p] = s;
+  if (s.phase != 3) atomicAdd(n_active, 1);
+}
+
+__global__ void loo_collect_kernel(const LooState* __restrict__ st, int P, double* __restrict__ out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) out[p] = st[p].result;
+}
+
+}  // namespace
+
+// Device-resident core: B densities (device Float64 d x N[b]), sigma_out_dev is B x d (device).  Enqueues the
+// whole search on the context stream; checks a device counter every few iterations to stop early.
+int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t* N, int B, int d,
+                        const uint8_t* circular, double* sigma_out_dev, void* scratch, size_t scratch_bytes,
+                        size_t* scratch_needed) {
+  const int P = B * d;
+  std::vector<LooProblem> probs(P);
+  std::vector<int2> cta_map;
+  int nparts = 0;
+  for (int b = 0; b < B; ++b)
+    for (int k = 0; k < d; ++k) {
+      LooProblem& pr = probs[(size_t)b * d + k];
+      pr.x = mu_dev[b] + k; pr.stride = d; pr.N = N[b];
+      pr.circular = circular ? circular[k] : 0;
+      pr.nrb = (N[b] + kThreads * kRI - 1) / (kThreads * kRI);
+      pr.part0 = nparts;
+      nparts += pr.nrb;
+      for (int rb = 0; rb < pr.nrb; ++rb) cta_map.push_back(make_int2(b * d + k, rb));
+    }
+  size_t need = cb2_align(sizeof(LooProblem) * P) + cb2_align(sizeof(LooState) * P) + cb2_align(sizeof(int2) * cta_map.size()) +
+                cb2_align(sizeof(double) * nparts) + cb2_align(sizeof(int) * 64) + 1024;
+  if (scratch_needed) *scratch_needed = need;
+  if (!scratch) return CB2_OK;  // sizing query
+  if (scratch_bytes < need) return cb2_fail(ctx, CB2_ERR_NOMEM, "loo scratch too small");
+  char* base = (char*)scratch;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* p = base + off; off += cb2_align(bytes); return p; };
+  LooProblem* probs_dev = (LooProblem*)take(sizeof(LooProblem) * P);
+  LooState* st_dev = (LooState*)take(sizeof(LooState) * P);
+  int2* map_dev = (int2*)take(sizeof(int2) * cta_map.size());
+  double* partial = (double*)take(sizeof(double) * nparts);
+  int* counters = (int*)take(sizeof(int) * 64);
+  CB2_CUDA(ctx, cudaMemcpyAsync(probs_dev, probs.data(), sizeof(LooProblem) * P, cudaMemcpyHostToDevice, ctx->stream));
+  CB2_CUDA(ctx, cudaMemcpyAsync(map_dev, cta_map.data(), sizeof(int2) * cta_map.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CB2_CUDA(ctx, cudaMemsetAsync(counters, 0, sizeof(int) * 64, ctx->stream));
+  loo_init_kernel<<<P, kThreads, 0, ctx->stream>>>(probs_dev, P, st_dev, nullptr);
+  CB2_CHECK_LAUNCH(ctx, "loo_init_kernel");
+  const int max_iter = 64, check_every = 8;
+  for (int it = 0; it < max_iter; ++it) {
+    if (ctx->precision == CB2_FP64)
+      loo_rows_kernel<double><<<(int)cta_map.size(), kThreads, 0, ctx->stream>>>(probs_dev, st_dev, map_dev, partial);
+    else
+      loo_rows_kernel<float><<<(int)cta_map.size(), kThreads, 0, ctx->stream>>>(probs_dev, st_dev, map_dev, partial);
+    CB2_CHECK_LAUNCH(ctx, "loo_rows_kernel");
+    golden_step_kernel<<<(P + 127) / 128, 128, 0, ctx->stream>>>(probs_dev, P, partial, st_dev, counters + it);
+    CB2_CHECK_LAUNCH(ctx, "golden_step_kernel");
+    if ((it + 1) % check_every == 0) {
+      int active = 0;
+      CB2_CUDA(ctx, cudaMemcpyAsync(&active, counters + it, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (active == 0) break;
+    }
+  }
+  loo_collect_kernel<<<(P + 127) / 128, 128, 0, ctx->stream>>>(st_dev, P, sigma_out_dev);
+  CB2_CHECK_LAUNCH(ctx, "loo_collect_kernel");
+  return CB2_OK;
+}
+
+extern "C" int cb2_kde_bw_loo_batch(cb2_ctx* ctx, const double* const* mu, const int32_t* N, int B, int d,
+                                    const uint8_t* circular, double* sigma_out) {
+  if (!ctx) return CB2_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CB2_REQUIRE(ctx, mu && N && sigma_out && B > 0, "null pointer or empty batch");
+  if (d < 1 || d > CB2_MAX_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d outside 1..%d", d, CB2_MAX_DIM);
+  size_t total = 0;
+  for (int b = 0; b < B; ++b) {
+    CB2_REQUIRE(ctx, mu[b] && N[b] >= 2, "density %d: need at least 2 points", b);
+    total += cb2_align((size_t)N[b] * d * sizeof(double));
+  }
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t loo_need = 0;
+  std::vector<const double*> fake(B, nullptr);
+  int rc = cb2_bw_loo_dev_core(ctx, fake.data(), N, B, d, circular, nullptr, nullptr, 0, &loo_need);
+  if (rc) return rc;
+  size_t out_bytes = cb2_align(sizeof(double) * B * d);
+  rc = cb2_arena_reserve(ctx, total + loo_need + out_bytes + 4096);
+  if (rc) return rc;
+  std::vector<const double*> dev(B);
+  for (int b = 0; b < B; ++b) {
+    double* p = (double*)cb2_arena_alloc(ctx, (size_t)N[b] * d * sizeof(double));
+    if (!p) return cb2_fail(ctx, CB2_ERR_NOMEM, "loo scratch exhausted");
+    CB2_CUDA(ctx, cudaMemcpyAsync(p, mu[b], (size_t)N[b] * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    dev[b] = p;
+  }
+  double* out_dev = (double*)cb2_arena_alloc(ctx, sizeof(double) * B * d);
+  void* scratch = cb2_arena_alloc(ctx, loo_need);
+  if (!out_dev || !scratch) return cb2_fail(ctx, CB2_ERR_NOMEM, "loo scratch exhausted");
+  rc = cb2_bw_loo_dev_core(ctx, dev.data(), N, B, d, circular, out_dev, scratch, loo_need, nullptr);
+  if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+  CB2_CUDA(ctx, cudaMemcpyAsync(sigma_out, out_dev, sizeof(double) * B * d, cudaMemcpyDeviceToHost, ctx->stream));
+  CB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return CB2_OK;
+}
+
+extern "C" int cb2_kde_bw_loo(cb2_ctx* ctx, const double* mu, int d, int N, const uint8_t* circular, double* sigma_out) {
+  const double* mus[1] = {mu};
+  int32_t Ns[1] = {N};
+  return cb2_kde_bw_loo_batch(ctx, mus, Ns, 1, d, circular, sigma_out);
+}

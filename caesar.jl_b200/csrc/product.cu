@@ -1,0 +1,945 @@
+// product.cu -- Gibbs-sampled products of Gaussian-kernel density messages on sm_100a (K5/K6), replacing
+// KernelDensityEstimate.prodAppxMSGibbsS behind ApproxManifoldProducts.manifoldProduct
+// (call site R:ext/services/additional.jl:24; algorithm: SURVEY.md App. A.3, restated in oracle/cb2_oracle.c).
+//
+// Two kernels per batch:
+//   tree_build_kernel : one CTA per message.  Level hierarchy of the ball tree by recursive median split on the
+//                       widest coordinate: per level a shared-memory bitonic sort on (node, coordinate, position),
+//                       always FP64 so that FP32 and FP64 mode (and the oracle) see the same tree.  Node
+//                       statistics bottom-up in FP64, written as padded records in the compute precision.
+//   gibbs_kernel      : one thread per output sample, one CTA per block of S samples of one product; all chains
+//                       of a CTA advance in lock step through (level, sweep, message).  The candidate nodes of
+//                       the current (message, level) are streamed once per CTA through shared memory with 1-D
+//                       TMA bulk copies (cp.async.bulk + mbarrier, double buffered) and read as warp-broadcast
+//                       128-bit loads, so every candidate record is fetched once per 256 chains.  The categorical
+//                       draw is a two-pass inverse CDF: pass 1 keeps per-chunk partial sums (running-max
+//                       rescaled, log-sum-exp safe), pass 2 re-scores only the selected chunk.
+//   Randomness: counter-based Philox4x32-10 keyed by (seed; sample, draw, stream, tag): results do not depend on
+//   batching, CTA shape or output-sample sharding across GPUs.
+#include "common.cuh"
+
+int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t* N, int B, int d,
+                        const uint8_t* circular, double* sigma_out_dev, void* scratch, size_t scratch_bytes,
+                        size_t* scratch_needed);
+
+namespace {
+
+constexpr int kMaxLev = 15;        // depth <= 14 for N <= 16384
+constexpr int kTreeThreads = 1024;
+constexpr int kS = 256;            // chains (threads) per Gibbs CTA
+constexpr int kNCH = 32;           // chunk partial sums per chain
+constexpr int kTileBytesF32 = 16384;
+
+__host__ __device__ inline int recn_of(int d) { return (2 * d + 1 + 3) / 4 * 4; }  // [mu(d), var(d), log2 w]
+__host__ __device__ inline int recl_of(int d) { return (d + 1 + 3) / 4 * 4; }      // [mu(d), log2 w]
+__host__ __device__ inline int ceil_log2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+__host__ __device__ inline int level_count(int N, int depth, int l) { return l < depth ? (1 << l) : N; }
+
+// leaf-position range [lo, lo+n) of node k at level l (< depth) under the balanced split left = ceil(n/2)
+__host__ __device__ inline void node_range(int N, int l, int k, int& lo, int& n) {
+  lo = 0; n = N;
+  for (int b = l - 1; b >= 0; --b) {
+    int left = (n + 1) >> 1;
+    if ((k >> b) & 1) { lo += left; n -= left; } else n = left;
+  }
+}
+__host__ __device__ inline int node_of(int N, int l, int p) {
+  int lo = 0, n = N, k = 0;
+  for (int b = 0; b < l; ++b) {
+    int left = (n + 1) >> 1;
+    if (p < lo + left) { k = 2 * k; n = left; } else { k = 2 * k + 1; lo += left; n -= left; }
+  }
+  return k;
+}
+
+struct DensMeta {
+  const double* pts;  // d x N device Float64
+  const double* w;    // N or null
+  double bw[CB2_MAX_DIM];
+  int N, depth;
+  long long rec_off[kMaxLev + 1];  // element offset of each level's records in the node pool
+  long long perm_off;              // offset in the int pool
+};
+
+struct ProdDev {
+  int D, Nout, sweeps, L;
+  uint32_t stream;
+  int sample_offset;
+  int dens[CB2_MAX_DENS];
+  double* out;   // d x Nout device
+  int* labels;   // D x Nout device or null
+};
+
+struct Work { int prod, s0; };
+
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ordered_bits(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ bool key_less(unsigned long long oa, uint32_t ta, unsigned long long ob, uint32_t tb) {
+  uint32_t na = ta >> 14, nb = tb >> 14;
+  if (na != nb) return na < nb;
+  if (oa != ob) return oa < ob;
+  return ta < tb;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTreeThreads)
+tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ int_pool, T* __restrict__ node_pool,
+                  double* __restrict__ stat_scratch, size_t stat_stride) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const DensMeta m = metas[blockIdx.x];
+  const int N = m.N, depth = m.depth, tid = threadIdx.x, nthr = blockDim.x;
+  int P2 = 1;
+  while (P2 < N) P2 <<= 1;
+  unsigned long long* ord = reinterpret_cast<unsigned long long*>(smem_raw);
+  uint32_t* tag = reinterpret_cast<uint32_t*>(ord + P2);
+  unsigned char* seg_dim = reinterpret_cast<unsigned char*>(tag + P2);
+  __shared__ double s_red[32];
+  __shared__ double s_wsum;
+  int* perm = int_pool + m.perm_off;
+  const bool pow2 = (P2 == N);
+
+  for (int p = tid; p < N; p += nthr) perm[p] = p;
+  __syncthreads();
+
+  for (int l = 0; l < depth; ++l) {
+    const int cnt = 1 << l;
+    // widest coordinate of every node: one warp per node, lanes over its points
+    for (int k = tid >> 5; k < cnt; k += nthr >> 5) {
+      int lo, n;
+      node_range(N, l, k, lo, n);
+      int best = 0;
+      double bestr = -1.0;
+      for (int i = 0; i < d; ++i) {
+        double mn = 1e300, mx = -1e300;
+        for (int p = lo + (tid & 31); p < lo + n; p += 32) {
+          double v = m.pts[(size_t)perm[p] * d + i];
+          mn = fmin(mn, v); mx = fmax(mx, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+          mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (mx - mn > bestr) { bestr = mx - mn; best = i; }
+      }
+      if ((tid & 31) == 0) seg_dim[k] = (unsigned char)best;
+    }
+    __syncthreads();
+    for (int p = tid; p < P2; p += nthr) {
+      if (p < N) {
+        int k = node_of(N, l, p);
+        ord[p] = ordered_bits(m.pts[(size_t)perm[p] * d + seg_dim[k]]);
+        tag[p] = ((uint32_t)k << 14) | (uint32_t)p;
+      } else {
+        ord[p] = ~0ull; tag[p] = ~0u;
+      }
+    }
+    __syncthreads();
+    // bitonic sort; when N is a power of two the nodes are aligned blocks of N>>l, sort inside blocks only
+    const int kmax = pow2 ? (N >> l) : P2;
+    for (int k = 2; k <= kmax; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < P2; i += nthr) {
+          int ixj = i ^ j;
+          if (ixj > i) {
+            bool up = (i & k) == 0;
+            unsigned long long oa = ord[i], ob = ord[ixj];
+            uint32_t ta = tag[i], tb = tag[ixj];
+            bool lt = key_less(ob, tb, oa, ta);  // b < a
+            if (lt == up) { ord[i] = ob; ord[ixj] = oa; tag[i] = tb; tag[ixj] = ta; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // apply the permutation: position p now holds the element that sat at position tag&0x3fff
+    int newp[CB2_MAX_PRODUCT_N / kTreeThreads];
+    for (int p = tid, c = 0; p < N; p += nthr, ++c) newp[c] = perm[tag[p] & 0x3fffu];
+    __syncthreads();
+    for (int p = tid, c = 0; p < N; p += nthr, ++c) perm[p] = newp[c];
+    __syncthreads();
+  }
+
+  // ---- statistics, bottom-up in FP64 (global scratch: per level mean[cnt*d], var[cnt*d], wt[cnt])
+  double wloc = 0;
+  if (m.w) for (int p = tid; p < N; p += nthr) wloc += m.w[p];
+  wloc = warp_sum(wloc);
+  if ((tid & 31) == 0) s_red[tid >> 5] = wloc;
+  __syncthreads();
+  if (tid == 0) { double s = 0; for (int w = 0; w < (nthr >> 5); ++w) s += s_red[w]; s_wsum = s; }
+  __syncthreads();
+  const double wsum = s_wsum;
+  double* sbase = stat_scratch + (size_t)blockIdx.x * stat_stride;
+  // level l statistics start at lvl_off(l) nodes; each node uses (2d+1) doubles
+  auto lvl_off = [&](int l) { return l < depth ? ((1 << l) - 1) : ((1 << depth) - 1); };
+  const int nd = 2 * d + 1;
+  const int RECN = recn_of(d), RECL = recl_of(d);
+  {
+    double* sl = sbase + (size_t)lvl_off(depth) * nd;
+    T* rec = node_pool + m.rec_off[depth];
+    for (int p = tid; p < N; p += nthr) {
+      int idx = perm[p];
+      double wt = m.w ? m.w[idx] / wsum : 1.0 / N;
+      for (int i = 0; i < d; ++i) {
+        double v = m.pts[(size_t)idx * d + i];
+        sl[(size_t)p * nd + i] = v;
+        sl[(size_t)p * nd + d + i] = m.bw[i] * m.bw[i];
+        rec[(size_t)p * RECL + i] = (T)v;
+      }
+      sl[(size_t)p * nd + 2 * d] = wt;
+      for (int i = d; i < RECL; ++i) rec[(size_t)p * RECL + i] = T(0);
+      rec[(size_t)p * RECL + d] = (T)(wt > 0 ? log2(wt) : -1e30);
+    }
+  }
+  __syncthreads();
+  for (int l = depth - 1; l >= 0; --l) {
+    const int cnt = 1 << l;
+    double* sl = sbase + (size_t)lvl_off(l) * nd;
+    const double* sc = sbase + (size_t)lvl_off(l + 1) * nd;
+    T* rec = node_pool + m.rec_off[l];
+    for (int k = tid; k < cnt; k += nthr) {
+      int c0, nch;
+      if (l + 1 == depth) { node_range(N, l, k, c0, nch); } else { c0 = 2 * k; nch = 2; }
+      double ws = 0;
+      for (int c = 0; c < nch; ++c) ws += sc[(size_t)(c0 + c) * nd + 2 * d];
+      sl[(size_t)k * nd + 2 * d] = ws;
+      for (int i = 0; i < d; ++i) {
+        double mm = 0;
+        for (int c = 0; c < nch; ++c) mm += sc[(size_t)(c0 + c) * nd + 2 * d] * sc[(size_t)(c0 + c) * nd + i];
+        mm /= ws;
+        double v = 0;
+        for (int c = 0; c < nch; ++c) {
+          double dm = sc[(size_t)(c0 + c) * nd + i] - mm;
+          v += sc[(size_t)(c0 + c) * nd + 2 * d] * (sc[(size_t)(c0 + c) * nd + d + i] + dm * dm);
+        }
+        v /= ws;
+        sl[(size_t)k * nd + i] = mm;
+        sl[(size_t)k * nd + d + i] = v;
+        rec[(size_t)k * RECN + i] = (T)mm;
+        rec[(size_t)k * RECN + d + i] = (T)v;
+      }
+      for (int i = 2 * d; i < RECN; ++i) rec[(size_t)k * RECN + i] = T(0);
+      rec[(size_t)k * RECN + 2 * d] = (T)(ws > 0 ? log2(ws) : -1e30);
+    }
+    __syncthreads();
+  }
+}
+
+// copies one level of the FP64 statistics scratch out for cb2_tree_debug
+__global__ void tree_debug_copy_kernel(const double* __restrict__ sbase, int d, int level_node0, int cnt,
+                                       double* __restrict__ mean, double* __restrict__ var, double* __restrict__ wt) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  const int nd = 2 * d + 1;
+  const double* s = sbase + (size_t)(level_node0 + k) * nd;
+  for (int i = 0; i < d; ++i) { mean[(size_t)k * d + i] = s[i]; var[(size_t)k * d + i] = s[d + i]; }
+  wt[k] = s[2 * d];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// mbarrier + 1-D TMA bulk copy helpers (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename T, int N> struct alignas(16) VecRec { T v[N]; };
+
+struct GibbsArgs {
+  const DensMeta* metas;
+  const ProdDev* prods;
+  const Work* work;
+  const int* int_pool;
+  const void* node_pool;
+  uint32_t k0, k1;
+  uint32_t circ_mask;
+};
+
+// score of one candidate, in log2 units (up to a constant shared by all candidates of the level)
+template <typename T, int DIM, bool LEAF>
+__device__ __forceinline__ T score(const T* __restrict__ rec, const T (&M)[DIM], const T (&Cq)[DIM], T qs, T cmul,
+                                   uint32_t circ) {
+  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
+  constexpr int NR = LEAF ? RECL : RECN;
+  VecRec<T, NR> r = *reinterpret_cast<const VecRec<T, NR>*>(rec);
+  if (LEAF) {  // Cq holds qs / (bw^2 + C): the log term is the same for every leaf and drops out
+    T e = r.v[DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      T df = r.v[i] - M[i];
+      if (circ >> i & 1) df = wrap_pi(df);
+      e = fma(-(df * df), Cq[i], e);
+    }
+    return e;
+  } else {
+    T e = r.v[2 * DIM];
+    T pa = T(1), pb = T(1);
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      T sv = fma(r.v[DIM + i], cmul, Cq[i]);
+      T df = r.v[i] - M[i];
+      if (circ >> i & 1) df = wrap_pi(df);
+      e = fma(-(df * df * qs), fast_rcp(sv), e);
+      if (i < 3) pa *= sv; else pb *= sv;
+    }
+    e -= T(0.5) * fast_log2(pa);
+    if (DIM > 3) e -= T(0.5) * fast_log2(pb);
+    return e;
+  }
+}
+
+// Gaussian product of the currently selected nodes of all messages except `skip` (skip = -1: all)
+template <typename T, int DIM>
+__device__ __forceinline__ void combine(const GibbsArgs& a, const ProdDev& pr, const int* __restrict__ ind_s, int tid,
+                                        int step, int skip, uint32_t circ, T (&M)[DIM], T (&C)[DIM]) {
+  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
+  T lam[DIM], s1[DIM], s2[DIM];
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) { lam[i] = T(0); s1[i] = T(0); s2[i] = T(0); }
+  const T* pool = reinterpret_cast<const T*>(a.node_pool);
+  for (int k = 0; k < pr.D; ++k) {
+    if (k == skip) continue;
+    const DensMeta& dm = a.metas[pr.dens[k]];
+    const int lev = min(step, dm.depth);
+    const int node = ind_s[k * kS + tid];
+    T mu[DIM], var[DIM];
+    if (lev == dm.depth) {
+      VecRec<T, RECL> r = *reinterpret_cast<const VecRec<T, RECL>*>(pool + dm.rec_off[lev] + (size_t)node * RECL);
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) { mu[i] = r.v[i]; var[i] = (T)(dm.bw[i] * dm.bw[i]); }
+    } else {
+      VecRec<T, RECN> r = *reinterpret_cast<const VecRec<T, RECN>*>(pool + dm.rec_off[lev] + (size_t)node * RECN);
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) { mu[i] = r.v[i]; var[i] = r.v[DIM + i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      T l = T(1) / var[i];
+      lam[i] += l;
+      if (circ >> i & 1) {
+        T sn, cs;
+        sincos_t(mu[i], &sn, &cs);
+        s1[i] = fma(l, sn, s1[i]); s2[i] = fma(l, cs, s2[i]);
+      } else {
+        s1[i] = fma(l, mu[i], s1[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) {
+    C[i] = T(1) / lam[i];
+    M[i] = (circ >> i & 1) ? atan2_t(s1[i], s2[i]) : s1[i] * C[i];
+  }
+}
+
+template <typename T, int DIM, uint32_t CIRC>
+__global__ void __launch_bounds__(kS)
+gibbs_kernel(const GibbsArgs a) {
+  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
+  constexpr int TILE_BYTES = kTileBytesF32 * (int)(sizeof(T) / 4);
+  constexpr int TN_NODE = TILE_BYTES / (RECN * (int)sizeof(T));
+  constexpr int TN_LEAF = TILE_BYTES / (RECL * (int)sizeof(T));
+  const uint32_t circ = CIRC == ~0u ? a.circ_mask : CIRC;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* tile[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw + TILE_BYTES)};
+  T* chunk = reinterpret_cast<T*>(smem_raw + 2 * TILE_BYTES);            // [kNCH][kS]
+  int* ind_s = reinterpret_cast<int*>(chunk + kNCH * kS);                  // [CB2_MAX_DENS][kS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ind_s + CB2_MAX_DENS * kS);  // [2]
+
+  const int tid = threadIdx.x;
+  const Work wk = a.work[blockIdx.x];
+  const ProdDev& pr = a.prods[wk.prod];
+  const int D = pr.D;
+  const int s = wk.s0 + tid;
+  const bool active = s < pr.Nout;
+  const uint32_t sid = (uint32_t)(pr.sample_offset + s);
+  const T* pool = reinterpret_cast<const T*>(a.node_pool);
+  const T HL = (T)(0.5 * CB2_LOG2E);
+  const bool single = D == 1;
+  const T qs = single ? T(0) : HL;
+  const T cmul = single ? T(0) : T(1);
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int k = 0; k < D; ++k) ind_s[k * kS + tid] = 0;
+  __syncthreads();
+  uint32_t use0 = 0, use1 = 0;  // completed uses of each tile buffer (phase parity)
+
+  for (int step = 1; step <= pr.L; ++step) {
+    // levelDown: a leaf stays itself, otherwise move to the first child
+    for (int k = 0; k < D; ++k) {
+      const DensMeta& dm = a.metas[pr.dens[k]];
+      if (step <= dm.depth) {
+        int node = ind_s[k * kS + tid];
+        if (step == dm.depth) { int lo, n; node_range(dm.N, step - 1, node, lo, n); node = lo; }
+        else node = 2 * node;
+        ind_s[k * kS + tid] = node;
+      }
+    }
+    for (int sweep = 0; sweep < pr.sweeps; ++sweep) {
+      for (int j = 0; j < D; ++j) {
+        const DensMeta& dj = a.metas[pr.dens[j]];
+        const int lev = min(step, dj.depth);
+        const bool leaf = lev == dj.depth;
+        const int cnt = level_count(dj.N, dj.depth, lev);
+        const T* lrec = pool + dj.rec_off[lev];
+        const int rec = leaf ? RECL : RECN;
+        const int TN = leaf ? TN_LEAF : TN_NODE;
+        const int ntiles = (cnt + TN - 1) / TN;
+        int CH = 4;
+        while (CH * kNCH < cnt) CH <<= 1;
+
+        T M[DIM], Cq[DIM];
+        if (!single) {
+          combine<T, DIM>(a, pr, ind_s, tid, step, j, circ, M, Cq);
+          if (leaf) {
+#pragma unroll
+            for (int i = 0; i < DIM; ++i) Cq[i] = HL / ((T)(dj.bw[i] * dj.bw[i]) + Cq[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < DIM; ++i) { M[i] = T(0); Cq[i] = leaf ? T(0) : T(1); }
+        }
+
+        // ---- pass 1: chunk partial sums of exp2(e - m), m = running (lazily raised) maximum
+        T m = -INFINITY, csum = T(0);
+        int cidx = 0;
+        if (tid == 0) {
+          uint32_t bytes = (uint32_t)(min(TN, cnt) * rec * (int)sizeof(T));
+          mbar_expect_tx(&bars[0], bytes);
+          tma_load_1d(tile[0], lrec, bytes, &bars[0]);
+        }
+        for (int t = 0; t < ntiles; ++t) {
+          const int b = t & 1;
+          if (tid == 0 && t + 1 < ntiles) {
+            int n1 = min(TN, cnt - (t + 1) * TN);
+            uint32_t bytes = (uint32_t)(n1 * rec * (int)sizeof(T));
+            mbar_expect_tx(&bars[b ^ 1], bytes);
+            tma_load_1d(tile[b ^ 1], lrec + (size_t)(t + 1) * TN * rec, bytes, &bars[b ^ 1]);
+          }
+          mbar_wait(&bars[b], (b ? use1 : use0) & 1);
+          if (b) ++use1; else ++use0;
+          const int nt = min(TN, cnt - t * TN);
+          const T* tb = tile[b];
+          const int zbase = t * TN;
+#pragma unroll 4
+          for (int z = 0; z < nt; ++z) {
+            T e = leaf ? score<T, DIM, true>(tb + z * RECL, M, Cq, qs, cmul, circ)
+                       : score<T, DIM, false>(tb + z * RECN, M, Cq, qs, cmul, circ);
+            if (e > m + T(60)) {  // rare: raise the reference maximum and rescale what has been summed
+              T sc = fast_exp2(m - e);
+              csum *= sc;
+              for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
+              m = e;
+            }
+            csum += fast_exp2(e - m);
+            if (((zbase + z + 1) & (CH - 1)) == 0) { chunk[cidx * kS + tid] = csum; csum = T(0); ++cidx; }
+          }
+          __syncthreads();  // everyone is done with tile[b] before it is refilled
+        }
+        if (cnt & (CH - 1)) { chunk[cidx * kS + tid] = csum; ++cidx; }
+        const int nch = cidx;
+
+        // ---- inverse CDF: pick the chunk, then re-score only that chunk
+        T tot = T(0);
+        for (int c = 0; c < nch; ++c) tot += chunk[c * kS + tid];
+        uint32_t rnd[4];
+        const uint32_t draw = (uint32_t)(((step - 1) * pr.sweeps + sweep) * D + j);
+        philox4x32_10(sid, draw, pr.stream, 0u, a.k0, a.k1, rnd);
+        const T tgt = u01<T>(rnd[0], rnd[1]) * tot;
+        T cum = T(0);
+        int sel = nch - 1;
+        for (int c = 0; c < nch; ++c) {
+          T v = chunk[c * kS + tid];
+          if (cum + v >= tgt) { sel = c; break; }
+          cum += v;
+        }
+        const int z0 = sel * CH, z1 = min(cnt, z0 + CH);
+        int pick = -1, lastpos = z0;
+        for (int z = z0; z < z1; ++z) {
+          T e = leaf ? score<T, DIM, true>(lrec + (size_t)z * RECL, M, Cq, qs, cmul, circ)
+                     : score<T, DIM, false>(lrec + (size_t)z * RECN, M, Cq, qs, cmul, circ);
+          T p = fast_exp2(e - m);
+          cum += p;
+          if (p > T(0)) lastpos = z;
+          if (cum >= tgt) { pick = z; break; }
+        }
+        if (pick < 0) pick = lastpos;
+        if (active) ind_s[j * kS + tid] = pick;
+      }
+    }
+  }
+
+  if (!active) return;
+  // final point: product of all selected kernels plus one Gaussian draw
+  T M[DIM], C[DIM];
+  combine<T, DIM>(a, pr, ind_s, tid, pr.L, -1, circ, M, C);
+  uint32_t rnd[4];
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) {
+    if ((i & 1) == 0) philox4x32_10(sid, (uint32_t)(i >> 1), pr.stream, 1u, a.k0, a.k1, rnd);
+    double u1 = (double)u01<T>(rnd[0], rnd[1]), u2 = (double)u01<T>(rnd[2], rnd[3]);
+    double r = sqrt(-2.0 * log(u1)), sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    double v = (double)M[i] + sqrt((double)C[i]) * ((i & 1) ? r * sn : r * cs);
+    if (circ >> i & 1) v = wrap_pi(v);
+    pr.out[(size_t)s * DIM + i] = v;
+  }
+  if (pr.labels) {
+    for (int k = 0; k < D; ++k) {
+      const DensMeta& dm = a.metas[pr.dens[k]];
+      pr.labels[(size_t)s * D + k] = a.int_pool[dm.perm_off + ind_s[k * kS + tid]];
+    }
+  }
+}
+
+template <typename T> size_t gibbs_smem_bytes() {
+  return 2 * (size_t)kTileBytesF32 * (sizeof(T) / 4) + sizeof(T) * kNCH * kS + sizeof(int) * CB2_MAX_DENS * kS + 64;
+}
+
+template <typename T, int DIM, uint32_t CIRC>
+int launch_gibbs_inst(cb2_ctx* ctx, int nwork, const GibbsArgs& a) {
+  size_t smem = gibbs_smem_bytes<T>();
+  cudaError_t e = cudaFuncSetAttribute(gibbs_kernel<T, DIM, CIRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "gibbs smem attribute: %s", cudaGetErrorString(e));
+  gibbs_kernel<T, DIM, CIRC><<<nwork, kS, smem, ctx->stream>>>(a);
+  CB2_CHECK_LAUNCH(ctx, "gibbs_kernel");
+  return CB2_OK;
+}
+
+template <typename T>
+int launch_gibbs(cb2_ctx* ctx, int d, uint32_t mask, int nwork, const GibbsArgs& a) {
+  // the common variable types get compile-time circular masks; anything else takes the run-time mask
+  if (d == 1 && mask == 0) return launch_gibbs_inst<T, 1, 0u>(ctx, nwork, a);
+  if (d == 2 && mask == 0) return launch_gibbs_inst<T, 2, 0u>(ctx, nwork, a);            // Point2
+  if (d == 3 && mask == 0) return launch_gibbs_inst<T, 3, 0u>(ctx, nwork, a);            // Point3
+  if (d == 3 && mask == 4u) return launch_gibbs_inst<T, 3, 4u>(ctx, nwork, a);           // Pose2
+  if (d == 6 && mask == 0x38u) return launch_gibbs_inst<T, 6, 0x38u>(ctx, nwork, a);     // Pose3
+  switch (d) {
+    case 1: return launch_gibbs_inst<T, 1, ~0u>(ctx, nwork, a);
+    case 2: return launch_gibbs_inst<T, 2, ~0u>(ctx, nwork, a);
+    case 3: return launch_gibbs_inst<T, 3, ~0u>(ctx, nwork, a);
+    case 4: return launch_gibbs_inst<T, 4, ~0u>(ctx, nwork, a);
+    case 5: return launch_gibbs_inst<T, 5, ~0u>(ctx, nwork, a);
+    case 6: return launch_gibbs_inst<T, 6, ~0u>(ctx, nwork, a);
+  }
+  return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d", d);
+}
+
+struct BatchPlan {
+  std::vector<DensMeta> metas;
+  std::vector<ProdDev> prods;
+  std::vector<Work> work;
+  size_t node_elems = 0, int_elems = 0;
+  int max_nodes = 0, maxP2 = 1;
+};
+
+int validate_and_plan(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d, BatchPlan& pl,
+                      uint32_t* mask_out) {
+  CB2_REQUIRE(ctx, descs && B > 0, "null descriptors or empty batch");
+  if (d < 1 || d > CB2_MAX_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d outside 1..%d", d, CB2_MAX_DIM);
+  uint32_t mask = 0;
+  for (int k = 0; k < d; ++k) if (circular && circular[k]) mask |= 1u << k;
+  *mask_out = mask;
+  const int RECN = recn_of(d), RECL = recl_of(d);
+  for (int b = 0; b < B; ++b) {
+    const cb2_product_desc& ds = descs[b];
+    CB2_REQUIRE(ctx, ds.dens && ds.pts_out, "product %d: null dens / pts_out", b);
+    if (ds.D < 1 || ds.D > CB2_MAX_DENS) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "product %d: D=%d outside 1..%d", b, ds.D, CB2_MAX_DENS);
+    CB2_REQUIRE(ctx, ds.Nout > 0 && ds.niter >= 0 && ds.sample_offset >= 0, "product %d: bad Nout/niter/sample_offset", b);
+    ProdDev pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.D = ds.D; pd.Nout = ds.Nout; pd.sweeps = 1 + ds.niter; pd.stream = ds.stream; pd.sample_offset = ds.sample_offset;
+    int maxN = 0;
+    for (int j = 0; j < ds.D; ++j) {
+      const cb2_density& dn = ds.dens[j];
+      CB2_REQUIRE(ctx, dn.pts && dn.bw && dn.N > 0, "product %d message %d: null pts/bw or N <= 0", b, j);
+      if (dn.N > CB2_MAX_PRODUCT_N) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "product %d message %d: N=%d exceeds %d", b, j, dn.N, CB2_MAX_PRODUCT_N);
+      DensMeta m;
+      memset(&m, 0, sizeof(m));
+      m.N = dn.N; m.depth = ceil_log2(dn.N);
+      m.perm_off = (long long)pl.int_elems;
+      pl.int_elems += (size_t)dn.N;
+      for (int l = 0; l <= m.depth; ++l) {
+        m.rec_off[l] = (long long)pl.node_elems;
+        pl.node_elems += (size_t)level_count(dn.N, m.depth, l) * (l < m.depth ? RECN : RECL);
+        pl.node_elems = (pl.node_elems + 31) / 32 * 32;  // keep every level 128-byte aligned for the bulk copies
+      }
+      int nodes = (1 << m.depth) + dn.N;
+      if (nodes > pl.max_nodes) pl.max_nodes = nodes;
+      int P2 = 1 << m.depth;
+      if (P2 > pl.maxP2) pl.maxP2 = P2;
+      if (dn.N > maxN) maxN = dn.N;
+      pd.dens[j] = (int)pl.metas.size();
+      pl.metas.push_back(m);
+    }
+    int L = 0;
+    while ((2 << L) <= maxN) ++L;
+    pd.L = L + 1;  // floor(log2(maxN)) + 1
+    for (int s0 = 0; s0 < ds.Nout; s0 += kS) pl.work.push_back({b, s0});
+    pl.prods.push_back(pd);
+  }
+  return CB2_OK;
+}
+
+struct DevLayout {
+  DensMeta* metas; ProdDev* prods; Work* work; int* int_pool; void* node_pool; double* stat; size_t stat_stride;
+};
+
+// Core: descriptors hold DEVICE pointers (pts, w, outputs); bw values are read from `bw_host[b][j]` (host copies).
+template <typename T>
+int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const std::vector<std::vector<const double*>>& bw_host,
+                       uint32_t mask, int d, uint64_t seed, BatchPlan& pl, char* base, size_t bytes, size_t* needed,
+                       DevLayout* lay_out) {
+  const int nd = 2 * d + 1;
+  const size_t stat_stride = (size_t)pl.max_nodes * nd;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += cb2_align(n); return o; };
+  size_t o_metas = take(sizeof(DensMeta) * pl.metas.size());
+  size_t o_prods = take(sizeof(ProdDev) * pl.prods.size());
+  size_t o_work = take(sizeof(Work) * pl.work.size());
+  size_t o_int = take(sizeof(int) * pl.int_elems);
+  size_t o_node = take(sizeof(T) * pl.node_elems + 256);
+  size_t o_stat = take(sizeof(double) * stat_stride * pl.metas.size());
+  if (needed) *needed = off + 1024;
+  if (!base) return CB2_OK;
+  if (off > bytes) return cb2_fail(ctx, CB2_ERR_NOMEM, "product scratch too small");
+  DevLayout lay;
+  lay.metas = (DensMeta*)(base + o_metas); lay.prods = (ProdDev*)(base + o_prods); lay.work = (Work*)(base + o_work);
+  lay.int_pool = (int*)(base + o_int); lay.node_pool = base + o_node; lay.stat = (double*)(base + o_stat);
+  lay.stat_stride = stat_stride;
+  size_t mi = 0;
+  for (int b = 0; b < B; ++b) {
+    for (int j = 0; j < descs[b].D; ++j, ++mi) {
+      pl.metas[mi].pts = descs[b].dens[j].pts;
+      pl.metas[mi].w = descs[b].dens[j].w;
+      for (int k = 0; k < d; ++k) {
+        double s = bw_host[b][j][k];
+        if (!(s > 0) || !isfinite(s)) return cb2_fail(ctx, CB2_ERR_INVALID, "product %d message %d: bandwidth[%d] must be positive", b, j, k);
+        pl.metas[mi].bw[k] = s;
+      }
+    }
+    pl.prods[b].out = descs[b].pts_out;
+    pl.prods[b].labels = descs[b].labels_out;
+  }
+  CB2_CUDA(ctx, cudaMemcpyAsync(lay.metas, pl.metas.data(), sizeof(DensMeta) * pl.metas.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CB2_CUDA(ctx, cudaMemcpyAsync(lay.prods, pl.prods.data(), sizeof(ProdDev) * pl.prods.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CB2_CUDA(ctx, cudaMemcpyAsync(lay.work, pl.work.data(), sizeof(Work) * pl.work.size(), cudaMemcpyHostToDevice, ctx->stream));
+
+  CB2_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  size_t tree_smem = (size_t)pl.maxP2 * 13 + 64;
+  cudaError_t e = cudaFuncSetAttribute(tree_build_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem);
+  if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "tree smem attribute (%zu bytes): %s", tree_smem, cudaGetErrorString(e));
+  tree_build_kernel<T><<<(int)pl.metas.size(), kTreeThreads, tree_smem, ctx->stream>>>(lay.metas, d, lay.int_pool, (T*)lay.node_pool,
+                                                                                          lay.stat, stat_stride);
+  CB2_CHECK_LAUNCH(ctx, "tree_build_kernel");
+  CB2_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+  GibbsArgs ga;
+  ga.metas = lay.metas; ga.prods = lay.prods; ga.work = lay.work; ga.int_pool = lay.int_pool; ga.node_pool = lay.node_pool;
+  ga.k0 = (uint32_t)seed; ga.k1 = (uint32_t)(seed >> 32); ga.circ_mask = mask;
+  int rc = launch_gibbs<T>(ctx, d, mask, (int)pl.work.size(), ga);
+  if (rc) return rc;
+  CB2_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (lay_out) *lay_out = lay;
+  return CB2_OK;
+}
+
+void record_product_stages(cb2_ctx* ctx, bool with_bw) {
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->stage_ms["tree"] = ms;
+  if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) ctx->stage_ms["gibbs"] = ms;
+  if (with_bw && cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->stage_ms["bw"] = ms;
+  cudaGetLastError();
+}
+
+// runs tree + gibbs (+ LOO bandwidth of the outputs) with every data pointer on the device
+int product_batch_dev_locked(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d, uint64_t seed,
+                             const std::vector<std::vector<const double*>>* bw_host_in, DevLayout* lay_out) {
+  BatchPlan pl;
+  uint32_t mask = 0;
+  int rc = validate_and_plan(ctx, descs, B, circular, d, pl, &mask);
+  if (rc) return rc;
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  // bandwidths are needed on the host for validation and the per-level record layout: fetch them if they live on the device
+  std::vector<std::vector<const double*>> bw_host;
+  std::vector<double> bw_store;
+  if (bw_host_in) bw_host = *bw_host_in;
+  else {
+    size_t nd = pl.metas.size();
+    bw_store.resize(nd * d);
+    size_t mi = 0;
+    for (int b = 0; b < B; ++b)
+      for (int j = 0; j < descs[b].D; ++j, ++mi)
+        CB2_CUDA(ctx, cudaMemcpyAsync(&bw_store[mi * d], descs[b].dens[j].bw, sizeof(double) * d, cudaMemcpyDeviceToHost, ctx->stream));
+    CB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bw_host.resize(B);
+    mi = 0;
+    for (int b = 0; b < B; ++b)
+      for (int j = 0; j < descs[b].D; ++j, ++mi) bw_host[b].push_back(&bw_store[mi * d]);
+  }
+  // optional LOO bandwidth of the outputs
+  std::vector<const double*> bw_mu;
+  std::vector<int32_t> bw_N;
+  std::vector<int> bw_idx;
+  for (int b = 0; b < B; ++b)
+    if (descs[b].bw_out) {
+      if (descs[b].Nout < 2) return cb2_fail(ctx, CB2_ERR_INVALID, "product %d: bw_out needs Nout >= 2", b);
+      bw_mu.push_back(descs[b].pts_out); bw_N.push_back(descs[b].Nout); bw_idx.push_back(b);
+    }
+  size_t need_prod = 0, need_loo = 0;
+  const bool f64 = ctx->precision == CB2_FP64;
+  rc = f64 ? product_batch_core<double>(ctx, descs, B, bw_host, mask, d, seed, pl, nullptr, 0, &need_prod, nullptr)
+           : product_batch_core<float>(ctx, descs, B, bw_host, mask, d, seed, pl, nullptr, 0, &need_prod, nullptr);
+  if (rc) return rc;
+  if (!bw_mu.empty()) {
+    rc = cb2_bw_loo_dev_core(ctx, bw_mu.data(), bw_N.data(), (int)bw_mu.size(), d, circular, nullptr, nullptr, 0, &need_loo);
+    if (rc) return rc;
+  }
+  size_t bw_out_bytes = cb2_align(sizeof(double) * d * (bw_mu.size() + 1));
+  rc = cb2_arena_reserve(ctx, need_prod + need_loo + bw_out_bytes + 8192);
+  if (rc) return rc;
+  char* base = (char*)cb2_arena_alloc(ctx, need_prod);
+  if (!base) return cb2_fail(ctx, CB2_ERR_NOMEM, "product scratch exhausted");
+  rc = f64 ? product_batch_core<double>(ctx, descs, B, bw_host, mask, d, seed, pl, base, need_prod, nullptr, lay_out)
+           : product_batch_core<float>(ctx, descs, B, bw_host, mask, d, seed, pl, base, need_prod, nullptr, lay_out);
+  if (rc) return rc;
+  if (!bw_mu.empty()) {
+    double* bw_dev = (double*)cb2_arena_alloc(ctx, bw_out_bytes);
+    void* scratch = cb2_arena_alloc(ctx, need_loo);
+    if (!bw_dev || !scratch) return cb2_fail(ctx, CB2_ERR_NOMEM, "bandwidth scratch exhausted");
+    rc = cb2_bw_loo_dev_core(ctx, bw_mu.data(), bw_N.data(), (int)bw_mu.size(), d, circular, bw_dev, scratch, need_loo, nullptr);
+    if (rc) return rc;
+    for (size_t i = 0; i < bw_idx.size(); ++i)
+      CB2_CUDA(ctx, cudaMemcpyAsync(descs[bw_idx[i]].bw_out, bw_dev + i * d, sizeof(double) * d, cudaMemcpyDeviceToDevice, ctx->stream));
+    CB2_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  }
+  ctx->stage_ms.erase("tree"); ctx->stage_ms.erase("gibbs"); ctx->stage_ms.erase("bw");
+  ctx->stage_ms["__pending_bw"] = bw_mu.empty() ? 0.0 : 1.0;
+  return CB2_OK;
+}
+
+}  // namespace
+
+// stage timings are resolved lazily (needs the events to have completed)
+void cb2_resolve_product_stages(cb2_ctx* ctx) {
+  auto it = ctx->stage_ms.find("__pending_bw");
+  if (it == ctx->stage_ms.end()) return;
+  bool with_bw = it->second > 0.5;
+  ctx->stage_ms.erase(it);
+  cudaStreamSynchronize(ctx->stream);
+  record_product_stages(ctx, with_bw);
+}
+
+extern "C" int cb2_product_batch_dev(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d,
+                                     uint64_t seed) {
+  if (!ctx) return CB2_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return product_batch_dev_locked(ctx, descs, B, circular, d, seed, nullptr, nullptr);
+}
+
+// Host-pointer flavour: stage everything into one device block, run, copy results back.
+static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d, uint64_t seed,
+                              cb2_pending* pend) {
+  CB2_REQUIRE(ctx, descs && B > 0, "null descriptors or empty batch");
+  if (d < 1 || d > CB2_MAX_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d outside 1..%d", d, CB2_MAX_DIM);
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t total = 0;
+  for (int b = 0; b < B; ++b) {
+    const cb2_product_desc& ds = descs[b];
+    CB2_REQUIRE(ctx, ds.dens && ds.pts_out, "product %d: null dens / pts_out", b);
+    if (ds.D < 1 || ds.D > CB2_MAX_DENS) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "product %d: D=%d outside 1..%d", b, ds.D, CB2_MAX_DENS);
+    CB2_REQUIRE(ctx, ds.Nout > 0, "product %d: Nout <= 0", b);
+    for (int j = 0; j < ds.D; ++j) {
+      CB2_REQUIRE(ctx, ds.dens[j].pts && ds.dens[j].bw && ds.dens[j].N > 0, "product %d message %d: null pts/bw or N <= 0", b, j);
+      total += cb2_align(sizeof(double) * (size_t)ds.dens[j].N * d);
+      if (ds.dens[j].w) total += cb2_align(sizeof(double) * (size_t)ds.dens[j].N);
+    }
+    total += cb2_align(sizeof(double) * (size_t)ds.Nout * d);
+    if (ds.labels_out) total += cb2_align(sizeof(int32_t) * (size_t)ds.Nout * ds.D);
+    if (ds.bw_out) total += cb2_align(sizeof(double) * d);
+  }
+  void* blk = nullptr;
+  cudaError_t e = cudaMalloc(&blk, total + 256);
+  if (e != cudaSuccess) { cudaGetLastError(); return cb2_fail(ctx, CB2_ERR_NOMEM, "device block of %zu bytes: %s", total, cudaGetErrorString(e)); }
+  char* p = (char*)blk;
+  size_t off = 0;
+  auto take = [&](size_t n) { char* q = p + off; off += cb2_align(n); return q; };
+  std::vector<cb2_product_desc> dd(descs, descs + B);
+  std::vector<std::vector<cb2_density>> ddens(B);
+  std::vector<std::vector<const double*>> bw_host(B);
+  int rc = CB2_OK;
+  cudaEventRecord(ctx->ev[4], ctx->stream);
+  for (int b = 0; b < B && rc == CB2_OK; ++b) {
+    ddens[b].assign(descs[b].dens, descs[b].dens + descs[b].D);
+    for (int j = 0; j < descs[b].D; ++j) {
+      const cb2_density& dn = descs[b].dens[j];
+      double* dp = (double*)take(sizeof(double) * (size_t)dn.N * d);
+      e = cudaMemcpyAsync(dp, dn.pts, sizeof(double) * (size_t)dn.N * d, cudaMemcpyHostToDevice, ctx->stream);
+      ddens[b][j].pts = dp;
+      if (dn.w && e == cudaSuccess) {
+        double* wp = (double*)take(sizeof(double) * (size_t)dn.N);
+        e = cudaMemcpyAsync(wp, dn.w, sizeof(double) * (size_t)dn.N, cudaMemcpyHostToDevice, ctx->stream);
+        ddens[b][j].w = wp;
+      }
+      if (e != cudaSuccess) { rc = cb2_fail(ctx, CB2_ERR_CUDA, "H2D copy: %s", cudaGetErrorString(e)); break; }
+      bw_host[b].push_back(dn.bw);
+    }
+    dd[b].dens = ddens[b].data();
+    dd[b].pts_out = (double*)take(sizeof(double) * (size_t)descs[b].Nout * d);
+    dd[b].labels_out = descs[b].labels_out ? (int32_t*)take(sizeof(int32_t) * (size_t)descs[b].Nout * descs[b].D) : nullptr;
+    dd[b].bw_out = descs[b].bw_out ? (double*)take(sizeof(double) * d) : nullptr;
+  }
+  if (rc == CB2_OK) { cudaEventRecord(ctx->ev[5], ctx->stream); rc = product_batch_dev_locked(ctx, dd.data(), B, circular, d, seed, &bw_host, nullptr); }
+  if (rc != CB2_OK) { cudaStreamSynchronize(ctx->stream); cudaFree(blk); return rc; }
+  cudaEventRecord(ctx->ev[6], ctx->stream);
+  for (int b = 0; b < B; ++b) {
+    e = cudaMemcpyAsync(descs[b].pts_out, dd[b].pts_out, sizeof(double) * (size_t)descs[b].Nout * d, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && descs[b].labels_out)
+      e = cudaMemcpyAsync(descs[b].labels_out, dd[b].labels_out, sizeof(int32_t) * (size_t)descs[b].Nout * descs[b].D, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && descs[b].bw_out)
+      e = cudaMemcpyAsync(descs[b].bw_out, dd[b].bw_out, sizeof(double) * d, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) { cudaStreamSynchronize(ctx->stream); cudaFree(blk); return cb2_fail(ctx, CB2_ERR_CUDA, "D2H copy: %s", cudaGetErrorString(e)); }
+  }
+  cudaEventRecord(ctx->ev[7], ctx->stream);
+  if (pend) {  // asynchronous: hand the block to the ticket
+    pend->dev_block = blk;
+    e = cudaEventCreateWithFlags(&pend->done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(pend->done, ctx->stream);
+    if (e != cudaSuccess) { cudaStreamSynchronize(ctx->stream); cudaFree(blk); pend->dev_block = nullptr; return cb2_fail(ctx, CB2_ERR_CUDA, "ticket event: %s", cudaGetErrorString(e)); }
+    return CB2_OK;
+  }
+  e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(blk);
+  if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "product batch failed: %s", cudaGetErrorString(e));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ctx->stage_ms["h2d"] = ms;
+  if (cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) ctx->stage_ms["d2h"] = ms;
+  cudaGetLastError();
+  return CB2_OK;
+}
+
+extern "C" int cb2_product_batch(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d, uint64_t seed) {
+  if (!ctx) return CB2_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return product_batch_host(ctx, descs, B, circular, d, seed, nullptr);
+}
+
+extern "C" int cb2_product(cb2_ctx* ctx, const cb2_density* dens, int D, const uint8_t* circular, int d, int Nout, int niter,
+                           uint64_t seed, uint32_t stream, int sample_offset, double* pts_out, int32_t* labels_out) {
+  cb2_product_desc ds;
+  memset(&ds, 0, sizeof(ds));
+  ds.dens = dens; ds.D = D; ds.Nout = Nout; ds.niter = niter; ds.stream = stream; ds.sample_offset = sample_offset;
+  ds.pts_out = pts_out; ds.labels_out = labels_out; ds.bw_out = nullptr;
+  return cb2_product_batch(ctx, &ds, 1, circular, d, seed);
+}
+
+extern "C" int cb2_product_batch_submit(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d,
+                                        uint64_t seed, cb2_ticket* ticket) {
+  if (!ctx) return CB2_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CB2_REQUIRE(ctx, ticket, "null ticket");
+  cb2_pending pend;
+  int rc = product_batch_host(ctx, descs, B, circular, d, seed, &pend);
+  if (rc) return rc;
+  *ticket = ctx->next_ticket++;
+  ctx->pending[*ticket] = pend;
+  return CB2_OK;
+}
+
+extern "C" int cb2_wait(cb2_ctx* ctx, cb2_ticket ticket) {
+  if (!ctx) return CB2_ERR_INVALID;
+  cb2_pending pend;
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    auto it = ctx->pending.find(ticket);
+    if (it == ctx->pending.end()) return cb2_fail(ctx, CB2_ERR_INVALID, "unknown ticket %lld", (long long)ticket);
+    pend = it->second;
+    ctx->pending.erase(it);
+  }
+  cudaError_t e = cudaEventSynchronize(pend.done);
+  cudaEventDestroy(pend.done);
+  if (pend.dev_block) cudaFree(pend.dev_block);
+  if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "async product batch failed: %s", cudaGetErrorString(e));
+  return CB2_OK;
+}
+
+extern "C" int cb2_tree_debug(cb2_ctx* ctx, const cb2_density* den, int d, int level, int32_t* depth_out, int32_t* count_out,
+                              int32_t* perm, double* mean, double* var, double* wt) {
+  if (!ctx) return CB2_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CB2_REQUIRE(ctx, den && den->pts && den->bw && den->N > 0, "null density");
+  if (d < 1 || d > CB2_MAX_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d", d);
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int N = den->N, depth = ceil_log2(N);
+  if (depth_out) *depth_out = depth;
+  CB2_REQUIRE(ctx, level >= 0 && level <= depth, "level %d outside 0..%d", level, depth);
+  const int cnt = level_count(N, depth, level);
+  if (count_out) *count_out = cnt;
+  // run a one-message, one-sample product to build the tree, then read the statistics scratch back
+  std::vector<double> dummy_out(d);
+  void* blk = nullptr;
+  size_t bytes = cb2_align(sizeof(double) * (size_t)N * d) + cb2_align(sizeof(double) * N) + cb2_align(sizeof(double) * d) +
+                 cb2_align(sizeof(double) * (size_t)cnt * (2 * d + 1)) + cb2_align(sizeof(int) * N) + 1024;
+  cudaError_t e = cudaMalloc(&blk, bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); return cb2_fail(ctx, CB2_ERR_NOMEM, "tree debug block"); }
+  char* p = (char*)blk;
+  size_t off = 0;
+  auto take = [&](size_t n) { char* q = p + off; off += cb2_align(n); return q; };
+  double* pts_dev = (double*)take(sizeof(double) * (size_t)N * d);
+  double* w_dev = (double*)take(sizeof(double) * N);
+  double* out_dev = (double*)take(sizeof(double) * d);
+  double* mean_dev = (double*)take(sizeof(double) * (size_t)cnt * (2 * d + 1));
+  double* var_dev = mean_dev + (size_t)cnt * d;
+  double* wt_dev = var_dev + (size_t)cnt * d;
+  cudaMemcpyAsync(pts_dev, den->pts, sizeof(double) * (size_t)N * d, cudaMemcpyHostToDevice, ctx->stream);
+  if (den->w) cudaMemcpyAsync(w_dev, den->w, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream);
+  cb2_density dd = {N, pts_dev, den->bw, den->w ? w_dev : nullptr};
+  cb2_product_desc ds;
+  memset(&ds, 0, sizeof(ds));
+  ds.dens = &dd; ds.D = 1; ds.Nout = 1; ds.niter = 0; ds.pts_out = out_dev;
+  std::vector<std::vector<const double*>> bw_host(1);
+  bw_host[0].push_back(den->bw);
+  DevLayout lay;
+  int rc = product_batch_dev_locked(ctx, &ds, 1, nullptr, d, 0, &bw_host, &lay);
+  if (rc == CB2_OK) {
+    int node0 = level < depth ? ((1 << level) - 1) : ((1 << depth) - 1);
+    tree_debug_copy_kernel<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(lay.stat, d, node0, cnt, mean_dev, var_dev, wt_dev);
+    ctx->launches++;
+    if (mean) cudaMemcpyAsync(mean, mean_dev, sizeof(double) * (size_t)cnt * d, cudaMemcpyDeviceToHost, ctx->stream);
+    if (var) cudaMemcpyAsync(var, var_dev, sizeof(double) * (size_t)cnt * d, cudaMemcpyDeviceToHost, ctx->stream);
+    if (wt) cudaMemcpyAsync(wt, wt_dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream);
+    if (perm) cudaMemcpyAsync(perm, lay.int_pool, sizeof(int) * N, cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = cb2_fail(ctx, CB2_ERR_CUDA, "tree debug: %s", cudaGetErrorString(e));
+  } else {
+    cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(blk);
+  return rc;
+}

@@ -1,0 +1,94 @@
+"""ScatterAlignPose2 / ScatterAlignPose3 factor plugin, mirroring the reference's IIF factor interface
+(struct R:ext/factors/ScatterAlignPose.jl:50-97; preambleCache R:ext/Images/ScatterAlignPose2.jl:115-152;
+getSample :155-187).  The alignment itself (fresh samples from both clouds, mmd cost, BFGS) runs in
+libcaesar_b200.so via cb2_scatter_align; K particles of the solver are aligned in one batched call."""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi
+from ._capi import f64, ptr
+
+
+@dataclass
+class ScatterAlign:
+    cloud1: object
+    cloud2: object
+    dim: int = 2
+    gridscale: float = 1.0
+    sample_count: int = 500
+    bw: float = 1.0
+    useStashing: bool = False
+    dataEntry_cloud1: str = ""
+    dataEntry_cloud2: str = ""
+    dataStoreHint: str = ""
+
+
+class _ScatterAlignPose:
+    DIM = 2
+
+    def __init__(self, cloud1=None, cloud2=None, sample_count=75, bw=5e-5, rescale=1.0, useStashing=False,
+                 dataEntry_cloud1="", dataEntry_cloud2="", dataStoreHint=""):
+        # keyword defaults as the reference constructors (R:ext/Images/ScatterAlignPose2.jl:36-46)
+        if cloud1 is None or cloud2 is None:
+            raise ValueError("cloud1 and cloud2 are required")
+        if cloud1.d != self.DIM or cloud2.d != self.DIM:
+            raise ValueError(f"{type(self).__name__} needs clouds over R^{self.DIM}")
+        self.align = ScatterAlign(cloud1, cloud2, self.DIM, float(rescale), int(sample_count), float(bw), useStashing,
+                                  str(dataEntry_cloud1), str(dataEntry_cloud2), str(dataStoreHint))
+
+    @property
+    def ncoord(self):
+        return 3 if self.DIM == 2 else 6
+
+
+class ScatterAlignPose2(_ScatterAlignPose):
+    DIM = 2
+
+
+class ScatterAlignPose3(_ScatterAlignPose):
+    DIM = 3
+
+
+@dataclass
+class CalcFactor:
+    """The slice of IIF.CalcFactor the factor uses: .factor, .cache, ._allowThreads."""
+    factor: object
+    cache: dict = field(default_factory=dict)
+    _allowThreads: bool = True
+
+
+def preambleCache(dfg, vars, fnc):
+    """Runs once at addFactor!.  Mirrors the named tuple (;M,e0,smps1,smps2,bw,score) of the reference; the
+    sample buffers live on the device inside cb2_scatter_align, so only sizes are recorded here."""
+    if fnc.align.sample_count < 0:
+        raise NotImplementedError("ICP branch (sample_count < 0) is outside the hot path (SURVEY sec. 8f N3)")
+    M = "SpecialEuclidean(2)" if fnc.DIM == 2 else "SpecialEuclidean(3)"
+    return dict(M=M, e0=np.zeros(fnc.ncoord), smps1=None, smps2=None, bw=np.array([fnc.align.bw]), score=[0.0])
+
+
+def getSample(cf, K=1, seed=0, x0=None, max_iter=200, g_tol=1e-8, ctx=None, return_info=False):
+    """getSample(cf::CalcFactor{ScatterAlignPose2/3}): draws sample_count fresh points from each cloud and
+    minimises mmd(smps1, T(c)^-1 smps2) over the SE(2)/SE(3) coordinates c, from the reference's random start
+    [5 randn(ntr); 0.1 randn(nrot)] (:182).  Returns the K x ncoord tangent coordinates (hat(M, e0, c) in the
+    reference is a re-labelling of the same numbers) and stores the last score in cf.cache['score']."""
+    from . import context
+    ctx = ctx or context()
+    fnc = cf.factor
+    al = fnc.align
+    nc, dim = fnc.ncoord, fnc.DIM
+    if x0 is None:
+        rng = np.random.default_rng(seed)
+        x0 = np.concatenate([5.0 * rng.standard_normal((K, dim)), 0.1 * rng.standard_normal((K, nc - dim))], axis=1)
+    x0 = f64(np.atleast_2d(x0))
+    K = x0.shape[0]
+    coords, score = np.zeros((K, nc)), np.zeros(K)
+    iters = np.zeros(K, dtype=np.int32)
+    d1, d2 = al.cloud1._density(), al.cloud2._density()
+    ctx.check(_capi.lib().cb2_scatter_align(ctx._h, C.byref(d1), C.byref(d2), dim, al.sample_count, al.bw, ptr(x0), K,
+                                            int(seed), int(max_iter), float(g_tol), ptr(coords), ptr(score), ptr(iters)))
+    cf.cache.setdefault("score", [0.0])[0] = float(score[-1])
+    if return_info:
+        return coords, score, iters
+    return coords

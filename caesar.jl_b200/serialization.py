@@ -1,0 +1,33 @@
+"""PackedManifoldKernelDensity wire format (the JSON the reference stores for beliefs and stashed clouds:
+fixtures R:test/ICRA2022_tests/test_data/tut3/*.json; writer R:test/ICRA2022_tests/insufficient_data.jl:34-44)."""
+import json
+
+import numpy as np
+
+
+def packDistribution(mkd, varType=None):
+    vt = varType or (mkd.manifold if isinstance(mkd.manifold, str) else "ContinuousEuclid")
+    if "." not in vt:
+        vt = "RoME." + vt
+    return {
+        "_type": "IncrementalInference.PackedManifoldKernelDensity",
+        "varType": vt,
+        "pts": [list(map(float, p)) for p in mkd.pts],
+        "bw": list(map(float, mkd.bw)),
+        "partial": list(mkd.partial) if mkd.partial is not None else list(range(1, mkd.d + 1)),
+        "infoPerCoord": list(map(float, mkd.infoPerCoord)),
+    }
+
+
+def unpackDistribution(packed):
+    from . import ManifoldKernelDensity
+    if isinstance(packed, (str, bytes)):
+        packed = json.loads(packed)
+    if packed.get("_type") != "IncrementalInference.PackedManifoldKernelDensity":
+        raise ValueError(f"unsupported packed type {packed.get('_type')!r}")
+    vt = packed["varType"].split(".")[-1]
+    pts = np.asarray(packed["pts"], dtype=np.float64)
+    partial = packed.get("partial")
+    if partial is not None and list(partial) == list(range(1, pts.shape[1] + 1)):
+        partial = None
+    return ManifoldKernelDensity(vt, pts, packed["bw"], None, partial, packed.get("infoPerCoord"))

@@ -1,0 +1,308 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): deterministic kernels 1e-5 relative in FP32 mode, 1e-12 in FP64 mode;
+stochastic products: same Philox stream -> (near-)identical label draws in FP64 mode, distribution-level
+agreement (moments + fixed-seed MMD two-sample statistic) in FP32 mode."""
+import numpy as np
+import pytest
+
+import oracle
+from __graft_entry__ import build, load_package
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {"fp32": 1e-5, "fp64": 1e-12}
+
+
+@pytest.fixture(scope="module")
+def cb():
+    build()
+    return load_package()
+
+
+@pytest.fixture(scope="module", params=["fp32", "fp64"])
+def ctx(request, cb):
+    return cb.Context(0, request.param)
+
+
+@pytest.fixture(scope="module")
+def ctx64(cb):
+    return cb.Context(0, "fp64")
+
+
+@pytest.fixture(scope="module")
+def ctx32(cb):
+    return cb.Context(0, "fp32")
+
+
+# ------------------------------------------------------------------------------------------------ mmd
+@pytest.mark.parametrize("d,N,M", [(1, 1, 1), (2, 100, 100), (3, 150, 77), (3, 1025, 4097), (6, 300, 513), (4, 64, 65)])
+def test_mmd_matches_oracle(cb, ctx, d, N, M):
+    rng = np.random.default_rng(d * 1000 + N)
+    a, b = rng.normal(size=(N, d)), rng.normal(size=(M, d)) * 1.2 + 0.4
+    for bw in (0.05, 1.0):
+        want, sums = oracle.mmd(a, b, bw, return_sums=True)
+        got_sums = cb.mmd_sums(a, b, bw, ctx=ctx)
+        assert np.allclose(got_sums, sums, rtol=RTOL[ctx.precision], atol=0)
+        got = cb.mmd(a, b, bw, ctx=ctx)
+        # the three terms nearly cancel: bound the error by the size of the terms
+        scale = sums[0] / N**2 + 2 * sums[1] / (N * M) + sums[2] / M**2
+        assert abs(got - want) <= RTOL[ctx.precision] * scale
+
+
+def test_mmd_far_from_origin_and_fixtures(cb, ctx, tut3):
+    """Clouds 1e4 m from the origin (FP32 would lose the differences without centring) and the reference's beliefs."""
+    rng = np.random.default_rng(3)
+    a, b = rng.normal(size=(400, 2)) + 1e4, rng.normal(size=(300, 2)) + 1e4 + 0.5
+    want, sums = oracle.mmd(a, b, 0.7, return_sums=True)
+    assert np.allclose(cb.mmd_sums(a, b, 0.7, ctx=ctx), sums, rtol=RTOL[ctx.precision])
+    for x, y in (("l3_2", "l3_3"), ("x1_2", "x1_3"), ("l1_1", "l2_1")):
+        A, B = cb.unpackDistribution(cb.packDistribution(cb.MKD("Point2", *tut3[x]))), cb.MKD("Point2", *tut3[y])
+        want = oracle.mmd(tut3[x][0], tut3[y][0], 0.001)
+        assert abs(cb.mmd(A, B, ctx=ctx) - want) <= RTOL[ctx.precision] * 4
+    # reference tolerances (insufficient_data.jl:143-248) hold on the device path too
+    assert cb.mmd(cb.MKD("Point2", *tut3["l1_1"]), cb.MKD("Point2", *tut3["l1_2"]), ctx=ctx) < 0.01
+    assert cb.isapprox(cb.MKD("Point2", *tut3["x0_1"]), cb.MKD("Point2", *tut3["x0_2"]), ctx=ctx)
+
+
+def test_mmd_row_shards_add_up(cb, ctx):
+    rng = np.random.default_rng(5)
+    a, b = rng.normal(size=(3000, 3)), rng.normal(size=(2500, 3))
+    full = cb.mmd_sums(a, b, 0.3, ctx=ctx)
+    parts = sum(cb.mmd_sums(a, b, 0.3, (r0, r1), (q0, q1), ctx=ctx)
+                for (r0, r1), (q0, q1) in zip([(0, 1000), (1000, 1001), (1001, 3000)], [(0, 7), (7, 2000), (2000, 2500)]))
+    assert np.allclose(parts, full, rtol=1e-12 if ctx.precision == "fp64" else 1e-6)
+    assert np.allclose(parts, oracle.mmd(a, b, 0.3, return_sums=True)[1], rtol=RTOL[ctx.precision])
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("backward", [True, False])
+def test_mmd_se_batch_value_and_gradient(cb, ctx, dim, backward):
+    rng = np.random.default_rng(dim + 10 * backward)
+    nc = 3 if dim == 2 else 6
+    a = rng.normal(size=(700, dim)) * 2 + 5.0
+    b = rng.normal(size=(650, dim)) * 2 + 4.0
+    coords = rng.normal(size=(13, nc)) * np.r_[np.ones(dim), 0.3 * np.ones(nc - dim)]
+    vals, grads = cb.mmd_se_batch(a, b, 0.4, coords, backward=backward, ctx=ctx)
+    ovals, ograds = oracle.mmd_se_batch(a, b, 0.4, coords, backward=backward)
+    tol = 2e-5 if ctx.precision == "fp32" else 1e-11
+    assert np.allclose(vals, ovals, rtol=0, atol=tol * 2.0)
+    assert np.allclose(grads, ograds, rtol=0, atol=tol * np.abs(ograds).max() * 20 + 1e-15)
+
+
+# ------------------------------------------------------------------------------------------------ KDE evaluate / bandwidth / sample
+@pytest.mark.parametrize("d,N,Q", [(1, 10, 5), (2, 100, 333), (3, 5000, 1100), (6, 777, 64)])
+def test_kde_eval_matches_oracle(cb, ctx, d, N, Q):
+    rng = np.random.default_rng(N)
+    mu = rng.normal(size=(N, d)) * 3 + 50.0
+    sig = rng.uniform(0.2, 1.5, size=d)
+    q = rng.normal(size=(Q, d)) * 3 + 50.0
+    w = rng.uniform(0.1, 1, size=N)
+    topo = [0] * d
+    for weights in (None, w):
+        m = cb.MKD(topo, mu, sig, weights)
+        want = oracle.kde_eval(mu, sig, q, weights)
+        got = m(q, ctx=ctx)
+        assert np.allclose(got, want, rtol=RTOL[ctx.precision] * 3, atol=1e-300)
+        gotl = m(q, logp=True, ctx=ctx)
+        assert np.allclose(gotl, oracle.kde_eval(mu, sig, q, weights, logp=True), rtol=0, atol=RTOL[ctx.precision] * 30)
+
+
+def test_bandwidth_matches_oracle_and_upstream_fixtures(cb, ctx, tut3):
+    names = sorted(tut3)[::4]
+    got = cb.kde_bandwidth_batch([tut3[n][0] for n in names], "Point2", ctx=ctx)
+    for n, g in zip(names, got):
+        want = oracle.kde_bw_loo(tut3[n][0])
+        # FP64 follows the oracle's golden-section path exactly; FP32 may leave it near convergence (tol 1e-2)
+        assert np.allclose(g, want, rtol=1e-6 if ctx.precision == "fp64" else 2e-2), (n, g, want)
+        assert np.abs(g / tut3[n][1] - 1).max() < (1e-2 if ctx.precision == "fp64" else 3e-2)  # upstream's own output
+    rng = np.random.default_rng(1)
+    x = np.c_[rng.normal(size=3000), np.angle(np.exp(1j * (3.0 + 0.4 * rng.normal(size=3000))))]
+    got = cb.kde_bandwidth(x, (0, 1), ctx=ctx)
+    want = oracle.kde_bw_loo(x, circular=[0, 1])
+    assert np.allclose(got, want, rtol=1e-6 if ctx.precision == "fp64" else 2e-2)
+    m = cb.manikde("Point2", tut3["l2_3"][0], ctx=ctx)
+    assert np.allclose(m.bw, got if False else cb.kde_bandwidth(tut3["l2_3"][0], ctx=ctx))
+
+
+def test_sample_matches_oracle_stream(cb, ctx):
+    rng = np.random.default_rng(2)
+    mu, sig = rng.normal(size=(200, 3)) * [5, 5, 1], np.array([0.3, 0.2, 0.4])
+    ub = 53 if ctx.precision == "fp64" else 24
+    for w in (None, rng.uniform(0.1, 1, size=200)):
+        m = cb.MKD("Pose2", mu, sig, w)
+        got, = cb.sample(m, 5000, seed=77, stream=3, ctx=ctx)
+        want = oracle.kde_sample(mu, sig, 5000, seed=77, stream=3, w=w, circular=[0, 0, 1], ubits=ub)
+        assert np.allclose(got, want, atol=1e-9)
+    assert np.abs(got[:, 2]).max() <= np.pi + 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ products
+@pytest.mark.parametrize("N", [1, 2, 3, 37, 64, 100, 1000])
+def test_device_tree_equals_oracle_tree(cb, ctx, N):
+    rng = np.random.default_rng(N)
+    pts = rng.normal(size=(N, 3)) * [4, 1, 0.3] + [100, 0, 0]
+    bw = np.array([0.2, 0.1, 0.05])
+    w = rng.uniform(0.5, 1.5, size=N) if N % 2 else None
+    depth, perm, levels = cb.tree_levels(pts, bw, w, ctx=ctx)
+    t = oracle.Tree(pts, bw, w)
+    assert depth == t.depth and np.array_equal(perm, t.perm)
+    for l in range(depth + 1):
+        assert levels[l][0].shape[0] == t.cnt[l]
+        assert np.allclose(levels[l][0], t.mean[l], rtol=1e-12, atol=1e-12)
+        assert np.allclose(levels[l][1], t.var[l], rtol=1e-9, atol=1e-14)
+        assert np.allclose(levels[l][2], t.wt[l], rtol=1e-12)
+
+
+def _messages(rng, D, N, d, spread=1.0):
+    dens = []
+    for j in range(D):
+        c = rng.normal(size=d) * 0.5 * spread
+        pts = c + rng.normal(size=(N + 7 * j, d)) * rng.uniform(0.5, 1.5, size=d) * spread
+        dens.append((pts, 1.06 * pts.std(0) * len(pts) ** -0.2))
+    return dens
+
+
+@pytest.mark.parametrize("D,N,d,circ", [(2, 100, 2, (0, 0)), (3, 100, 3, (0, 0, 1)), (4, 257, 6, (0, 0, 0, 1, 1, 1)),
+                                        (2, 64, 1, (0,)), (8, 128, 3, (0, 0, 0)), (3, 50, 4, (0, 1, 0, 1))])
+def test_product_fp64_reproduces_oracle_chains(cb, ctx64, D, N, d, circ):
+    """Same tree, same Philox counters, FP64 arithmetic -> the device Gibbs chains must select the same labels as the
+    oracle's (a chunked vs sequential cumulative sum can flip a draw only at the 1e-15 level)."""
+    rng = np.random.default_rng(D * 100 + N)
+    dens = _messages(rng, D, N, d, spread=0.6 if any(circ) else 1.0)
+    Nout = 300
+    pts, lab = cb.product_points(dens, circ, Nout, seed=5, stream=2, ctx=ctx64)
+    opts, olab = oracle.product(dens, Nout, seed=5, circular=list(circ), stream=2, ubits=53)
+    same = (lab == olab).all(axis=1)
+    assert same.mean() >= 0.99, same.mean()
+    assert np.allclose(pts[same], opts[same], rtol=1e-9, atol=1e-9)
+    for j in range(D):
+        assert lab[:, j].min() >= 0 and lab[:, j].max() < len(dens[j][0])
+
+
+def two_sample_mmd(x, y, bw):
+    return oracle.mmd(x, y, bw)
+
+
+@pytest.mark.parametrize("D,N,d,circ", [(3, 100, 3, (0, 0, 1)), (4, 300, 6, (0, 0, 0, 1, 1, 1)), (2, 1000, 2, (0, 0))])
+def test_product_fp32_matches_oracle_in_distribution(cb, ctx32, D, N, d, circ):
+    rng = np.random.default_rng(D + N)
+    dens = _messages(rng, D, N, d, spread=0.6)
+    Nout = 2000
+    pts, lab = cb.product_points(dens, circ, Nout, seed=11, ctx=ctx32)
+    opts, olab = oracle.product(dens, Nout, seed=11, circular=list(circ), ubits=24)
+    # most chains coincide even in FP32 (same uniforms), the rest are equally valid draws
+    assert (lab == olab).all(axis=1).mean() > 0.9
+    sd = opts.std(0)
+    assert np.allclose(pts.mean(0), opts.mean(0), atol=0.1 * sd.max())
+    assert np.allclose(np.cov(pts.T).reshape(d, d), np.cov(opts.T).reshape(d, d), atol=0.15 * (sd.max() ** 2))
+    # fixed-seed two-sample test: MMD^2 between device and oracle sets vs the spread between two oracle sets
+    opts2, _ = oracle.product(dens, Nout, seed=12, circular=list(circ), ubits=24)
+    bwk = 0.5 / (sd**2).sum()
+    assert two_sample_mmd(pts, opts, bwk) <= two_sample_mmd(opts2, opts, bwk) + 1e-3
+
+
+def test_product_batch_is_independent_of_batching_and_sharding(cb, ctx):
+    rng = np.random.default_rng(9)
+    groups = [[cb.MKD("Pose2", *x) for x in _messages(rng, D, 90 + 10 * D, 3, 0.6)] for D in (2, 3, 4, 2)]
+    batch = cb.manifoldProducts(groups, N=128, seed=3, streams=[4, 5, 6, 7], return_labels=True, bw=None, ctx=ctx)
+    for b, g in enumerate(groups):
+        solo = cb.manifoldProducts([g], N=128, seed=3, streams=[4 + b], return_labels=True, bw=None, ctx=ctx)[0]
+        assert np.array_equal(batch[b][1], solo[1]) and np.array_equal(batch[b][0].pts, solo[0].pts)
+        # output-sample sharding: samples [64, 128) computed alone equal the tail of the full product
+        tail = cb.manifoldProducts([g], N=64, seed=3, streams=[4 + b], sample_offsets=[64], return_labels=True, bw=None, ctx=ctx)[0]
+        assert np.array_equal(tail[1], solo[1][64:]) and np.array_equal(tail[0].pts, solo[0].pts[64:])
+
+
+def test_manifold_product_api_behaviour(cb, ctx, tut3):
+    a, b, c = (cb.MKD("Point2", *tut3[k]) for k in ("l3_2", "l3_3", "l3_4"))
+    p = cb.manifoldProduct([a, b, c], seed=1, ctx=ctx)
+    assert p.N == 100 and p.d == 2 and np.isfinite(p.pts).all() and (p.bw > 0).all()
+    want_bw = oracle.kde_bw_loo(p.pts)
+    assert np.allclose(p.bw, want_bw, rtol=1e-6 if ctx.precision == "fp64" else 2e-2)  # fresh LOO bandwidth on the result
+    assert cb.manifoldProduct([a], ctx=ctx) is a                                        # single input is returned unchanged
+    p2 = cb.manifoldProduct([a, b], N=250, seed=1, ctx=ctx)
+    assert p2.N == 250
+    # the ZMQ multiplyDistributions example (ext/services/additional.jl:34): two 10-point 1-D densities
+    x1 = np.array([-0.8272759752535751, 1.90340735325013, 0.5617238720356695, -1.2610130840544629, -0.5196580171571705,
+                   0.47808234574398156, -0.5034354386657888, -0.1289061606999511, -0.6283440136328498, -0.04520468574277743])
+    x2 = np.array([0.6986754683541115, 0.4206784705438769, -0.01798641761511103, 0.2862258908507545, 0.5021835960347083,
+                   -1.4424531814460273, 0.7667313775874391, 0.13048774810077268, -0.004778323705883176, -0.6408606329686699])
+    f1, f2 = cb.manikde("ContinuousScalar", x1[:, None], ctx=ctx), cb.manikde("ContinuousScalar", x2[:, None], ctx=ctx)
+    pq = cb.manifoldProduct([f1, f2], N=2000, seed=4, ctx=ctx)
+    o, _ = oracle.product([(f1.pts, f1.bw), (f2.pts, f2.bw)], 2000, seed=4, ubits=53 if ctx.precision == "fp64" else 24)
+    assert abs(pq.pts.mean() - o.mean()) < 0.05 and abs(pq.pts.std() - o.std()) < 0.05
+
+
+def test_product_far_apart_messages_do_not_underflow(cb, ctx):
+    """Upstream has no max-subtraction and can underflow; the device path must stay finite."""
+    rng = np.random.default_rng(4)
+    dens = [(rng.normal(size=(80, 2)) * 0.1, np.array([0.02, 0.02])), (rng.normal(size=(80, 2)) * 0.1 + 40.0, np.array([0.02, 0.02]))]
+    pts, lab = cb.product_points(dens, (0, 0), 200, seed=1, ctx=ctx)
+    assert np.isfinite(pts).all() and np.abs(pts.mean(0) - 20.0).max() < 1.0
+
+
+def test_full_size_product_chains_match_oracle_subset(cb, ctx64):
+    """C5 shape (D=8 messages x N=4096 kernels, d=6, 3 circular): the oracle re-runs a slice of the chains."""
+    rng = np.random.default_rng(1000)
+    circ = (0, 0, 0, 1, 1, 1)
+    truth = np.r_[rng.normal(size=3) * 2, rng.uniform(-1, 1, size=3)]
+    dens = []
+    for j in range(8):
+        off = np.r_[rng.normal(size=3) * 0.3, rng.normal(size=3) * 0.1]
+        comp = rng.uniform(size=4096) < 0.5
+        pts = truth + off + np.where(comp[:, None], 0.4, -0.4) * np.r_[1, 0, 0, 0, 0, 0] + rng.normal(size=(4096, 6)) * np.r_[0.5, 0.5, 0.5, 0.15, 0.15, 0.15]
+        dens.append((pts, 1.06 * pts.std(0) * 4096 ** -0.2))
+    pts, lab = cb.product_points(dens, circ, 4096, seed=21, stream=9, ctx=ctx64)
+    assert np.isfinite(pts).all() and np.abs(pts[:, 3:]).max() <= np.pi + 1e-12
+    assert lab.min() >= 0 and lab.max() < 4096
+    opts, olab = oracle.product(dens, 96, seed=21, circular=list(circ), stream=9, ubits=53, sample_offset=2000)
+    same = (lab[2000:2096] == olab).all(axis=1)
+    assert same.mean() >= 0.97
+    assert np.allclose(pts[2000:2096][same], opts[same], atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------------ ScatterAlign
+def _blobs(rng, n_per=50):
+    c = np.array([[3.0, 0], [8.0, 0], [0, 5.0]])
+    return np.concatenate([ci + 0.1 * rng.normal(size=(n_per, 2)) for ci in c])
+
+
+def test_scatter_align_pose2_recovers_transform(cb, ctx):
+    """test/testScatterAlignPose2.jl:171-199: 3-blob clouds, true qTp offset [2, 0, pi/6]; the reference asserts
+    recovery within 1.5 m / 0.2 rad (:68-69)."""
+    rng = np.random.default_rng(0)
+    p1 = _blobs(rng)
+    p2 = _blobs(rng)
+    true = np.array([2.0, 0.0, np.pi / 6])
+    # cloud2 = independent redraw of the scene mapped by qTp (testScatterAlignPose2.jl:180-186): q = T(true) p
+    q2 = oracle.transform_points(2, true, p2, backward=False)
+    c1, c2 = cb.manikde("Point2", p1, ctx=ctx), cb.manikde("Point2", q2, ctx=ctx)
+    sap = cb.ScatterAlignPose2(cloud1=c1, cloud2=c2, sample_count=100, bw=1.0)
+    cf = cb.CalcFactor(sap, cb.preambleCache(None, [], sap))
+    x0 = np.tile(true, (16, 1)) + np.c_[0.5 * rng.normal(size=(16, 2)), 0.1 * rng.normal(size=16)]
+    coords, score, iters = cb.getSample(cf, x0=x0, seed=5, ctx=ctx, return_info=True)
+    # cost = mmd(smps1, T(c)^-1 smps2) is minimal at c = true
+    assert np.abs(coords[:, :2] - true[:2]).max() < 1.5 and np.abs(coords[:, 2] - true[2]).max() < 0.2
+    assert (score < 0.5).all() and (iters > 0).all() and cf.cache["score"][0] == score[-1]
+    # the optimiser's final cost is the device mmd at the optimum of its own sample sets: never above the start cost
+    start = cb.getSample(cf, x0=x0, seed=5, max_iter=1, ctx=ctx, return_info=True)[1]
+    assert (score <= start + 1e-12).all()
+
+
+# ------------------------------------------------------------------------------------------------ error behaviour
+def test_errors_are_codes_not_crashes(cb, ctx):
+    with pytest.raises(cb.CB2Error) as e:
+        cb.mmd(np.zeros((3, 9)), np.zeros((3, 9)), 1.0, ctx=ctx)
+    assert e.value.code == -5
+    with pytest.raises(cb.CB2Error) as e:
+        cb.mmd(np.zeros((3, 2)), np.zeros((3, 2)), -1.0, ctx=ctx)
+    assert e.value.code == -1 and "bw" in str(e.value)
+    with pytest.raises(cb.CB2Error) as e:
+        cb.product_points([(np.zeros((20000, 2)), np.ones(2))] * 2, (0, 0), 10, ctx=ctx)
+    assert e.value.code == -5
+    with pytest.raises(cb.CB2Error) as e:
+        cb.product_points([(np.zeros((10, 2)), np.zeros(2))] * 2, (0, 0), 10, ctx=ctx)
+    assert e.value.code == -1 and "bandwidth" in str(e.value)
+    # the context is still usable afterwards
+    assert np.isfinite(cb.mmd(np.zeros((3, 2)), np.ones((3, 2)), 1.0, ctx=ctx))
