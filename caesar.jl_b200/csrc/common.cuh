@@ -92,11 +92,11 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// uniform in (0,1): float path keeps 24 bits (exactly representable, shared with the oracle's ubits=24),
+// uniform in (0,1): float path keeps 23 bits + 1/2 (exactly representable in FP32; the oracle's ubits=24 mode),
 // double path keeps 53 bits (oracle's ubits=53)
 template <typename T> __device__ __forceinline__ T u01(uint32_t x0, uint32_t x1);
 template <> __device__ __forceinline__ float u01<float>(uint32_t x0, uint32_t) {
-  return ((float)(x0 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return ((float)(x0 >> 9) + 0.5f) * (1.0f / 8388608.0f);  // 23 bits + 1/2: exact in FP32
 }
 template <> __device__ __forceinline__ double u01<double>(uint32_t x0, uint32_t x1) {
   uint64_t v = (((uint64_t)x0 << 32) | x1) >> 11;

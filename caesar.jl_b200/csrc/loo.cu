@@ -123,7 +123,8 @@ loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict
     // the diagonal (j == i) only meets this sub-tile if it overlaps the CTA's rows
     const bool has_diag = cs < rbase + kThreads * kRI && cs + kCT > rbase;
     if (has_diag || pr.circular) {
-      for (int j = 0; j < kCT; ++j) {
+      const int jn = min(kCT, pr.N - cs);  // no padding columns here: the wrap would fold the sentinel back
+      for (int j = 0; j < jn; ++j) {
         T q = sx[j];
 #pragma unroll
         for (int r = 0; r < kRI; ++r) {

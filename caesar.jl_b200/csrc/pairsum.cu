@@ -543,7 +543,7 @@ static int upload_block(cb2_ctx* ctx, const std::vector<const double*>& src, con
   dev.resize(src.size());
   for (size_t i = 0; i < src.size(); ++i) {
     dev[i] = (double*)((char*)p + off);
-    if (count[i]) {
+    if (count[i] && src[i]) {
       e = cudaMemcpyAsync(dev[i], src[i], count[i] * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
       if (e != cudaSuccess) { cudaFree(p); *block = nullptr; return cb2_fail(ctx, CB2_ERR_CUDA, "H2D copy: %s", cudaGetErrorString(e)); }
     }

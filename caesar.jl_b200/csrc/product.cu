@@ -146,7 +146,7 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
         for (int i = tid; i < P2; i += nthr) {
           int ixj = i ^ j;
           if (ixj > i) {
-            bool up = (i & k) == 0;
+            bool up = (i & k) == 0 || k == kmax;  // the last merge leaves every block ascending
             unsigned long long oa = ord[i], ob = ord[ixj];
             uint32_t ta = tag[i], tb = tag[ixj];
             bool lt = key_less(ob, tb, oa, ta);  // b < a

@@ -43,7 +43,7 @@ void cb2o_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[
 }
 
 static double u_from_words(uint32_t x0, uint32_t x1, int ubits) {
-  if (ubits == 24) return ((double)(x0 >> 8) + 0.5) * (1.0 / 16777216.0);
+  if (ubits == 24) return ((double)(x0 >> 9) + 0.5) * (1.0 / 8388608.0); /* FP32-exact: 23 bits + 1/2 */
   uint64_t v = (((uint64_t)x0 << 32) | x1) >> 11; /* 53 bits */
   return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
 }

@@ -37,7 +37,7 @@ typedef struct {
 /* Philox4x32-10 (Salmon et al. 2011).  Shared counter layout with the CUDA path:
  * ctr = {sample, draw, stream, tag}, key = {seed_lo, seed_hi}. */
 void cb2o_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* uniform in (0,1): ubits=24 -> ((x0>>8)+0.5)*2^-24 ; ubits=53 -> 53-bit from (x0,x1) */
+/* uniform in (0,1): ubits=24 -> ((x0>>9)+0.5)*2^-23 (exact in FP32) ; ubits=53 -> 53-bit from (x0,x1) */
 double cb2o_uniform(uint64_t seed, uint32_t sample, uint32_t draw, uint32_t stream, uint32_t tag, int ubits);
 /* standard normal number `i` of (sample, stream, tag): Box-Muller on philox words of draw=i/2 */
 double cb2o_normal(uint64_t seed, uint32_t sample, uint32_t i, uint32_t stream, uint32_t tag, int ubits);

@@ -24,7 +24,7 @@ def philox4x32(ctr, key):
 
 def _u(x0, x1, ubits):
     if ubits == 24:
-        return ((x0 >> 8) + 0.5) / 16777216.0
+        return ((x0 >> 9) + 0.5) / 8388608.0
     return ((((x0 << 32) | x1) >> 11) + 0.5) / 9007199254740992.0
 
 
