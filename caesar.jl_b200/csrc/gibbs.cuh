@@ -1,0 +1,348 @@
+// gibbs.cuh -- the multiscale Gibbs product kernel (included by product.cu inside its anonymous namespace).
+//
+// Per-candidate instruction budget (what bounds this kernel is the issue rate, 1 warp-instruction / clk / SMSP,
+// and the XU pipe for MUFU): with the per-chain constants pre-folded,
+//   leaf level    : Euclidean dim = 2 FFMA, circular dim = FFMA + FADD + FMNMX + FFMA, then FADD + MUFU.EX2 + FADD
+//   coarser levels: the node variances differ, so 1/(var+C) is needed per node: dims are handled in groups of
+//                   three over a common denominator (1 MUFU.RCP + 1 MUFU.LG2 per group instead of 3 + 3).
+// Circular coordinates are stored wrapped to [-pi, pi] (tree_build_kernel) and the chain mean comes out of atan2,
+// so |mu - M| <= 2 pi and the wrapped distance is min(|df|, 2 pi - |df|): no rounding instruction needed.
+
+template <typename T, int N> struct alignas(16) VecRec { T v[N]; };
+
+struct GibbsArgs {
+  const DensMeta* metas;
+  const ProdDev* prods;
+  const Work* work;
+  const int* int_pool;
+  const void* node_pool;
+  uint32_t k0, k1;
+  uint32_t circ_mask;
+};
+
+// what the kernel needs of each message, staged once per CTA in shared memory
+struct SMeta {
+  long long rec_off[kMaxLev + 1];
+  long long perm_off;
+  float bw2[CB2_MAX_DIM];
+  double bw2d[CB2_MAX_DIM];
+  double cen[CB2_MAX_DIM];  // offset to add back to Euclidean output coordinates
+  int N, depth;
+};
+
+template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
+template <> __device__ __forceinline__ float tmin<float>(float a, float b) { return fminf(a, b); }
+template <> __device__ __forceinline__ double tmin<double>(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float tabs(float a) { return fabsf(a); }
+__device__ __forceinline__ double tabs(double a) { return fabs(a); }
+__device__ __forceinline__ float tsqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ double tsqrt(double a) { return sqrt(a); }
+
+// per-chain constants of one (message, level) scoring pass
+template <typename T, int DIM> struct ChainConst {
+  T a[DIM];  // leaf: sqrt(h_i)            coarse: M_i
+  T b[DIM];  // leaf: M_i sqrt(h_i)        coarse: C_i (or 1 when the product has a single message)
+  T p[DIM];  // leaf: 2 pi sqrt(h_i)       coarse: unused
+  T qs, cmul;
+};
+
+// log2-score of a leaf: log2 w - sum_i wrapdiff_i^2 * h_i   (h_i = 0.5 log2e / (bw_i^2 + C_i); the log-variance
+// term is the same for every leaf of the level and cancels in the normalisation)
+template <typename T, int DIM>
+__device__ __forceinline__ T score_leaf(const T* __restrict__ rec, const ChainConst<T, DIM>& c, uint32_t circ) {
+  constexpr int RECL = (DIM + 1 + 3) / 4 * 4;
+  const VecRec<T, RECL> r = *reinterpret_cast<const VecRec<T, RECL>*>(rec);
+  T e = r.v[DIM];
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) {
+    T df = fma(r.v[i], c.a[i], -c.b[i]);
+    if (circ >> i & 1) {
+      T ad = tabs(df);
+      df = tmin(ad, c.p[i] - ad);
+    }
+    e = fma(-df, df, e);
+  }
+  return e;
+}
+
+// log2-score of a coarse node: log2 w - qs sum_i d_i^2/(var_i + C_i) - 0.5 sum_i log2(var_i + C_i)
+template <typename T, int DIM>
+__device__ __forceinline__ T score_node(const T* __restrict__ rec, const ChainConst<T, DIM>& c, uint32_t circ) {
+  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4;
+  const VecRec<T, RECN> r = *reinterpret_cast<const VecRec<T, RECN>*>(rec);
+  T t[DIM], sv[DIM];
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) {
+    T df = r.v[i] - c.a[i];
+    if (circ >> i & 1) {
+      T ad = tabs(df);
+      df = tmin(ad, T(CB2_TWO_PI) - ad);
+    }
+    t[i] = df * df;
+    sv[i] = fma(r.v[DIM + i], c.cmul, c.b[i]);
+  }
+  T e = r.v[2 * DIM];
+#pragma unroll
+  for (int g = 0; g < DIM; g += 3) {
+    if (g + 2 < DIM) {  // three dims over one denominator
+      T s01 = sv[g] * sv[g + 1], s12 = sv[g + 1] * sv[g + 2], s02 = sv[g] * sv[g + 2];
+      T num = fma(t[g], s12, fma(t[g + 1], s02, t[g + 2] * s01));
+      T den = s01 * sv[g + 2];
+      e = fma(-c.qs * num, fast_rcp(den), e);
+      e = fma(T(-0.5), fast_log2(den), e);
+    } else if (g + 1 < DIM) {
+      T den = sv[g] * sv[g + 1];
+      T num = fma(t[g], sv[g + 1], t[g + 1] * sv[g]);
+      e = fma(-c.qs * num, fast_rcp(den), e);
+      e = fma(T(-0.5), fast_log2(den), e);
+    } else {
+      e = fma(-c.qs * t[g], fast_rcp(sv[g]), e);
+      e = fma(T(-0.5), fast_log2(sv[g]), e);
+    }
+  }
+  return e;
+}
+
+// Gaussian product of the currently selected nodes of all messages except `skip` (skip = -1: all)
+template <typename T, int DIM>
+__device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta* __restrict__ sm, int D,
+                                        const int* __restrict__ ind_s, int tid, int step, int skip, uint32_t circ,
+                                        T (&M)[DIM], T (&C)[DIM]) {
+  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
+  T lam[DIM], s1[DIM], s2[DIM];
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) { lam[i] = T(0); s1[i] = T(0); s2[i] = T(0); }
+  for (int k = 0; k < D; ++k) {
+    if (k == skip) continue;
+    const SMeta& dm = sm[k];
+    const int lev = min(step, dm.depth);
+    const int node = ind_s[k * kS + tid];
+    T mu[DIM], var[DIM];
+    if (lev == dm.depth) {
+      const VecRec<T, RECL> r = *reinterpret_cast<const VecRec<T, RECL>*>(pool + dm.rec_off[lev] + (size_t)node * RECL);
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) { mu[i] = r.v[i]; var[i] = sizeof(T) == 4 ? (T)dm.bw2[i] : (T)dm.bw2d[i]; }
+    } else {
+      const VecRec<T, RECN> r = *reinterpret_cast<const VecRec<T, RECN>*>(pool + dm.rec_off[lev] + (size_t)node * RECN);
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) { mu[i] = r.v[i]; var[i] = r.v[DIM + i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      T l = T(1) / var[i];
+      lam[i] += l;
+      if (circ >> i & 1) {
+        T sn, cs;
+        sincos_t(mu[i], &sn, &cs);
+        s1[i] = fma(l, sn, s1[i]); s2[i] = fma(l, cs, s2[i]);
+      } else {
+        s1[i] = fma(l, mu[i], s1[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) {
+    C[i] = T(1) / lam[i];
+    M[i] = (circ >> i & 1) ? atan2_t(s1[i], s2[i]) : s1[i] * C[i];
+  }
+}
+
+template <typename T, int DIM, uint32_t CIRC>
+__global__ void __launch_bounds__(kS, 2)
+gibbs_kernel(const GibbsArgs a) {
+  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
+  constexpr int TILE_BYTES = kTileBytesF32 * (int)(sizeof(T) / 4);
+  constexpr int TN_NODE = TILE_BYTES / (RECN * (int)sizeof(T));
+  constexpr int TN_LEAF = TILE_BYTES / (RECL * (int)sizeof(T));
+  constexpr int G = 4;  // candidates scored together (ILP); tiles and chunks are multiples of G
+  const uint32_t circ = CIRC == ~0u ? a.circ_mask : CIRC;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* tile[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw + TILE_BYTES)};
+  T* chunk = reinterpret_cast<T*>(smem_raw + 2 * TILE_BYTES);                // [kNCH][kS]
+  int* ind_s = reinterpret_cast<int*>(chunk + kNCH * kS);                      // [CB2_MAX_DENS][kS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ind_s + CB2_MAX_DENS * kS);    // [2]
+  SMeta* sm = reinterpret_cast<SMeta*>(bars + 2);                              // [CB2_MAX_DENS]
+
+  const int tid = threadIdx.x;
+  const Work wk = a.work[blockIdx.x];
+  const ProdDev* __restrict__ prp = &a.prods[wk.prod];
+  const int D = prp->D, L = prp->L, sweeps = prp->sweeps, Nout = prp->Nout;
+  const uint32_t pstream = prp->stream;
+  const int s = wk.s0 + tid;
+  const bool active = s < Nout;
+  const uint32_t sid = (uint32_t)(prp->sample_offset + s);
+  const T* pool = reinterpret_cast<const T*>(a.node_pool);
+  const T HL = (T)(0.5 * CB2_LOG2E);
+  const bool single = D == 1;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < D) {
+    const DensMeta& dm = a.metas[prp->dens[tid]];
+    SMeta m;
+    for (int l = 0; l <= kMaxLev; ++l) m.rec_off[l] = dm.rec_off[l];
+    m.perm_off = dm.perm_off;
+    for (int i = 0; i < CB2_MAX_DIM; ++i) {
+      m.bw2d[i] = dm.bw[i] * dm.bw[i]; m.bw2[i] = (float)m.bw2d[i];
+      m.cen[i] = (i < DIM && !(circ >> i & 1)) ? dm.center[i] : 0.0;
+    }
+    m.N = dm.N; m.depth = dm.depth;
+    sm[tid] = m;
+  }
+  for (int k = 0; k < D; ++k) ind_s[k * kS + tid] = 0;
+  __syncthreads();
+  uint32_t use0 = 0, use1 = 0;  // completed uses of each tile buffer (phase parity)
+
+  for (int step = 1; step <= L; ++step) {
+    // levelDown: a leaf stays itself, otherwise move to the first child
+    for (int k = 0; k < D; ++k) {
+      const int depth = sm[k].depth;
+      if (step <= depth) {
+        int node = ind_s[k * kS + tid];
+        if (step == depth) { int lo, n; node_range(sm[k].N, step - 1, node, lo, n); node = lo; }
+        else node = 2 * node;
+        ind_s[k * kS + tid] = node;
+      }
+    }
+    for (int sweep = 0; sweep < sweeps; ++sweep) {
+      for (int j = 0; j < D; ++j) {
+        const SMeta& dj = sm[j];
+        const int lev = min(step, dj.depth);
+        const bool leaf = lev == dj.depth;
+        const int cnt = level_count(dj.N, dj.depth, lev);
+        const T* lrec = pool + dj.rec_off[lev];
+        const int rec = leaf ? RECL : RECN;
+        const int TN = leaf ? TN_LEAF : TN_NODE;
+        const int ntiles = (cnt + TN - 1) / TN;
+        int CH = G;
+        while (CH * kNCH < cnt) CH <<= 1;
+
+        ChainConst<T, DIM> cc;
+        {
+          T M[DIM], C[DIM];
+          if (!single) combine<T, DIM>(pool, sm, D, ind_s, tid, step, j, circ, M, C);
+          cc.qs = single ? T(0) : HL;
+          cc.cmul = single ? T(0) : T(1);
+#pragma unroll
+          for (int i = 0; i < DIM; ++i) {
+            if (leaf) {
+              T h = single ? T(0) : HL / ((sizeof(T) == 4 ? (T)dj.bw2[i] : (T)dj.bw2d[i]) + C[i]);
+              T sh = tsqrt(h);
+              cc.a[i] = sh; cc.b[i] = single ? T(0) : M[i] * sh; cc.p[i] = T(CB2_TWO_PI) * sh;
+            } else {
+              cc.a[i] = single ? T(0) : M[i]; cc.b[i] = single ? T(1) : C[i]; cc.p[i] = T(0);
+            }
+          }
+        }
+
+        // ---- pass 1: chunk partial sums of exp2(e - m), m = running (lazily raised) reference maximum
+        T m = -INFINITY, csum = T(0);
+        int cidx = 0;
+        if (tid == 0) {
+          uint32_t bytes = (uint32_t)(min(TN, cnt) * rec * (int)sizeof(T));
+          mbar_expect_tx(&bars[0], bytes);
+          tma_load_1d(tile[0], lrec, bytes, &bars[0]);
+        }
+        for (int t = 0; t < ntiles; ++t) {
+          const int b = t & 1;
+          if (tid == 0 && t + 1 < ntiles) {
+            int n1 = min(TN, cnt - (t + 1) * TN);
+            uint32_t bytes = (uint32_t)(n1 * rec * (int)sizeof(T));
+            mbar_expect_tx(&bars[b ^ 1], bytes);
+            tma_load_1d(tile[b ^ 1], lrec + (size_t)(t + 1) * TN * rec, bytes, &bars[b ^ 1]);
+          }
+          mbar_wait(&bars[b], (b ? use1 : use0) & 1);
+          if (b) ++use1; else ++use0;
+          const int nt = min(TN, cnt - t * TN);
+          const T* tb = tile[b];
+          const int zbase = t * TN;
+          const int ntg = nt & ~(G - 1);
+          for (int z = 0; z < ntg; z += G) {
+            T e[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              e[g] = leaf ? score_leaf<T, DIM>(tb + (z + g) * RECL, cc, circ) : score_node<T, DIM>(tb + (z + g) * RECN, cc, circ);
+            T gm = fmax(fmax(e[0], e[1]), fmax(e[2], e[3]));
+            if (gm > m + T(60)) {  // rare: raise the reference and rescale what has been summed so far
+              T sc = fast_exp2(m - gm);
+              csum *= sc;
+              for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
+              m = gm;
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) csum += fast_exp2(e[g] - m);
+            if (((zbase + z + G) & (CH - 1)) == 0) { chunk[cidx * kS + tid] = csum; csum = T(0); ++cidx; }
+          }
+          for (int z = ntg; z < nt; ++z) {  // ragged tail of the level (cnt not a multiple of G)
+            T e = leaf ? score_leaf<T, DIM>(tb + z * RECL, cc, circ) : score_node<T, DIM>(tb + z * RECN, cc, circ);
+            if (e > m + T(60)) {
+              T sc = fast_exp2(m - e);
+              csum *= sc;
+              for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
+              m = e;
+            }
+            csum += fast_exp2(e - m);
+          }
+          __syncthreads();  // everyone is done with tile[b] before it is refilled
+        }
+        if (cnt & (CH - 1)) { chunk[cidx * kS + tid] = csum; ++cidx; }
+        const int nch = cidx;
+
+        // ---- inverse CDF: pick the chunk, then re-score only that chunk
+        T tot = T(0);
+        for (int c = 0; c < nch; ++c) tot += chunk[c * kS + tid];
+        uint32_t rnd[4];
+        const uint32_t draw = (uint32_t)(((step - 1) * sweeps + sweep) * D + j);
+        philox4x32_10(sid, draw, pstream, 0u, a.k0, a.k1, rnd);
+        const T tgt = u01<T>(rnd[0], rnd[1]) * tot;
+        T cum = T(0);
+        int sel = nch - 1;
+        for (int c = 0; c < nch; ++c) {
+          T v = chunk[c * kS + tid];
+          if (cum + v >= tgt) { sel = c; break; }
+          cum += v;
+        }
+        const int z0 = sel * CH, z1 = min(cnt, z0 + CH);
+        int pick = -1, lastpos = z0;
+        for (int z = z0; z < z1; ++z) {
+          T e = leaf ? score_leaf<T, DIM>(lrec + (size_t)z * RECL, cc, circ) : score_node<T, DIM>(lrec + (size_t)z * RECN, cc, circ);
+          T p = fast_exp2(e - m);
+          cum += p;
+          if (p > T(0)) lastpos = z;
+          if (cum >= tgt) { pick = z; break; }
+        }
+        if (pick < 0) pick = lastpos;
+        if (active) ind_s[j * kS + tid] = pick;
+      }
+    }
+  }
+
+  if (!active) return;
+  // final point: product of all selected kernels plus one Gaussian draw
+  T M[DIM], C[DIM];
+  combine<T, DIM>(pool, sm, D, ind_s, tid, L, -1, circ, M, C);
+  uint32_t rnd[4];
+  double* out = prp->out;
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) {
+    if ((i & 1) == 0) philox4x32_10(sid, (uint32_t)(i >> 1), pstream, 1u, a.k0, a.k1, rnd);
+    double u1 = (double)u01<T>(rnd[0], rnd[1]), u2 = (double)u01<T>(rnd[2], rnd[3]);
+    double r = sqrt(-2.0 * log(u1)), sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    double v = (double)M[i] + sm[0].cen[i] + sqrt((double)C[i]) * ((i & 1) ? r * sn : r * cs);
+    if (circ >> i & 1) v = wrap_pi(v);
+    out[(size_t)s * DIM + i] = v;
+  }
+  int* labels = prp->labels;
+  if (labels) {
+    for (int k = 0; k < D; ++k) labels[(size_t)s * D + k] = a.int_pool[sm[k].perm_off + ind_s[k * kS + tid]];
+  }
+}
+
+template <typename T> size_t gibbs_smem_bytes() {
+  return 2 * (size_t)kTileBytesF32 * (sizeof(T) / 4) + sizeof(T) * kNCH * kS + sizeof(int) * CB2_MAX_DENS * kS + 16 +
+         sizeof(SMeta) * CB2_MAX_DENS + 64;
+}

@@ -59,6 +59,7 @@ struct DensMeta {
   int N, depth;
   long long rec_off[kMaxLev + 1];  // element offset of each level's records in the node pool
   long long perm_off;              // offset in the int pool
+  const double* center;            // d values (device): Euclidean coordinates are stored relative to this point
 };
 
 struct ProdDev {
@@ -88,7 +89,7 @@ __device__ __forceinline__ bool key_less(unsigned long long oa, uint32_t ta, uns
 template <typename T>
 __global__ void __launch_bounds__(kTreeThreads)
 tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ int_pool, T* __restrict__ node_pool,
-                  double* __restrict__ stat_scratch, size_t stat_stride) {
+                  double* __restrict__ stat_scratch, size_t stat_stride, uint32_t circ_mask) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const DensMeta m = metas[blockIdx.x];
   const int N = m.N, depth = m.depth, tid = threadIdx.x, nthr = blockDim.x;
@@ -188,7 +189,7 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
         double v = m.pts[(size_t)idx * d + i];
         sl[(size_t)p * nd + i] = v;
         sl[(size_t)p * nd + d + i] = m.bw[i] * m.bw[i];
-        rec[(size_t)p * RECL + i] = (T)v;
+        rec[(size_t)p * RECL + i] = (T)((circ_mask >> i & 1) ? wrap_pi(v) : v - m.center[i]);
       }
       sl[(size_t)p * nd + 2 * d] = wt;
       for (int i = d; i < RECL; ++i) rec[(size_t)p * RECL + i] = T(0);
@@ -219,7 +220,7 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
         v /= ws;
         sl[(size_t)k * nd + i] = mm;
         sl[(size_t)k * nd + d + i] = v;
-        rec[(size_t)k * RECN + i] = (T)mm;
+        rec[(size_t)k * RECN + i] = (T)((circ_mask >> i & 1) ? wrap_pi(mm) : mm - m.center[i]);
         rec[(size_t)k * RECN + d + i] = (T)v;
       }
       for (int i = 2 * d; i < RECN; ++i) rec[(size_t)k * RECN + i] = T(0);
@@ -266,262 +267,8 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                : "memory");
 }
 
-template <typename T, int N> struct alignas(16) VecRec { T v[N]; };
+#include "gibbs.cuh"
 
-struct GibbsArgs {
-  const DensMeta* metas;
-  const ProdDev* prods;
-  const Work* work;
-  const int* int_pool;
-  const void* node_pool;
-  uint32_t k0, k1;
-  uint32_t circ_mask;
-};
-
-// score of one candidate, in log2 units (up to a constant shared by all candidates of the level)
-template <typename T, int DIM, bool LEAF>
-__device__ __forceinline__ T score(const T* __restrict__ rec, const T (&M)[DIM], const T (&Cq)[DIM], T qs, T cmul,
-                                   uint32_t circ) {
-  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
-  constexpr int NR = LEAF ? RECL : RECN;
-  VecRec<T, NR> r = *reinterpret_cast<const VecRec<T, NR>*>(rec);
-  if (LEAF) {  // Cq holds qs / (bw^2 + C): the log term is the same for every leaf and drops out
-    T e = r.v[DIM];
-#pragma unroll
-    for (int i = 0; i < DIM; ++i) {
-      T df = r.v[i] - M[i];
-      if (circ >> i & 1) df = wrap_pi(df);
-      e = fma(-(df * df), Cq[i], e);
-    }
-    return e;
-  } else {
-    T e = r.v[2 * DIM];
-    T pa = T(1), pb = T(1);
-#pragma unroll
-    for (int i = 0; i < DIM; ++i) {
-      T sv = fma(r.v[DIM + i], cmul, Cq[i]);
-      T df = r.v[i] - M[i];
-      if (circ >> i & 1) df = wrap_pi(df);
-      e = fma(-(df * df * qs), fast_rcp(sv), e);
-      if (i < 3) pa *= sv; else pb *= sv;
-    }
-    e -= T(0.5) * fast_log2(pa);
-    if (DIM > 3) e -= T(0.5) * fast_log2(pb);
-    return e;
-  }
-}
-
-// Gaussian product of the currently selected nodes of all messages except `skip` (skip = -1: all)
-template <typename T, int DIM>
-__device__ __forceinline__ void combine(const GibbsArgs& a, const ProdDev& pr, const int* __restrict__ ind_s, int tid,
-                                        int step, int skip, uint32_t circ, T (&M)[DIM], T (&C)[DIM]) {
-  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
-  T lam[DIM], s1[DIM], s2[DIM];
-#pragma unroll
-  for (int i = 0; i < DIM; ++i) { lam[i] = T(0); s1[i] = T(0); s2[i] = T(0); }
-  const T* pool = reinterpret_cast<const T*>(a.node_pool);
-  for (int k = 0; k < pr.D; ++k) {
-    if (k == skip) continue;
-    const DensMeta& dm = a.metas[pr.dens[k]];
-    const int lev = min(step, dm.depth);
-    const int node = ind_s[k * kS + tid];
-    T mu[DIM], var[DIM];
-    if (lev == dm.depth) {
-      VecRec<T, RECL> r = *reinterpret_cast<const VecRec<T, RECL>*>(pool + dm.rec_off[lev] + (size_t)node * RECL);
-#pragma unroll
-      for (int i = 0; i < DIM; ++i) { mu[i] = r.v[i]; var[i] = (T)(dm.bw[i] * dm.bw[i]); }
-    } else {
-      VecRec<T, RECN> r = *reinterpret_cast<const VecRec<T, RECN>*>(pool + dm.rec_off[lev] + (size_t)node * RECN);
-#pragma unroll
-      for (int i = 0; i < DIM; ++i) { mu[i] = r.v[i]; var[i] = r.v[DIM + i]; }
-    }
-#pragma unroll
-    for (int i = 0; i < DIM; ++i) {
-      T l = T(1) / var[i];
-      lam[i] += l;
-      if (circ >> i & 1) {
-        T sn, cs;
-        sincos_t(mu[i], &sn, &cs);
-        s1[i] = fma(l, sn, s1[i]); s2[i] = fma(l, cs, s2[i]);
-      } else {
-        s1[i] = fma(l, mu[i], s1[i]);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < DIM; ++i) {
-    C[i] = T(1) / lam[i];
-    M[i] = (circ >> i & 1) ? atan2_t(s1[i], s2[i]) : s1[i] * C[i];
-  }
-}
-
-template <typename T, int DIM, uint32_t CIRC>
-__global__ void __launch_bounds__(kS)
-gibbs_kernel(const GibbsArgs a) {
-  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
-  constexpr int TILE_BYTES = kTileBytesF32 * (int)(sizeof(T) / 4);
-  constexpr int TN_NODE = TILE_BYTES / (RECN * (int)sizeof(T));
-  constexpr int TN_LEAF = TILE_BYTES / (RECL * (int)sizeof(T));
-  const uint32_t circ = CIRC == ~0u ? a.circ_mask : CIRC;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  T* tile[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw + TILE_BYTES)};
-  T* chunk = reinterpret_cast<T*>(smem_raw + 2 * TILE_BYTES);            // [kNCH][kS]
-  int* ind_s = reinterpret_cast<int*>(chunk + kNCH * kS);                  // [CB2_MAX_DENS][kS]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ind_s + CB2_MAX_DENS * kS);  // [2]
-
-  const int tid = threadIdx.x;
-  const Work wk = a.work[blockIdx.x];
-  const ProdDev& pr = a.prods[wk.prod];
-  const int D = pr.D;
-  const int s = wk.s0 + tid;
-  const bool active = s < pr.Nout;
-  const uint32_t sid = (uint32_t)(pr.sample_offset + s);
-  const T* pool = reinterpret_cast<const T*>(a.node_pool);
-  const T HL = (T)(0.5 * CB2_LOG2E);
-  const bool single = D == 1;
-  const T qs = single ? T(0) : HL;
-  const T cmul = single ? T(0) : T(1);
-
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int k = 0; k < D; ++k) ind_s[k * kS + tid] = 0;
-  __syncthreads();
-  uint32_t use0 = 0, use1 = 0;  // completed uses of each tile buffer (phase parity)
-
-  for (int step = 1; step <= pr.L; ++step) {
-    // levelDown: a leaf stays itself, otherwise move to the first child
-    for (int k = 0; k < D; ++k) {
-      const DensMeta& dm = a.metas[pr.dens[k]];
-      if (step <= dm.depth) {
-        int node = ind_s[k * kS + tid];
-        if (step == dm.depth) { int lo, n; node_range(dm.N, step - 1, node, lo, n); node = lo; }
-        else node = 2 * node;
-        ind_s[k * kS + tid] = node;
-      }
-    }
-    for (int sweep = 0; sweep < pr.sweeps; ++sweep) {
-      for (int j = 0; j < D; ++j) {
-        const DensMeta& dj = a.metas[pr.dens[j]];
-        const int lev = min(step, dj.depth);
-        const bool leaf = lev == dj.depth;
-        const int cnt = level_count(dj.N, dj.depth, lev);
-        const T* lrec = pool + dj.rec_off[lev];
-        const int rec = leaf ? RECL : RECN;
-        const int TN = leaf ? TN_LEAF : TN_NODE;
-        const int ntiles = (cnt + TN - 1) / TN;
-        int CH = 4;
-        while (CH * kNCH < cnt) CH <<= 1;
-
-        T M[DIM], Cq[DIM];
-        if (!single) {
-          combine<T, DIM>(a, pr, ind_s, tid, step, j, circ, M, Cq);
-          if (leaf) {
-#pragma unroll
-            for (int i = 0; i < DIM; ++i) Cq[i] = HL / ((T)(dj.bw[i] * dj.bw[i]) + Cq[i]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < DIM; ++i) { M[i] = T(0); Cq[i] = leaf ? T(0) : T(1); }
-        }
-
-        // ---- pass 1: chunk partial sums of exp2(e - m), m = running (lazily raised) maximum
-        T m = -INFINITY, csum = T(0);
-        int cidx = 0;
-        if (tid == 0) {
-          uint32_t bytes = (uint32_t)(min(TN, cnt) * rec * (int)sizeof(T));
-          mbar_expect_tx(&bars[0], bytes);
-          tma_load_1d(tile[0], lrec, bytes, &bars[0]);
-        }
-        for (int t = 0; t < ntiles; ++t) {
-          const int b = t & 1;
-          if (tid == 0 && t + 1 < ntiles) {
-            int n1 = min(TN, cnt - (t + 1) * TN);
-            uint32_t bytes = (uint32_t)(n1 * rec * (int)sizeof(T));
-            mbar_expect_tx(&bars[b ^ 1], bytes);
-            tma_load_1d(tile[b ^ 1], lrec + (size_t)(t + 1) * TN * rec, bytes, &bars[b ^ 1]);
-          }
-          mbar_wait(&bars[b], (b ? use1 : use0) & 1);
-          if (b) ++use1; else ++use0;
-          const int nt = min(TN, cnt - t * TN);
-          const T* tb = tile[b];
-          const int zbase = t * TN;
-#pragma unroll 4
-          for (int z = 0; z < nt; ++z) {
-            T e = leaf ? score<T, DIM, true>(tb + z * RECL, M, Cq, qs, cmul, circ)
-                       : score<T, DIM, false>(tb + z * RECN, M, Cq, qs, cmul, circ);
-            if (e > m + T(60)) {  // rare: raise the reference maximum and rescale what has been summed
-              T sc = fast_exp2(m - e);
-              csum *= sc;
-              for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
-              m = e;
-            }
-            csum += fast_exp2(e - m);
-            if (((zbase + z + 1) & (CH - 1)) == 0) { chunk[cidx * kS + tid] = csum; csum = T(0); ++cidx; }
-          }
-          __syncthreads();  // everyone is done with tile[b] before it is refilled
-        }
-        if (cnt & (CH - 1)) { chunk[cidx * kS + tid] = csum; ++cidx; }
-        const int nch = cidx;
-
-        // ---- inverse CDF: pick the chunk, then re-score only that chunk
-        T tot = T(0);
-        for (int c = 0; c < nch; ++c) tot += chunk[c * kS + tid];
-        uint32_t rnd[4];
-        const uint32_t draw = (uint32_t)(((step - 1) * pr.sweeps + sweep) * D + j);
-        philox4x32_10(sid, draw, pr.stream, 0u, a.k0, a.k1, rnd);
-        const T tgt = u01<T>(rnd[0], rnd[1]) * tot;
-        T cum = T(0);
-        int sel = nch - 1;
-        for (int c = 0; c < nch; ++c) {
-          T v = chunk[c * kS + tid];
-          if (cum + v >= tgt) { sel = c; break; }
-          cum += v;
-        }
-        const int z0 = sel * CH, z1 = min(cnt, z0 + CH);
-        int pick = -1, lastpos = z0;
-        for (int z = z0; z < z1; ++z) {
-          T e = leaf ? score<T, DIM, true>(lrec + (size_t)z * RECL, M, Cq, qs, cmul, circ)
-                     : score<T, DIM, false>(lrec + (size_t)z * RECN, M, Cq, qs, cmul, circ);
-          T p = fast_exp2(e - m);
-          cum += p;
-          if (p > T(0)) lastpos = z;
-          if (cum >= tgt) { pick = z; break; }
-        }
-        if (pick < 0) pick = lastpos;
-        if (active) ind_s[j * kS + tid] = pick;
-      }
-    }
-  }
-
-  if (!active) return;
-  // final point: product of all selected kernels plus one Gaussian draw
-  T M[DIM], C[DIM];
-  combine<T, DIM>(a, pr, ind_s, tid, pr.L, -1, circ, M, C);
-  uint32_t rnd[4];
-#pragma unroll
-  for (int i = 0; i < DIM; ++i) {
-    if ((i & 1) == 0) philox4x32_10(sid, (uint32_t)(i >> 1), pr.stream, 1u, a.k0, a.k1, rnd);
-    double u1 = (double)u01<T>(rnd[0], rnd[1]), u2 = (double)u01<T>(rnd[2], rnd[3]);
-    double r = sqrt(-2.0 * log(u1)), sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
-    double v = (double)M[i] + sqrt((double)C[i]) * ((i & 1) ? r * sn : r * cs);
-    if (circ >> i & 1) v = wrap_pi(v);
-    pr.out[(size_t)s * DIM + i] = v;
-  }
-  if (pr.labels) {
-    for (int k = 0; k < D; ++k) {
-      const DensMeta& dm = a.metas[pr.dens[k]];
-      pr.labels[(size_t)s * D + k] = a.int_pool[dm.perm_off + ind_s[k * kS + tid]];
-    }
-  }
-}
-
-template <typename T> size_t gibbs_smem_bytes() {
-  return 2 * (size_t)kTileBytesF32 * (sizeof(T) / 4) + sizeof(T) * kNCH * kS + sizeof(int) * CB2_MAX_DENS * kS + 64;
-}
 
 template <typename T, int DIM, uint32_t CIRC>
 int launch_gibbs_inst(cb2_ctx* ctx, int nwork, const GibbsArgs& a) {
@@ -639,6 +386,7 @@ int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const
     for (int j = 0; j < descs[b].D; ++j, ++mi) {
       pl.metas[mi].pts = descs[b].dens[j].pts;
       pl.metas[mi].w = descs[b].dens[j].w;
+      pl.metas[mi].center = descs[b].dens[0].pts;  // first kernel of the first message: products are translation invariant
       for (int k = 0; k < d; ++k) {
         double s = bw_host[b][j][k];
         if (!(s > 0) || !isfinite(s)) return cb2_fail(ctx, CB2_ERR_INVALID, "product %d message %d: bandwidth[%d] must be positive", b, j, k);
@@ -657,7 +405,7 @@ int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const
   cudaError_t e = cudaFuncSetAttribute(tree_build_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem);
   if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "tree smem attribute (%zu bytes): %s", tree_smem, cudaGetErrorString(e));
   tree_build_kernel<T><<<(int)pl.metas.size(), kTreeThreads, tree_smem, ctx->stream>>>(lay.metas, d, lay.int_pool, (T*)lay.node_pool,
-                                                                                          lay.stat, stat_stride);
+                                                                                          lay.stat, stat_stride, mask);
   CB2_CHECK_LAUNCH(ctx, "tree_build_kernel");
   CB2_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
   GibbsArgs ga;
