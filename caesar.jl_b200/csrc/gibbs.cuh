@@ -27,7 +27,7 @@ struct SMeta {
   float bw2[CB2_MAX_DIM];
   double bw2d[CB2_MAX_DIM];
   double cen[CB2_MAX_DIM];  // offset to add back to Euclidean output coordinates
-  int N, depth;
+  int N, depth, uniform;
 };
 
 template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
@@ -46,16 +46,44 @@ template <typename T, int DIM> struct ChainConst {
   T qs, cmul;
 };
 
-// log2-score of a leaf: log2 w - sum_i wrapdiff_i^2 * h_i   (h_i = 0.5 log2e / (bw_i^2 + C_i); the log-variance
-// term is the same for every leaf of the level and cancels in the normalisation)
-template <typename T, int DIM>
-__device__ __forceinline__ T score_leaf(const T* __restrict__ rec, const ChainConst<T, DIM>& c, uint32_t circ) {
+// 16-byte vector loads of one padded record; SHARED: 32-bit shared-window address (LDS.128), else read-only global
+template <bool SHARED> __device__ __forceinline__ void load16(const float* p, float (&v)[4]) {
+  if (SHARED) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(smem_u32(p)));
+  else asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+}
+template <bool SHARED> __device__ __forceinline__ void load16(const double* p, double (&v)[2]) {
+  if (SHARED) asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(smem_u32(p)));
+  else asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+}
+template <int N, bool SHARED> __device__ __forceinline__ void load_rec(const float* p, float (&v)[N]) {
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) {
+    float t[4];
+    load16<SHARED>(p + 4 * q, t);
+    v[4 * q] = t[0]; v[4 * q + 1] = t[1]; v[4 * q + 2] = t[2]; v[4 * q + 3] = t[3];
+  }
+}
+template <int N, bool SHARED> __device__ __forceinline__ void load_rec(const double* p, double (&v)[N]) {
+#pragma unroll
+  for (int q = 0; q < N / 2; ++q) {
+    double t[2];
+    load16<SHARED>(p + 2 * q, t);
+    v[2 * q] = t[0]; v[2 * q + 1] = t[1];
+  }
+}
+
+// log2-score of a leaf relative to the running reference m (nm = -m):
+//   log2 w - m - sum_i wrapdiff_i^2 * h_i   (h_i = 0.5 log2e / (bw_i^2 + C_i); the log-variance term is the same
+//   for every leaf of the level and cancels in the normalisation; with uniform weights so does log2 w: UW)
+template <typename T, int DIM, bool SHARED, bool UW>
+__device__ __forceinline__ T score_leaf(const T* __restrict__ rec, const ChainConst<T, DIM>& c, uint32_t circ, T nm) {
   constexpr int RECL = (DIM + 1 + 3) / 4 * 4;
-  const VecRec<T, RECL> r = *reinterpret_cast<const VecRec<T, RECL>*>(rec);
-  T e = r.v[DIM];
+  T r[RECL];
+  load_rec<RECL, SHARED>(rec, r);
+  T e = UW ? nm : r[DIM] + nm;
 #pragma unroll
   for (int i = 0; i < DIM; ++i) {
-    T df = fma(r.v[i], c.a[i], -c.b[i]);
+    T df = fma(r[i], c.a[i], -c.b[i]);
     if (circ >> i & 1) {
       T ad = tabs(df);
       df = tmin(ad, c.p[i] - ad);
@@ -65,23 +93,24 @@ __device__ __forceinline__ T score_leaf(const T* __restrict__ rec, const ChainCo
   return e;
 }
 
-// log2-score of a coarse node: log2 w - qs sum_i d_i^2/(var_i + C_i) - 0.5 sum_i log2(var_i + C_i)
-template <typename T, int DIM>
-__device__ __forceinline__ T score_node(const T* __restrict__ rec, const ChainConst<T, DIM>& c, uint32_t circ) {
+// log2-score of a coarse node relative to m: log2 w - m - qs sum_i d_i^2/(var_i + C_i) - 0.5 sum_i log2(var_i + C_i)
+template <typename T, int DIM, bool SHARED>
+__device__ __forceinline__ T score_node(const T* __restrict__ rec, const ChainConst<T, DIM>& c, uint32_t circ, T nm) {
   constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4;
-  const VecRec<T, RECN> r = *reinterpret_cast<const VecRec<T, RECN>*>(rec);
+  T r[RECN];
+  load_rec<RECN, SHARED>(rec, r);
   T t[DIM], sv[DIM];
 #pragma unroll
   for (int i = 0; i < DIM; ++i) {
-    T df = r.v[i] - c.a[i];
+    T df = r[i] - c.a[i];
     if (circ >> i & 1) {
       T ad = tabs(df);
       df = tmin(ad, T(CB2_TWO_PI) - ad);
     }
     t[i] = df * df;
-    sv[i] = fma(r.v[DIM + i], c.cmul, c.b[i]);
+    sv[i] = fma(r[DIM + i], c.cmul, c.b[i]);
   }
-  T e = r.v[2 * DIM];
+  T e = r[2 * DIM] + nm;
 #pragma unroll
   for (int g = 0; g < DIM; g += 3) {
     if (g + 2 < DIM) {  // three dims over one denominator
@@ -101,6 +130,86 @@ __device__ __forceinline__ T score_node(const T* __restrict__ rec, const ChainCo
     }
   }
   return e;
+}
+
+// one scoring pass over the candidates of a level held in shared-memory tiles: chunk partial sums of exp2(e - m).
+// MODE 0: coarse level, 1: leaf level with per-kernel weights, 2: leaf level with uniform weights
+template <typename T, int DIM, int MODE>
+__device__ __forceinline__ T score_any_s(const T* rec, const ChainConst<T, DIM>& c, uint32_t circ, T nm) {
+  return MODE == 0 ? score_node<T, DIM, true>(rec, c, circ, nm)
+                   : (MODE == 1 ? score_leaf<T, DIM, true, false>(rec, c, circ, nm) : score_leaf<T, DIM, true, true>(rec, c, circ, nm));
+}
+template <typename T, int DIM, int MODE>
+__device__ __forceinline__ T score_any_g(const T* rec, const ChainConst<T, DIM>& c, uint32_t circ, T nm) {
+  return MODE == 0 ? score_node<T, DIM, false>(rec, c, circ, nm)
+                   : (MODE == 1 ? score_leaf<T, DIM, false, false>(rec, c, circ, nm) : score_leaf<T, DIM, false, true>(rec, c, circ, nm));
+}
+
+template <typename T, int DIM, int MODE>
+__device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int zbase, int CH, const ChainConst<T, DIM>& cc,
+                                          uint32_t circ, T* __restrict__ chunk, int tid, T& m, T& csum, int& cidx) {
+  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
+  constexpr int REC = MODE == 0 ? RECN : RECL;
+  constexpr int G = 4;
+  const int ntg = nt & ~(G - 1);
+  T nm = -m;
+  for (int z = 0; z < ntg; z += G) {
+    T e[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) e[g] = score_any_s<T, DIM, MODE>(tb + (z + g) * REC, cc, circ, nm);
+    T gm = fmax(fmax(e[0], e[1]), fmax(e[2], e[3]));
+    if (gm > T(60)) {  // rare: raise the reference by gm and rescale what has been summed so far
+      if (nm == INFINITY) {  // first group of the pass: scores were computed against m = -inf, nothing summed yet
+#pragma unroll
+        for (int g = 0; g < G; ++g) e[g] = score_any_s<T, DIM, MODE>(tb + (z + g) * REC, cc, circ, T(0));
+        gm = fmax(fmax(e[0], e[1]), fmax(e[2], e[3]));
+        m = gm;
+      } else {
+        T sc = fast_exp2(-gm);
+        csum *= sc;
+        for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
+        m += gm;
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) e[g] -= gm;
+      nm = -m;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) csum += fast_exp2(e[g]);
+    if (((zbase + z + G) & (CH - 1)) == 0) { chunk[cidx * kS + tid] = csum; csum = T(0); ++cidx; }
+  }
+  for (int z = ntg; z < nt; ++z) {  // ragged tail of the level (count not a multiple of G)
+    T e = score_any_s<T, DIM, MODE>(tb + z * REC, cc, circ, nm);
+    if (e > T(60)) {
+      if (nm == INFINITY) { e = score_any_s<T, DIM, MODE>(tb + z * REC, cc, circ, T(0)); m = e; }
+      else {
+        T sc = fast_exp2(-e);
+        csum *= sc;
+        for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
+        m += e;
+      }
+      e = T(0);
+      nm = -m;
+    }
+    csum += fast_exp2(e);
+  }
+}
+
+// pass 2: re-score the selected chunk from global memory until the cumulative sum crosses the target
+template <typename T, int DIM, int MODE>
+__device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, int z1, const ChainConst<T, DIM>& cc, uint32_t circ,
+                                          T m, T cum, T tgt) {
+  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
+  constexpr int REC = MODE == 0 ? RECN : RECL;
+  int pick = -1, lastpos = z0;
+  const T nm = -m;
+  for (int z = z0; z < z1; ++z) {
+    T p = fast_exp2(score_any_g<T, DIM, MODE>(lrec + (size_t)z * REC, cc, circ, nm));
+    cum += p;
+    if (p > T(0)) lastpos = z;
+    if (cum >= tgt) { pick = z; break; }
+  }
+  return pick < 0 ? lastpos : pick;
 }
 
 // Gaussian product of the currently selected nodes of all messages except `skip` (skip = -1: all)
@@ -154,7 +263,7 @@ gibbs_kernel(const GibbsArgs a) {
   constexpr int TILE_BYTES = kTileBytesF32 * (int)(sizeof(T) / 4);
   constexpr int TN_NODE = TILE_BYTES / (RECN * (int)sizeof(T));
   constexpr int TN_LEAF = TILE_BYTES / (RECL * (int)sizeof(T));
-  constexpr int G = 4;  // candidates scored together (ILP); tiles and chunks are multiples of G
+  constexpr int G = 4;  // candidates scored together (ILP, see tile_pass); tiles and chunks are multiples of G
   const uint32_t circ = CIRC == ~0u ? a.circ_mask : CIRC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* tile[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw + TILE_BYTES)};
@@ -189,7 +298,7 @@ gibbs_kernel(const GibbsArgs a) {
       m.bw2d[i] = dm.bw[i] * dm.bw[i]; m.bw2[i] = (float)m.bw2d[i];
       m.cen[i] = (i < DIM && !(circ >> i & 1)) ? dm.center[i] : 0.0;
     }
-    m.N = dm.N; m.depth = dm.depth;
+    m.N = dm.N; m.depth = dm.depth; m.uniform = dm.w == nullptr;
     sm[tid] = m;
   }
   for (int k = 0; k < D; ++k) ind_s[k * kS + tid] = 0;
@@ -257,35 +366,10 @@ gibbs_kernel(const GibbsArgs a) {
           mbar_wait(&bars[b], (b ? use1 : use0) & 1);
           if (b) ++use1; else ++use0;
           const int nt = min(TN, cnt - t * TN);
-          const T* tb = tile[b];
-          const int zbase = t * TN;
-          const int ntg = nt & ~(G - 1);
-          for (int z = 0; z < ntg; z += G) {
-            T e[G];
-#pragma unroll
-            for (int g = 0; g < G; ++g)
-              e[g] = leaf ? score_leaf<T, DIM>(tb + (z + g) * RECL, cc, circ) : score_node<T, DIM>(tb + (z + g) * RECN, cc, circ);
-            T gm = fmax(fmax(e[0], e[1]), fmax(e[2], e[3]));
-            if (gm > m + T(60)) {  // rare: raise the reference and rescale what has been summed so far
-              T sc = fast_exp2(m - gm);
-              csum *= sc;
-              for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
-              m = gm;
-            }
-#pragma unroll
-            for (int g = 0; g < G; ++g) csum += fast_exp2(e[g] - m);
-            if (((zbase + z + G) & (CH - 1)) == 0) { chunk[cidx * kS + tid] = csum; csum = T(0); ++cidx; }
-          }
-          for (int z = ntg; z < nt; ++z) {  // ragged tail of the level (cnt not a multiple of G)
-            T e = leaf ? score_leaf<T, DIM>(tb + z * RECL, cc, circ) : score_node<T, DIM>(tb + z * RECN, cc, circ);
-            if (e > m + T(60)) {
-              T sc = fast_exp2(m - e);
-              csum *= sc;
-              for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
-              m = e;
-            }
-            csum += fast_exp2(e - m);
-          }
+          const T* tb = reinterpret_cast<const T*>(smem_raw + b * TILE_BYTES);
+          if (!leaf) tile_pass<T, DIM, 0>(tb, nt, t * TN, CH, cc, circ, chunk, tid, m, csum, cidx);
+          else if (!dj.uniform) tile_pass<T, DIM, 1>(tb, nt, t * TN, CH, cc, circ, chunk, tid, m, csum, cidx);
+          else tile_pass<T, DIM, 2>(tb, nt, t * TN, CH, cc, circ, chunk, tid, m, csum, cidx);
           __syncthreads();  // everyone is done with tile[b] before it is refilled
         }
         if (cnt & (CH - 1)) { chunk[cidx * kS + tid] = csum; ++cidx; }
@@ -306,15 +390,9 @@ gibbs_kernel(const GibbsArgs a) {
           cum += v;
         }
         const int z0 = sel * CH, z1 = min(cnt, z0 + CH);
-        int pick = -1, lastpos = z0;
-        for (int z = z0; z < z1; ++z) {
-          T e = leaf ? score_leaf<T, DIM>(lrec + (size_t)z * RECL, cc, circ) : score_node<T, DIM>(lrec + (size_t)z * RECN, cc, circ);
-          T p = fast_exp2(e - m);
-          cum += p;
-          if (p > T(0)) lastpos = z;
-          if (cum >= tgt) { pick = z; break; }
-        }
-        if (pick < 0) pick = lastpos;
+        const int pick = !leaf ? chunk_pick<T, DIM, 0>(lrec, z0, z1, cc, circ, m, cum, tgt)
+                               : (!dj.uniform ? chunk_pick<T, DIM, 1>(lrec, z0, z1, cc, circ, m, cum, tgt)
+                                              : chunk_pick<T, DIM, 2>(lrec, z0, z1, cc, circ, m, cum, tgt));
         if (active) ind_s[j * kS + tid] = pick;
       }
     }
