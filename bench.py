@@ -94,6 +94,7 @@ class ClockSampler:
 def cpu_reference_arm(steps, warmup):
     """The CPU restatement on all host cores: one variable (8 x 4096 -> 4096 samples + LOO bandwidth) per step."""
     import oracle
+    oracle.use_all_cores()
     dens = make_variable(0)
     times = []
     for it in range(warmup + steps):
@@ -139,6 +140,9 @@ def main():
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    # libraries (NCCL, torch) may write to stdout: keep fd 1 clean for the single JSON line
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from __graft_entry__ import load_package
@@ -239,6 +243,10 @@ def main():
     # device result == host-API result for the same seed (the two arms run the same kernels)
     assert np.isfinite(pin_out[0].numpy()).all() and (bw_out[0] > 0).all()
 
+    extra = {}
+    if not args.no_extras:
+        extra = mmd_extras(cb, ctx, torch, tstream, rank, world, dist if world > 1 else None)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -268,10 +276,6 @@ def main():
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}, "traffic": None,
     }
 
-    extra = {}
-    if not args.no_extras:
-        extra = mmd_extras(cb, ctx, torch, tstream)
-
     cpu = None
     if not args.no_cpu_baseline:
         val, sec, thr = cpu_reference_arm(1, 0)
@@ -286,15 +290,21 @@ def main():
                 "steps": e2e_steps, "timer": "host perf_counter around the synchronous C-ABI call"},
         "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
     }
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def mmd_extras(cb, ctx, torch, tstream):
-    """Second headline of BASELINE.json: mmd kernel-pairs/s on C3 (ScatterAlignPose3 clouds, randn(P,3), bw=1)."""
+def mmd_extras(cb, ctx, torch, tstream, rank=0, world=1, dist=None):
+    """Second headline of BASELINE.json: mmd kernel-pairs/s on C3 (ScatterAlignPose3 clouds, randn(P,3), bw=1).
+    With N GPUs the rows of the three pair sums are sharded and the 3 partial sums all-reduced over NCCL (strong scaling)."""
+    from importlib import import_module
+    shard_range = import_module("caesar_jl_b200.distributed").shard_range
     import ctypes as C
     import oracle
+    oracle.use_all_cores()
     L = cb._capi.lib()
     P = 100000
     rng = np.random.default_rng(3)
@@ -304,17 +314,33 @@ def mmd_extras(cb, ctx, torch, tstream):
     with torch.cuda.stream(tstream):
         da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
         out = torch.zeros(3, dtype=torch.float64, device="cuda")
-        run = lambda: ctx.check(L.cb2_mmd_sums_dev(ctx._h, C.c_void_p(da.data_ptr()), P, C.c_void_p(db.data_ptr()), P, 3, 1.0, 0, P, 0, P,
-                                                   C.c_void_p(out.data_ptr())))
+        r0, r1 = shard_range(P, rank, world)
+
+        def run():
+            ctx.check(L.cb2_mmd_sums_dev(ctx._h, C.c_void_p(da.data_ptr()), P, C.c_void_p(db.data_ptr()), P, 3, 1.0, r0, r1, r0, r1,
+                                         C.c_void_p(out.data_ptr())))
+            if dist is not None:
+                dist.all_reduce(out, op=dist.ReduceOp.SUM)
         for _ in range(2):
             run()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(tstream)
         for _ in range(3):
             run()
         e1.record(tstream)
         tstream.synchronize()
+        sums = out.cpu().numpy()
     ms = e0.elapsed_time(e1) / 3
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sharded_value = sums[0] / (P * P) - 2 * sums[1] / (P * P) + sums[2] / (P * P)
+    if rank != 0:
+        return {}
     t0 = time.perf_counter()
     v = cb.mmd(a, b, 1.0, ctx=ctx)
     e2e_s = time.perf_counter() - t0
@@ -324,7 +350,8 @@ def mmd_extras(cb, ctx, torch, tstream):
     oracle.mmd_rows(a, b, 1.0, (0, rows), (0, rows))
     cpu_s = time.perf_counter() - t0
     sfu_peak = 148 * 16 * 1965e6
-    return {"mmd_pairs_per_s": pairs / (ms * 1e-3), "mmd_ms": ms, "mmd_points": P, "mmd_value": v,
+    assert abs(sharded_value - v) <= 1e-6 * max(abs(v), 1e-3), (sharded_value, v)
+    return {"mmd_pairs_per_s": pairs / (ms * 1e-3), "mmd_ms": ms, "mmd_points": P, "mmd_value": v, "mmd_row_shards": world,
             "mmd_e2e_pairs_per_s": pairs / e2e_s, "mmd_sfu_frac": pairs / (ms * 1e-3) / sfu_peak,
             "mmd_cpu_pairs_per_s": 3.0 * rows * P / cpu_s, "mmd_cpu_cores": oracle.num_threads(),
             "mmd_cpu_sample": f"rows [0,{rows}) of each of the three pair sums against all {P} columns"}

@@ -1,0 +1,212 @@
+# CaesarB200.jl -- the reference-side binding: Julia host code keeps the existing API (`manikde!`, `manifoldProduct`,
+# `mmd`, `sample`, evaluation of a ManifoldKernelDensity, the ScatterAlign `getSample`) and reaches the B200 kernels
+# through `ccall` into libcaesar_b200.so (C ABI: include/caesar_b200.h).  No CUDA.jl, no multi-backend dispatch, no CPU
+# fallback: if the library cannot create a context the methods throw.
+#
+# NOT EXERCISED IN THE BUILD CONTAINER (Julia is not installed there).  The same entry points, argument order and
+# layouts are exercised from Python/ctypes by tests/test_gpu_parity.py; INTEGRATION.md shows where each method hooks
+# into ApproxManifoldProducts / IncrementalInference / Caesar.
+module CaesarB200
+
+using ApproxManifoldProducts
+using ApproxManifoldProducts: ManifoldKernelDensity, getPoints, getBW
+using Manifolds, ManifoldsBase
+using StaticArrays
+import IncrementalInference as IIF
+
+const libcb2 = get(ENV, "CAESAR_B200_LIB", joinpath(@__DIR__, "..", "libcaesar_b200.so"))
+const CB2_FP32 = Cint(0)
+const CB2_FP64 = Cint(1)
+
+struct CB2Density
+  N::Int32
+  pts::Ptr{Float64}
+  bw::Ptr{Float64}
+  w::Ptr{Float64}
+end
+
+struct CB2ProductDesc
+  dens::Ptr{CB2Density}
+  D::Int32
+  Nout::Int32
+  niter::Int32
+  stream::UInt32
+  sample_offset::Int32
+  pts_out::Ptr{Float64}
+  labels_out::Ptr{Int32}
+  bw_out::Ptr{Float64}
+end
+
+mutable struct Context
+  h::Ptr{Cvoid}
+  lk::ReentrantLock
+end
+
+function Context(; device::Integer = parse(Int, get(ENV, "CAESAR_B200_DEVICE", "0")),
+                   precision::Symbol = Symbol(get(ENV, "CAESAR_B200_PRECISION", "fp32")))
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  rc = ccall((:cb2_create, libcb2), Cint, (Cint, Cint, Ref{Ptr{Cvoid}}), device, precision == :fp64 ? CB2_FP64 : CB2_FP32, h)
+  rc == 0 || error("libcaesar_b200: " * unsafe_string(ccall((:cb2_last_error, libcb2), Cstring, (Ptr{Cvoid},), C_NULL)))
+  ctx = Context(h[], ReentrantLock())
+  finalizer(c -> ccall((:cb2_destroy, libcb2), Cvoid, (Ptr{Cvoid},), c.h), ctx)
+  return ctx
+end
+
+const _ctx = Ref{Union{Nothing,Context}}(nothing)
+context() = (_ctx[] === nothing && (_ctx[] = Context()); _ctx[]::Context)
+
+# a non-zero status becomes a Julia error, so a clique Task fails the way it does today (SURVEY sec. 5)
+function _check(ctx::Context, rc::Cint)
+  rc == 0 && return nothing
+  error("libcaesar_b200 error $rc: " * unsafe_string(ccall((:cb2_last_error, libcb2), Cstring, (Ptr{Cvoid},), ctx.h)))
+end
+
+# d x N Float64, point-contiguous: a Matrix{Float64} as is; Vector{<:StaticVector{d,Float64}} is bit-identical
+_flat(pts::AbstractMatrix{Float64}) = pts
+_flat(pts::AbstractVector{<:StaticVector{D,Float64}}) where {D} = reinterpret(reshape, Float64, pts)
+_flat(pts::AbstractVector{<:AbstractVector{<:Real}}) = Float64.(reduce(hcat, pts))
+
+# coordinate topology of a manifold / variable type: 1 = circular
+_circular(::typeof(TranslationGroup(1))) = UInt8[0]
+_circular(::typeof(TranslationGroup(2))) = UInt8[0, 0]
+_circular(::typeof(TranslationGroup(3))) = UInt8[0, 0, 0]
+_circular(::typeof(SpecialEuclidean(2))) = UInt8[0, 0, 1]
+_circular(::typeof(SpecialEuclidean(3))) = UInt8[0, 0, 0, 1, 1, 1]
+_circular(M) = zeros(UInt8, manifold_dimension(M))
+
+# ------------------------------------------------------------------------------------------------ mmd
+# replaces AMP.mmd(MF, a, b, N, M, threads; bw)  -- call site Caesar ext/Images/ScatterAlignPose2.jl:179
+function b200_mmd(a, b; bw::AbstractVector{<:Real} = SA[0.001;], ctx::Context = context())
+  A, B = _flat(a), _flat(b)
+  out = Ref{Float64}(0.0)
+  lock(ctx.lk) do
+    _check(ctx, ccall((:cb2_mmd, libcb2), Cint,
+                      (Ptr{Cvoid}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Cint, Float64, Ref{Float64}),
+                      ctx.h, A, size(A, 2), B, size(B, 2), size(A, 1), Float64(bw[1]), out))
+  end
+  return out[]
+end
+ApproxManifoldProducts.mmd(MF::AbstractManifold, a::AbstractVector, b::AbstractVector, N::Int = length(a), M::Int = length(b),
+                           threads::Bool = true; bw::AbstractVector{<:Real} = SA[0.001;]) = b200_mmd(a, b; bw)
+ApproxManifoldProducts.mmd(a::ManifoldKernelDensity, b::ManifoldKernelDensity; bw::AbstractVector{<:Real} = SA[0.001;]) =
+  b200_mmd(getPoints(a.belief), getPoints(b.belief); bw)
+
+# value + analytic gradient of cost(c) = mmd(a, T(c)^-1 b) for K coordinate vectors (columns of `coords`);
+# lets getSample call Optim.optimize(f, g!, x0, BFGS()) instead of finite differences (ScatterAlignPose2.jl:182)
+function b200_mmd_se_batch(a, b, coords::AbstractMatrix{Float64}; bw::Real, backward::Bool = true, ctx::Context = context())
+  A, B = _flat(a), _flat(b)
+  K = size(coords, 2)
+  vals = zeros(K); grads = zeros(size(coords))
+  lock(ctx.lk) do
+    _check(ctx, ccall((:cb2_mmd_se_batch, libcb2), Cint,
+                      (Ptr{Cvoid}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Cint, Float64, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}),
+                      ctx.h, A, size(A, 2), B, size(B, 2), size(A, 1), Float64(bw), coords, K, backward, vals, grads))
+  end
+  return vals, grads
+end
+
+# ------------------------------------------------------------------------------------------------ manikde! / evaluate / sample
+# replaces the LOO-CV bandwidth search inside AMP.manikde!(M, pts) when `bw` is not given
+function b200_bandwidth(M, pts; ctx::Context = context())
+  P = _flat(pts)
+  d, N = size(P)
+  sigma = zeros(d)
+  circ = _circular(M)
+  lock(ctx.lk) do
+    _check(ctx, ccall((:cb2_kde_bw_loo, libcb2), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Ptr{UInt8}, Ptr{Float64}),
+                      ctx.h, P, d, N, circ, sigma))
+  end
+  return sigma
+end
+
+# (mkd)(pts): flat-coordinate evaluation, exact sum (upstream: dual-tree approximation, rel. tol 1e-3)
+function b200_evaluate(mkd::ManifoldKernelDensity, q::AbstractMatrix{Float64}; logp::Bool = false, ctx::Context = context())
+  mu = getPoints(mkd.belief); sigma = vec(getBW(mkd.belief)[:, 1])
+  out = zeros(size(q, 2))
+  lock(ctx.lk) do
+    _check(ctx, ccall((:cb2_kde_eval, libcb2), Cint,
+                      (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}),
+                      ctx.h, mu, sigma, C_NULL, size(mu, 1), size(mu, 2), q, size(q, 2), logp, out))
+  end
+  return out
+end
+
+function b200_sample(mkd::ManifoldKernelDensity, n::Integer; seed::UInt64 = rand(UInt64), stream::Integer = 0, ctx::Context = context())
+  mu = getPoints(mkd.belief); sigma = vec(getBW(mkd.belief)[:, 1])
+  d, N = size(mu)
+  out = zeros(d, n)
+  circ = _circular(mkd.manifold)
+  lock(ctx.lk) do
+    _check(ctx, ccall((:cb2_kde_sample, libcb2), Cint,
+                      (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Cint, Ptr{UInt8}, Cint, UInt64, UInt32, Ptr{Float64}),
+                      ctx.h, mu, sigma, C_NULL, d, N, circ, n, seed, UInt32(stream), out))
+  end
+  return out   # coordinates; the caller maps them to manifold points exactly as AMP.sample does
+end
+
+# ------------------------------------------------------------------------------------------------ products
+# One batched pass over B independent products (all variables of a Gibbs sweep / all ready cliques).
+# groups[b] is the Vector{ManifoldKernelDensity} that IIF.propagateBelief hands to AMP.manifoldProduct.
+function b200_products(groups::Vector{<:Vector{<:ManifoldKernelDensity}}, M; N::Vector{Int}, Niter::Int = 1,
+                       seed::UInt64 = rand(UInt64), streams = collect(0:length(groups)-1), ctx::Context = context())
+  B = length(groups)
+  d = manifold_dimension(M)
+  circ = _circular(M)
+  keep = Any[]
+  dens = [Vector{CB2Density}(undef, length(g)) for g in groups]
+  outs = [zeros(d, N[b]) for b in 1:B]
+  labels = [zeros(Int32, length(groups[b]), N[b]) for b in 1:B]
+  bws = [zeros(d) for _ in 1:B]
+  descs = Vector{CB2ProductDesc}(undef, B)
+  for b in 1:B
+    for (j, mkd) in enumerate(groups[b])
+      pts = getPoints(mkd.belief); bw = vec(getBW(mkd.belief)[:, 1])
+      push!(keep, pts, bw)
+      dens[b][j] = CB2Density(size(pts, 2), pointer(pts), pointer(bw), C_NULL)
+    end
+    descs[b] = CB2ProductDesc(pointer(dens[b]), length(groups[b]), N[b], Niter, UInt32(streams[b]), 0,
+                              pointer(outs[b]), pointer(labels[b]), pointer(bws[b]))
+  end
+  GC.@preserve keep dens outs labels bws descs begin
+    lock(ctx.lk) do
+      _check(ctx, ccall((:cb2_product_batch, libcb2), Cint, (Ptr{Cvoid}, Ptr{CB2ProductDesc}, Cint, Ptr{UInt8}, Cint, UInt64),
+                        ctx.h, descs, B, circ, d, seed))
+    end
+  end
+  return outs, bws, labels
+end
+
+# drop-in for AMP.manifoldProduct(ff, M; Niter, N): Gibbs product on the device, fresh LOO bandwidth, new MKD
+function ApproxManifoldProducts.manifoldProduct(ff::AbstractVector{<:ManifoldKernelDensity}, M::AbstractManifold = ff[1].manifold;
+                                                Niter::Int = 1, N::Int = maximum(Npts.(ff)), kw...)
+  length(ff) == 1 && return ff[1]                     # upstream early-out: one input is returned unchanged
+  outs, bws, _ = b200_products([collect(ff)], M; N = [N], Niter)
+  e0 = identity_element(M)
+  pts = [exp(M, e0, hat(M, e0, view(outs[1], :, i))) for i in 1:N]
+  return manikde!(M, pts; bw = bws[1])
+end
+
+# ------------------------------------------------------------------------------------------------ ScatterAlign getSample
+# drop-in body for Caesar's getSample(cf::CalcFactor{<:ScatterAlignPose2/3}) (ext/Images/ScatterAlignPose2.jl:155-187):
+# K alignments (one per particle of the solver) as one batched BFGS on the device.
+function b200_scatter_align(cloud1::ManifoldKernelDensity, cloud2::ManifoldKernelDensity, dim::Int, sample_count::Int, bw::Real,
+                            x0::AbstractMatrix{Float64}; seed::UInt64 = rand(UInt64), max_iter::Int = 200, g_tol::Real = 1e-8,
+                            ctx::Context = context())
+  K = size(x0, 2)
+  p1 = getPoints(cloud1.belief); b1 = vec(getBW(cloud1.belief)[:, 1])
+  p2 = getPoints(cloud2.belief); b2 = vec(getBW(cloud2.belief)[:, 1])
+  coords = zeros(size(x0)); score = zeros(K); iters = zeros(Int32, K)
+  GC.@preserve p1 b1 p2 b2 begin
+    d1 = Ref(CB2Density(size(p1, 2), pointer(p1), pointer(b1), C_NULL))
+    d2 = Ref(CB2Density(size(p2, 2), pointer(p2), pointer(b2), C_NULL))
+    lock(ctx.lk) do
+      _check(ctx, ccall((:cb2_scatter_align, libcb2), Cint,
+                        (Ptr{Cvoid}, Ref{CB2Density}, Ref{CB2Density}, Cint, Cint, Float64, Ptr{Float64}, Cint, UInt64, Cint, Float64,
+                         Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+                        ctx.h, d1, d2, dim, sample_count, Float64(bw), x0, K, seed, max_iter, Float64(g_tol), coords, score, iters))
+    end
+  end
+  return coords, score, iters
+end
+
+end # module

@@ -61,6 +61,12 @@ def num_threads():
     return lib().cb2o_num_threads()
 
 
+def use_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs ask for every host core explicitly."""
+    lib().cb2o_set_num_threads(len(os.sched_getaffinity(0)))
+    return num_threads()
+
+
 def philox(ctr, key):
     c = np.asarray(ctr, dtype=np.uint32)
     k = np.asarray(key, dtype=np.uint32)

@@ -525,3 +525,12 @@ int cb2o_product(const cb2o_density* dens, int D, const uint8_t* circ, int d, in
   free(tr);
   return 0;
 }
+
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs of bench.py ask for all host cores explicitly */
+void cb2o_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}

@@ -87,6 +87,7 @@ const double* cb2o_tree_level_var(const cb2o_tree* t, int level);  /* cnt x d */
 const double* cb2o_tree_level_wt(const cb2o_tree* t, int level);   /* cnt */
 
 int cb2o_num_threads(void);
+void cb2o_set_num_threads(int n);
 
 #ifdef __cplusplus
 }
