@@ -3,10 +3,14 @@
 //
 // A "problem" is one coordinate of one density: N scalars.  The golden-section search state of every problem
 // lives on the device; each iteration is two launches for the whole batch (no host round trip):
-//   loo_rows_kernel   : for every active problem, sum_i log( sum_{j != i} exp2(-(x_i-x_j)^2 c(h)) ), one CTA per
-//                       (problem, block of 1024 rows), rows in registers, columns broadcast from shared memory
-//   golden_step_kernel: one thread per problem folds the row-block partials in fixed order, turns them into
-//                       the objective value and advances that problem's bracket.
+//   loo_sort_init_kernel : once: sorts the coordinate (shared-memory bitonic sort, FP64), derives the bracket from
+//                          the smallest neighbour gap and the range
+//   loo_rows_kernel      : for every active problem, sum_i log( sum_{j != i} exp2(-(x_i-x_j)^2 c(h)) ), one CTA per
+//                          (problem, block of 1024 sorted rows), rows in registers, columns broadcast from shared
+//                          memory.  On sorted data a column tile that is farther than the flush-to-zero radius from
+//                          the whole row block contributes exactly 0 and is skipped (bit-identical result).
+//   golden_step_kernel   : one thread per problem folds the row-block partials in fixed order, turns them into
+//                          the objective value and advances that problem's bracket.
 // The bracket and the update rule follow Ihler's `ksize(..., 'lcv')` / `golden` as restated in oracle/cb2_oracle.c.
 #include "common.cuh"
 
@@ -15,6 +19,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kRI = 4;
 constexpr int kCT = 1024;
+constexpr int kSortThreads = 1024;
 constexpr double kTol = 1e-2;
 
 struct LooProblem {
@@ -24,6 +29,7 @@ struct LooProblem {
   int circular;
   int part0;        // first slot in the row-block partial array
   int nrb;
+  long long xs_off; // offset of this problem's sorted copy in the xs scratch
 };
 
 struct LooState {
@@ -34,102 +40,129 @@ struct LooState {
   double result;
 };
 
-// one thread per problem: bracket from the smallest neighbour gap and the data range
-__global__ void loo_init_kernel(const LooProblem* __restrict__ probs, int P, LooState* __restrict__ st,
-                                double* __restrict__ sortbuf) {
-  int p = blockIdx.x;
-  if (p >= P) return;
-  const LooProblem pr = probs[p];
-  // block-wide min gap: every thread scans a slice for its nearest right neighbour (O(N^2 / threads), N <= 16K)
-  __shared__ double smin[kThreads], slo[kThreads], shi[kThreads];
-  double mn = 1e300, lo = 1e300, hi = -1e300;
-  for (int i = threadIdx.x; i < pr.N; i += blockDim.x) {
-    double xi = pr.x[(size_t)i * pr.stride];
-    lo = fmin(lo, xi); hi = fmax(hi, xi);
-    double best = 1e300;
-    for (int j = 0; j < pr.N; ++j) {
-      double xj = pr.x[(size_t)j * pr.stride];
-      double g = xj - xi;
-      // nearest neighbour at or to the right (ties broken by index so duplicates give gap 0 once)
-      if ((g > 0 || (g == 0 && j > i)) && g < best) best = g;
-    }
-    mn = fmin(mn, best);
-  }
-  smin[threadIdx.x] = mn; slo[threadIdx.x] = lo; shi[threadIdx.x] = hi;
+// one CTA per problem: sorted copy + golden-section bracket
+__global__ void __launch_bounds__(kSortThreads)
+loo_sort_init_kernel(const LooProblem* __restrict__ probs, LooState* __restrict__ st, double* __restrict__ xs_all) {
+  extern __shared__ __align__(16) double skey[];
+  __shared__ double sred[kSortThreads / 32];
+  const LooProblem pr = probs[blockIdx.x];
+  const int N = pr.N, tid = threadIdx.x, nthr = blockDim.x;
+  int P2 = 1;
+  while (P2 < N) P2 <<= 1;
+  for (int i = tid; i < P2; i += nthr) skey[i] = i < N ? pr.x[(size_t)i * pr.stride] : 1.7976931348623157e308;
   __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      smin[threadIdx.x] = fmin(smin[threadIdx.x], smin[threadIdx.x + o]);
-      slo[threadIdx.x] = fmin(slo[threadIdx.x], slo[threadIdx.x + o]);
-      shi[threadIdx.x] = fmax(shi[threadIdx.x], shi[threadIdx.x + o]);
+  for (int k = 2; k <= P2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P2; i += nthr) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          double a = skey[i], b = skey[ixj];
+          bool up = (i & k) == 0;
+          if ((b < a) == up) { skey[i] = b; skey[ixj] = a; }
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
+  double* xs = xs_all + pr.xs_off;
+  double mn = 1e300;
+  for (int i = tid; i < N; i += nthr) {
+    xs[i] = skey[i];
+    if (i + 1 < N) mn = fmin(mn, skey[i + 1] - skey[i]);
   }
-  if (threadIdx.x == 0) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if ((tid & 31) == 0) sred[tid >> 5] = mn;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < nthr / 32; ++w) mn = fmin(mn, sred[w]);
     LooState s;
-    double m = smin[0] < 1e-6 ? 1e-6 : smin[0];
-    double range = shi[0] - slo[0];
+    double m = mn < 1e-6 ? 1e-6 : mn;
+    double range = skey[N - 1] - skey[0];
     if (!(range >= 1e-6)) {
       s.phase = 3; s.result = 1e-6; s.h_eval = 1.0;
       s.x0 = s.x1 = s.x2 = s.x3 = s.f1 = s.f2 = 0; s.slot = 0;
-      st[p] = s;
-      return;
+    } else {
+      const double C = (3.0 - sqrt(5.0)) / 2.0;
+      double ax = 2.0 * m / (1.0 + sqrt(5.0)), bx = m, cx = 2.0 * range;
+      s.x0 = ax; s.x3 = cx;
+      if (fabs(cx - bx) > fabs(bx - ax)) { s.x1 = bx; s.x2 = bx + C * (cx - bx); }
+      else { s.x2 = bx; s.x1 = bx - C * (bx - ax); }
+      s.f1 = s.f2 = 0; s.phase = 0; s.slot = 1; s.h_eval = s.x1; s.result = 0;
     }
-    const double C = (3.0 - sqrt(5.0)) / 2.0;
-    double ax = 2.0 * m / (1.0 + sqrt(5.0)), bx = m, cx = 2.0 * range;
-    s.x0 = ax; s.x3 = cx;
-    if (fabs(cx - bx) > fabs(bx - ax)) { s.x1 = bx; s.x2 = bx + C * (cx - bx); }
-    else { s.x2 = bx; s.x1 = bx - C * (bx - ax); }
-    s.f1 = s.f2 = 0; s.phase = 0; s.slot = 1; s.h_eval = s.x1; s.result = 0;
-    st[p] = s;
+    st[blockIdx.x] = s;
   }
-  (void)sortbuf;
 }
+
+template <typename T> struct ZeroRadius;  // |scaled difference| beyond which exp2(-d^2) is exactly 0 in T
+template <> struct ZeroRadius<float> { static constexpr double value = 11.4; };   // d^2 > 129: below FP32 min normal (ftz)
+template <> struct ZeroRadius<double> { static constexpr double value = 33.0; };  // d^2 > 1089: below FP64 denormals
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict__ st, const int2* __restrict__ cta_map,
-                double* __restrict__ partial) {
+                const double* __restrict__ xs_all, double* __restrict__ partial) {
   const int2 cm = cta_map[blockIdx.x];  // (problem, row block)
   const LooState s = st[cm.x];
   if (s.phase == 3) return;
   const LooProblem pr = probs[cm.x];
+  const double* __restrict__ xs = xs_all + pr.xs_off;
   __shared__ T sx[kCT];
   __shared__ double sred[kThreads / 32];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, N = pr.N;
   // exponent in base 2: (x_i - x_j)^2 * 0.5*log2e/h^2 -> pre-scale the coordinates by sc
   const double sc = sqrt(0.5 * CB2_LOG2E) / s.h_eval;
-  const double x_first = pr.x[0];  // common shift keeps FP32 differences accurate
+  const bool circ = pr.circular != 0;
+  // common shift keeps FP32 differences accurate; circular coordinates are wrapped to [-pi, pi] instead, so that
+  // |x_i - x_j| <= 2 pi and the wrapped distance is min(|d|, 2 pi - |d|)
+  const double x_mid = circ ? 0.0 : xs[N >> 1];
   const T period = (T)(CB2_TWO_PI * sc);
-  const T inv_period = (T)(1.0 / (CB2_TWO_PI * sc));
   T xi[kRI], acc[kRI];
   int rowi[kRI];
   const int rbase = cm.y * (kThreads * kRI);
+  const int rend = min(rbase + kThreads * kRI, N);
 #pragma unroll
   for (int r = 0; r < kRI; ++r) {
     int row = rbase + r * kThreads + tid;
     rowi[r] = row;
-    int rr = row < pr.N ? row : 0;
-    xi[r] = (T)((pr.x[(size_t)rr * pr.stride] - x_first) * sc);
+    double v = xs[row < N ? row : rbase];
+    xi[r] = (T)(((circ ? wrap_pi(v) : v) - x_mid) * sc);
     acc[r] = T(0);
   }
-  for (int cs = 0; cs < pr.N; cs += kCT) {
+  const double row_lo = xs[rbase], row_hi = xs[rend - 1];
+  const double zero_r = ZeroRadius<T>::value / sc;
+  for (int cs = 0; cs < N; cs += kCT) {
+    const int cend = min(cs + kCT, N);
+    if (!circ) {  // sorted data: tiles entirely beyond the flush-to-zero radius contribute exactly 0
+      double gap = fmax(xs[cs] - row_hi, row_lo - xs[cend - 1]);
+      if (gap > zero_r) continue;
+    }
     __syncthreads();
     for (int j = tid; j < kCT; j += kThreads) {
       int col = cs + j;
-      sx[j] = col < pr.N ? (T)((pr.x[(size_t)col * pr.stride] - x_first) * sc) : T(1e18);
+      if (col < N) { double v = xs[col]; sx[j] = (T)(((circ ? wrap_pi(v) : v) - x_mid) * sc); }
+      else sx[j] = T(1e18);
     }
     __syncthreads();
-    // the diagonal (j == i) only meets this sub-tile if it overlaps the CTA's rows
+    // the diagonal (j == i) only meets this tile if it overlaps the CTA's rows
     const bool has_diag = cs < rbase + kThreads * kRI && cs + kCT > rbase;
-    if (has_diag || pr.circular) {
-      const int jn = min(kCT, pr.N - cs);  // no padding columns here: the wrap would fold the sentinel back
+    const int jn = cend - cs;
+    if (circ) {
       for (int j = 0; j < jn; ++j) {
-        T q = sx[j];
+        const T q = sx[j];
+#pragma unroll
+        for (int r = 0; r < kRI; ++r) {
+          T ad = fabs(xi[r] - q);
+          T v = fmin(ad, period - ad);
+          T kv = fast_exp2(-(v * v));
+          acc[r] += (has_diag && cs + j == rowi[r]) ? T(0) : kv;
+        }
+      }
+    } else if (has_diag) {
+      for (int j = 0; j < jn; ++j) {
+        const T q = sx[j];
 #pragma unroll
         for (int r = 0; r < kRI; ++r) {
           T df = xi[r] - q;
-          if (pr.circular) df = df - period * rint_t(df * inv_period);
           T kv = fast_exp2(-(df * df));
           acc[r] += (cs + j == rowi[r]) ? T(0) : kv;
         }
@@ -137,7 +170,7 @@ loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict
     } else {
 #pragma unroll 8
       for (int j = 0; j < kCT; ++j) {
-        T q = sx[j];
+        const T q = sx[j];
 #pragma unroll
         for (int r = 0; r < kRI; ++r) {
           T df = xi[r] - q;
@@ -149,7 +182,7 @@ loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict
   double v = 0;
 #pragma unroll
   for (int r = 0; r < kRI; ++r)
-    if (rowi[r] < pr.N) {
+    if (rowi[r] < N) {
       double a = (double)acc[r];
       v += log(a > 2.2250738585072014e-308 ? a : 2.2250738585072014e-308);
     }
@@ -208,7 +241,8 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
   const int P = B * d;
   std::vector<LooProblem> probs(P);
   std::vector<int2> cta_map;
-  int nparts = 0;
+  int nparts = 0, maxN = 2;
+  long long xs_elems = 0;
   for (int b = 0; b < B; ++b)
     for (int k = 0; k < d; ++k) {
       LooProblem& pr = probs[(size_t)b * d + k];
@@ -216,11 +250,15 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
       pr.circular = circular ? circular[k] : 0;
       pr.nrb = (N[b] + kThreads * kRI - 1) / (kThreads * kRI);
       pr.part0 = nparts;
+      pr.xs_off = xs_elems;
+      xs_elems += (N[b] + 31) / 32 * 32;
       nparts += pr.nrb;
+      if (N[b] > maxN) maxN = N[b];
       for (int rb = 0; rb < pr.nrb; ++rb) cta_map.push_back(make_int2(b * d + k, rb));
     }
+  if (maxN > CB2_MAX_PRODUCT_N) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "bandwidth search supports N <= %d (got %d)", CB2_MAX_PRODUCT_N, maxN);
   size_t need = cb2_align(sizeof(LooProblem) * P) + cb2_align(sizeof(LooState) * P) + cb2_align(sizeof(int2) * cta_map.size()) +
-                cb2_align(sizeof(double) * nparts) + cb2_align(sizeof(int) * 64) + 1024;
+                cb2_align(sizeof(double) * nparts) + cb2_align(sizeof(int) * 64) + cb2_align(sizeof(double) * (size_t)xs_elems) + 1024;
   if (scratch_needed) *scratch_needed = need;
   if (!scratch) return CB2_OK;  // sizing query
   if (scratch_bytes < need) return cb2_fail(ctx, CB2_ERR_NOMEM, "loo scratch too small");
@@ -232,17 +270,23 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
   int2* map_dev = (int2*)take(sizeof(int2) * cta_map.size());
   double* partial = (double*)take(sizeof(double) * nparts);
   int* counters = (int*)take(sizeof(int) * 64);
+  double* xs_dev = (double*)take(sizeof(double) * (size_t)xs_elems);
   CB2_CUDA(ctx, cudaMemcpyAsync(probs_dev, probs.data(), sizeof(LooProblem) * P, cudaMemcpyHostToDevice, ctx->stream));
   CB2_CUDA(ctx, cudaMemcpyAsync(map_dev, cta_map.data(), sizeof(int2) * cta_map.size(), cudaMemcpyHostToDevice, ctx->stream));
   CB2_CUDA(ctx, cudaMemsetAsync(counters, 0, sizeof(int) * 64, ctx->stream));
-  loo_init_kernel<<<P, kThreads, 0, ctx->stream>>>(probs_dev, P, st_dev, nullptr);
-  CB2_CHECK_LAUNCH(ctx, "loo_init_kernel");
+  int P2 = 1;
+  while (P2 < maxN) P2 <<= 1;
+  size_t sort_smem = sizeof(double) * P2;
+  cudaError_t e = cudaFuncSetAttribute(loo_sort_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
+  if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "loo sort smem attribute: %s", cudaGetErrorString(e));
+  loo_sort_init_kernel<<<P, kSortThreads, sort_smem, ctx->stream>>>(probs_dev, st_dev, xs_dev);
+  CB2_CHECK_LAUNCH(ctx, "loo_sort_init_kernel");
   const int max_iter = 64, check_every = 8;
   for (int it = 0; it < max_iter; ++it) {
     if (ctx->precision == CB2_FP64)
-      loo_rows_kernel<double><<<(int)cta_map.size(), kThreads, 0, ctx->stream>>>(probs_dev, st_dev, map_dev, partial);
+      loo_rows_kernel<double><<<(int)cta_map.size(), kThreads, 0, ctx->stream>>>(probs_dev, st_dev, map_dev, xs_dev, partial);
     else
-      loo_rows_kernel<float><<<(int)cta_map.size(), kThreads, 0, ctx->stream>>>(probs_dev, st_dev, map_dev, partial);
+      loo_rows_kernel<float><<<(int)cta_map.size(), kThreads, 0, ctx->stream>>>(probs_dev, st_dev, map_dev, xs_dev, partial);
     CB2_CHECK_LAUNCH(ctx, "loo_rows_kernel");
     golden_step_kernel<<<(P + 127) / 128, 128, 0, ctx->stream>>>(probs_dev, P, partial, st_dev, counters + it);
     CB2_CHECK_LAUNCH(ctx, "golden_step_kernel");
