@@ -351,10 +351,61 @@ def mmd_extras(cb, ctx, torch, tstream, rank=0, world=1, dist=None):
     cpu_s = time.perf_counter() - t0
     sfu_peak = 148 * 16 * 1965e6
     assert abs(sharded_value - v) <= 1e-6 * max(abs(v), 1e-3), (sharded_value, v)
-    return {"mmd_pairs_per_s": pairs / (ms * 1e-3), "mmd_ms": ms, "mmd_points": P, "mmd_value": v, "mmd_row_shards": world,
-            "mmd_e2e_pairs_per_s": pairs / e2e_s, "mmd_sfu_frac": pairs / (ms * 1e-3) / sfu_peak,
-            "mmd_cpu_pairs_per_s": 3.0 * rows * P / cpu_s, "mmd_cpu_cores": oracle.num_threads(),
-            "mmd_cpu_sample": f"rows [0,{rows}) of each of the three pair sums against all {P} columns"}
+    out = {"mmd_pairs_per_s": pairs / (ms * 1e-3), "mmd_ms": ms, "mmd_points": P, "mmd_value": v, "mmd_row_shards": world,
+           "mmd_e2e_pairs_per_s": pairs / e2e_s, "mmd_sfu_frac": pairs / (ms * 1e-3) / sfu_peak,
+           "mmd_cpu_pairs_per_s": 3.0 * rows * P / cpu_s, "mmd_cpu_cores": oracle.num_threads(),
+           "mmd_cpu_sample": f"rows [0,{rows}) of each of the three pair sums against all {P} columns"}
+    # K2: one BFGS evaluation batch of ScatterAlignPose3 = K=13 candidate transforms (value + 2*6 finite-difference
+    # points in the reference; here value + analytic gradient for each), cross term only, transform fused in-kernel
+    K = 13
+    coords = np.array([2.0, 0, 2.0, 0, 0, np.pi / 10]) + 0.05 * rng.normal(size=(K, 6))
+    vals = np.zeros(K)
+    grads = np.zeros((K, 6))
+    with torch.cuda.stream(tstream):
+        run2 = lambda: ctx.check(L.cb2_mmd_se_batch_dev(ctx._h, C.c_void_p(da.data_ptr()), P, C.c_void_p(db.data_ptr()), P, 3, 1.0,
+                                                        coords.ctypes.data_as(C.c_void_p), K, 1, vals.ctypes.data_as(C.c_void_p),
+                                                        grads.ctypes.data_as(C.c_void_p)))
+        run2()
+        t0 = time.perf_counter()
+        run2()
+        se_s = time.perf_counter() - t0
+    Ps = 2000
+    t0 = time.perf_counter()
+    oracle.mmd_se_batch(a[:Ps], b, 1.0, coords[:1], backward=True)
+    cpu2 = time.perf_counter() - t0
+    out.update({"se_batch_K": K, "se_batch_s": se_s, "se_batch_pairs_per_s": (K + 3.0) * P * P / se_s,
+                "se_batch_note": "host-timed cb2_mmd_se_batch_dev: aa+bb pass, K cross terms with gradient moments, D2H of 8K doubles",
+                "se_batch_cpu_pairs_per_s": (Ps * Ps + Ps * P + float(P) * P) / cpu2,
+                "se_batch_cpu_sample": f"1 transform, a[:{Ps}] x b (value + gradient), oracle"})
+    # C1: ScatterAlignPose2 getSample on the 3-blob test clouds (sample_count=100), K=100 particles as one batched BFGS
+    c = np.array([[3.0, 0], [8.0, 0], [0, 5.0]])
+    p1 = np.concatenate([ci + 0.1 * rng.normal(size=(50, 2)) for ci in c])
+    p2 = oracle.transform_points(2, np.array([2.0, 0, np.pi / 6]), np.concatenate([ci + 0.1 * rng.normal(size=(50, 2)) for ci in c]), False)
+    sap = cb.ScatterAlignPose2(cloud1=cb.manikde("Point2", p1, ctx=ctx), cloud2=cb.manikde("Point2", p2, ctx=ctx), sample_count=100, bw=1.0)
+    cf = cb.CalcFactor(sap, cb.preambleCache(None, [], sap))
+    x0 = np.array([2.0, 0, np.pi / 6]) + np.c_[0.5 * rng.normal(size=(100, 2)), 0.1 * rng.normal(size=100)]
+    cb.getSample(cf, x0=x0[:4], seed=1, ctx=ctx)
+    t0 = time.perf_counter()
+    cs, score, iters = cb.getSample(cf, x0=x0, seed=2, ctx=ctx, return_info=True)
+    sap_s = time.perf_counter() - t0
+    out.update({"sap2_getsample_ms_per_particle": sap_s * 1e3 / 100, "sap2_particles": 100, "sap2_mean_bfgs_iters": float(iters.mean()),
+                "sap2_median_abs_err": [float(x) for x in np.median(np.abs(cs - np.array([2.0, 0, np.pi / 6])), axis=0)]})
+    # C2: hexagonal Pose2 SLAM through the caller harness (caesar.jl_b200/solver.py), third headline of BASELINE.json
+    solver = import_module("caesar_jl_b200.solver")
+    from oracle.solver_backend import OracleBackend
+    hexr = {}
+    for Np in (100, 1000):
+        solver.solveGraph(solver.generateGraph_Hexagonal(N=Np), solver.DeviceBackend(cb, ctx), gibbs_iters=1, seed=0)  # warm-up
+        fg = solver.generateGraph_Hexagonal(N=Np)
+        st = solver.solveGraph(fg, solver.DeviceBackend(cb, ctx), gibbs_iters=3, seed=1)
+        fgo = solver.generateGraph_Hexagonal(N=Np)
+        sto = solver.solveGraph(fgo, OracleBackend(ubits=24), gibbs_iters=3, seed=1)
+        x6 = solver.getPPE(fg.variables["x6"].belief)
+        hexr[f"N{Np}"] = {"solve_s": st["seconds"], "products": st["products"], "product_calls": st["product_calls"], "shapes": st["shapes"],
+                          "t_products_s": st["t_products"], "t_bandwidth_s": st["t_bandwidth"], "x6_ppe": [float(v) for v in x6],
+                          "cpu_oracle_solve_s": sto["seconds"], "cpu_t_products_s": sto["t_products"], "cpu_t_bandwidth_s": sto["t_bandwidth"]}
+    out["hex_pose2_solve"] = hexr
+    return out
 
 
 if __name__ == "__main__":

@@ -36,6 +36,7 @@ struct cb2_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cb2_arena arena;       // device scratch
+  cb2_arena io;          // grow-only device block for the host-pointer API's staged inputs / outputs
   char* pinned = nullptr;  // pinned host staging
   size_t pinned_cap = 0;
   uint64_t launches = 0;
@@ -74,6 +75,7 @@ int cb2_fail(cb2_ctx* ctx, int code, const char* fmt, ...);
 int cb2_arena_reserve(cb2_ctx* ctx, size_t bytes);  // ensure capacity (may reallocate: only call when off==0)
 void* cb2_arena_alloc(cb2_ctx* ctx, size_t bytes);  // nullptr when out of reserved space
 int cb2_pinned_reserve(cb2_ctx* ctx, size_t bytes);
+void* cb2_io_block(cb2_ctx* ctx, size_t bytes);  // staged I/O of synchronous host-pointer calls (no per-call cudaMalloc/cudaFree)
 void cb2_resolve_product_stages(cb2_ctx* ctx);  // product.cu: turns recorded events into stage_ms
 
 static inline size_t cb2_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }

@@ -72,6 +72,7 @@ extern "C" void cb2_destroy(cb2_ctx* ctx) {
   for (int i = 0; i < 8; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
+  if (ctx->io.base) cudaFree(ctx->io.base);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -129,6 +130,25 @@ void* cb2_arena_alloc(cb2_ctx* ctx, size_t bytes) {
   if (o + bytes > ctx->arena.cap) return nullptr;
   ctx->arena.off = o + bytes;
   return ctx->arena.base + o;
+}
+
+void* cb2_io_block(cb2_ctx* ctx, size_t bytes) {
+  bytes = cb2_align(bytes, 1 << 20);
+  if (bytes <= ctx->io.cap) return ctx->io.base;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cb2_fail(ctx, CB2_ERR_CUDA, "stream sync before I/O block growth failed"); return nullptr; }
+  if (ctx->io.base) cudaFree(ctx->io.base);
+  ctx->io.base = nullptr;
+  ctx->io.cap = 0;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cb2_fail(ctx, CB2_ERR_NOMEM, "device I/O block of %zu bytes: %s", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  ctx->io.base = (char*)p;
+  ctx->io.cap = bytes;
+  return p;
 }
 
 int cb2_pinned_reserve(cb2_ctx* ctx, size_t bytes) {

@@ -150,19 +150,23 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
                                           uint32_t circ, T* __restrict__ chunk, int tid, T& m, T& csum, int& cidx) {
   constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
   constexpr int REC = MODE == 0 ? RECN : RECL;
-  constexpr int G = 4;
+  constexpr int G = kG;
   const int ntg = nt & ~(G - 1);
   T nm = -m;
   for (int z = 0; z < ntg; z += G) {
     T e[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) e[g] = score_any_s<T, DIM, MODE>(tb + (z + g) * REC, cc, circ, nm);
-    T gm = fmax(fmax(e[0], e[1]), fmax(e[2], e[3]));
+    T gm = e[0];
+#pragma unroll
+    for (int g = 1; g < G; ++g) gm = fmax(gm, e[g]);
     if (gm > T(60)) {  // rare: raise the reference by gm and rescale what has been summed so far
       if (nm == INFINITY) {  // first group of the pass: scores were computed against m = -inf, nothing summed yet
 #pragma unroll
         for (int g = 0; g < G; ++g) e[g] = score_any_s<T, DIM, MODE>(tb + (z + g) * REC, cc, circ, T(0));
-        gm = fmax(fmax(e[0], e[1]), fmax(e[2], e[3]));
+        gm = e[0];
+#pragma unroll
+        for (int g = 1; g < G; ++g) gm = fmax(gm, e[g]);
         m = gm;
       } else {
         T sc = fast_exp2(-gm);
@@ -263,7 +267,7 @@ gibbs_kernel(const GibbsArgs a) {
   constexpr int TILE_BYTES = kTileBytesF32 * (int)(sizeof(T) / 4);
   constexpr int TN_NODE = TILE_BYTES / (RECN * (int)sizeof(T));
   constexpr int TN_LEAF = TILE_BYTES / (RECL * (int)sizeof(T));
-  constexpr int G = 4;  // candidates scored together (ILP, see tile_pass); tiles and chunks are multiples of G
+  constexpr int G = kG;  // candidates scored together (ILP, see tile_pass); tiles and chunks are multiples of G
   const uint32_t circ = CIRC == ~0u ? a.circ_mask : CIRC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* tile[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw + TILE_BYTES)};

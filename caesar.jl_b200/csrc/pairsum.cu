@@ -529,23 +529,23 @@ extern "C" int cb2_mmd_sums_dev(cb2_ctx* ctx, const double* a_dev, int N, const 
                                     : mmd_sums_dev_impl<float>(ctx, a_dev, N, b_dev, M, d, bw, ra0, ra1, rb0, rb1, sums3_dev);
 }
 
-// uploads host Float64 arrays into one fresh device block (caller frees); used by the host-pointer API
+// uploads host Float64 arrays into the context's I/O block; used by the (synchronous) host-pointer API
 static int upload_block(cb2_ctx* ctx, const std::vector<const double*>& src, const std::vector<size_t>& count,
                         std::vector<double*>& dev, double** block) {
   size_t total = 0;
   for (size_t c : count) total += cb2_align(c * sizeof(double));
   total += 256;
-  void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, total);
-  if (e != cudaSuccess) { cudaGetLastError(); return cb2_fail(ctx, CB2_ERR_NOMEM, "device input block of %zu bytes: %s", total, cudaGetErrorString(e)); }
-  *block = (double*)p;
+  void* p = cb2_io_block(ctx, total);  // context-owned, reused across calls (the callers' cudaFree(block) is a no-op)
+  if (!p) return CB2_ERR_NOMEM;
+  *block = nullptr;
+  cudaError_t e = cudaSuccess;
   size_t off = 0;
   dev.resize(src.size());
   for (size_t i = 0; i < src.size(); ++i) {
     dev[i] = (double*)((char*)p + off);
     if (count[i] && src[i]) {
       e = cudaMemcpyAsync(dev[i], src[i], count[i] * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-      if (e != cudaSuccess) { cudaFree(p); *block = nullptr; return cb2_fail(ctx, CB2_ERR_CUDA, "H2D copy: %s", cudaGetErrorString(e)); }
+      if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "H2D copy: %s", cudaGetErrorString(e));
     }
     off += cb2_align(count[i] * sizeof(double));
   }

@@ -29,6 +29,7 @@ constexpr int kTreeThreads = 1024;
 constexpr int kS = 256;            // chains (threads) per Gibbs CTA
 constexpr int kNCH = 32;           // chunk partial sums per chain
 constexpr int kTileBytesF32 = 16384;
+constexpr int kG = 8;              // candidates scored together by one chain (ILP); tiles and chunks are multiples of kG
 
 __host__ __device__ inline int recn_of(int d) { return (2 * d + 1 + 3) / 4 * 4; }  // [mu(d), var(d), log2 w]
 __host__ __device__ inline int recl_of(int d) { return (d + 1 + 3) / 4 * 4; }      // [mu(d), log2 w]
@@ -532,9 +533,17 @@ static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B
     if (ds.labels_out) total += cb2_align(sizeof(int32_t) * (size_t)ds.Nout * ds.D);
     if (ds.bw_out) total += cb2_align(sizeof(double) * d);
   }
+  // synchronous calls stage through the context's I/O block; a ticketed (asynchronous) batch owns its block until cb2_wait
+  const bool own = pend != nullptr;
   void* blk = nullptr;
-  cudaError_t e = cudaMalloc(&blk, total + 256);
-  if (e != cudaSuccess) { cudaGetLastError(); return cb2_fail(ctx, CB2_ERR_NOMEM, "device block of %zu bytes: %s", total, cudaGetErrorString(e)); }
+  cudaError_t e = cudaSuccess;
+  if (own) {
+    e = cudaMalloc(&blk, total + 256);
+    if (e != cudaSuccess) { cudaGetLastError(); return cb2_fail(ctx, CB2_ERR_NOMEM, "device block of %zu bytes: %s", total, cudaGetErrorString(e)); }
+  } else {
+    blk = cb2_io_block(ctx, total + 256);
+    if (!blk) return CB2_ERR_NOMEM;
+  }
   char* p = (char*)blk;
   size_t off = 0;
   auto take = [&](size_t n) { char* q = p + off; off += cb2_align(n); return q; };
@@ -564,7 +573,7 @@ static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B
     dd[b].bw_out = descs[b].bw_out ? (double*)take(sizeof(double) * d) : nullptr;
   }
   if (rc == CB2_OK) { cudaEventRecord(ctx->ev[5], ctx->stream); rc = product_batch_dev_locked(ctx, dd.data(), B, circular, d, seed, &bw_host, nullptr); }
-  if (rc != CB2_OK) { cudaStreamSynchronize(ctx->stream); cudaFree(blk); return rc; }
+  if (rc != CB2_OK) { cudaStreamSynchronize(ctx->stream); if (own) cudaFree(blk); return rc; }
   cudaEventRecord(ctx->ev[6], ctx->stream);
   for (int b = 0; b < B; ++b) {
     e = cudaMemcpyAsync(descs[b].pts_out, dd[b].pts_out, sizeof(double) * (size_t)descs[b].Nout * d, cudaMemcpyDeviceToHost, ctx->stream);
@@ -572,18 +581,18 @@ static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B
       e = cudaMemcpyAsync(descs[b].labels_out, dd[b].labels_out, sizeof(int32_t) * (size_t)descs[b].Nout * descs[b].D, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && descs[b].bw_out)
       e = cudaMemcpyAsync(descs[b].bw_out, dd[b].bw_out, sizeof(double) * d, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e != cudaSuccess) { cudaStreamSynchronize(ctx->stream); cudaFree(blk); return cb2_fail(ctx, CB2_ERR_CUDA, "D2H copy: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { cudaStreamSynchronize(ctx->stream); if (own) cudaFree(blk); return cb2_fail(ctx, CB2_ERR_CUDA, "D2H copy: %s", cudaGetErrorString(e)); }
   }
   cudaEventRecord(ctx->ev[7], ctx->stream);
   if (pend) {  // asynchronous: hand the block to the ticket
     pend->dev_block = blk;
     e = cudaEventCreateWithFlags(&pend->done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventRecord(pend->done, ctx->stream);
-    if (e != cudaSuccess) { cudaStreamSynchronize(ctx->stream); cudaFree(blk); pend->dev_block = nullptr; return cb2_fail(ctx, CB2_ERR_CUDA, "ticket event: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { cudaStreamSynchronize(ctx->stream); if (own) cudaFree(blk); pend->dev_block = nullptr; return cb2_fail(ctx, CB2_ERR_CUDA, "ticket event: %s", cudaGetErrorString(e)); }
     return CB2_OK;
   }
   e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(blk);
+  if (own) cudaFree(blk);
   if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "product batch failed: %s", cudaGetErrorString(e));
   float ms = 0;
   if (cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ctx->stage_ms["h2d"] = ms;

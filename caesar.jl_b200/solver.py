@@ -1,0 +1,215 @@
+"""Caller harness for the batched product path: a small nonparametric Gibbs solver over Pose2 / Point2 graphs.
+
+This is NOT a port of IncrementalInference's Bayes-tree / clique-state-machine solver (out of scope).  It
+plays the role IIF's `propagateBelief` plays for the hot path -- per variable: one proposal per factor
+(`approxConvBelief`, closed form for the group factors used here: SURVEY sec. 8f N1), `manikde!` of every proposal,
+`manifoldProduct`, `manikde!` of the result -- and issues those products the way the Julia shim would: variables that
+share no factor are batched into ONE cb2_product_batch call per Gibbs colour (K6), proposals' LOO bandwidths in one
+cb2_kde_bw_loo_batch call.  Used for BASELINE config C2 (hexagonal Pose2 SLAM, `generateGraph_Hexagonal`;
+recipe R:docs/src/examples/basic_hexagonal2d.md:21-43,89-111) and as an end-to-end parity test of the product path.
+
+The whole graph is treated as one clique (what IIF does inside the root clique): `gibbs_iters` sweeps (IIF default 3)
+after a forward initialisation (`initAll!`).
+"""
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+TWO_PI = 2.0 * np.pi
+
+
+def _wrap(a):
+    return (a + np.pi) % TWO_PI - np.pi
+
+
+@dataclass
+class Variable:
+    label: str
+    vartype: str  # "Pose2" | "Point2"
+    belief: object = None  # ManifoldKernelDensity
+
+
+@dataclass
+class PriorPose2:
+    mean: np.ndarray
+    cov: np.ndarray
+
+
+@dataclass
+class Pose2Pose2:
+    mean: np.ndarray  # [dx, dy, dtheta] in the first pose's frame
+    cov: np.ndarray
+
+
+@dataclass
+class Pose2Point2BearingRange:
+    bearing: tuple  # (mean, sigma)
+    range: tuple
+
+
+@dataclass
+class FactorGraph:
+    variables: dict = field(default_factory=dict)
+    factors: list = field(default_factory=list)  # (labels, factor)
+    N: int = 100
+
+    def addVariable(self, label, vartype):
+        self.variables[label] = Variable(label, vartype)
+
+    def addFactor(self, labels, factor):
+        self.factors.append((list(labels), factor))
+
+    def factors_of(self, label):
+        return [(ls, f) for ls, f in self.factors if label in ls]
+
+
+def generateGraph_Hexagonal(N=100, landmark=True, loop_closure=True):
+    """RoME.generateGraph_Hexagonal as spelled out in R:docs/src/examples/basic_hexagonal2d.md."""
+    fg = FactorGraph(N=N)
+    fg.addVariable("x0", "Pose2")
+    fg.addFactor(["x0"], PriorPose2(np.zeros(3), 0.01 * np.eye(3)))
+    for i in range(6):
+        fg.addVariable(f"x{i + 1}", "Pose2")
+        fg.addFactor([f"x{i}", f"x{i + 1}"], Pose2Pose2(np.array([10.0, 0.0, np.pi / 3]), np.diag([0.1, 0.1, 0.1]) ** 2))
+    if landmark:
+        fg.addVariable("l1", "Point2")
+        fg.addFactor(["x0", "l1"], Pose2Point2BearingRange((0.0, 0.1), (20.0, 1.0)))
+        if loop_closure:
+            fg.addFactor(["x6", "l1"], Pose2Point2BearingRange((0.0, 0.1), (20.0, 1.0)))
+    return fg
+
+
+# ---------------------------------------------------------------- closed-form convolutions (approxConvBelief)
+def _compose(p, X):
+    """p o exp_e(X) on SE(2) with the product exponential (translation = coordinates)."""
+    c, s = np.cos(p[:, 2]), np.sin(p[:, 2])
+    return np.c_[p[:, 0] + c * X[:, 0] - s * X[:, 1], p[:, 1] + s * X[:, 0] + c * X[:, 1], _wrap(p[:, 2] + X[:, 2])]
+
+
+def _compose_inv(q, X):
+    """q o exp_e(X)^-1"""
+    th = _wrap(q[:, 2] - X[:, 2])
+    c, s = np.cos(th), np.sin(th)
+    return np.c_[q[:, 0] - (c * X[:, 0] - s * X[:, 1]), q[:, 1] - (s * X[:, 0] + c * X[:, 1]), th]
+
+
+def _resample(pts, N, rng):
+    return pts if len(pts) == N else pts[rng.integers(0, len(pts), size=N)]
+
+
+def approx_conv(fg, labels, factor, target, rng):
+    """Samples of `target` implied by `factor` and the current belief of the other variable (N points)."""
+    N = fg.N
+    if isinstance(factor, PriorPose2):
+        x = rng.multivariate_normal(factor.mean, factor.cov, size=N)
+        x[:, 2] = _wrap(x[:, 2])
+        return x
+    other = labels[0] if labels[1] == target else labels[1]
+    src = _resample(fg.variables[other].belief.pts, N, rng)
+    if isinstance(factor, Pose2Pose2):
+        X = rng.multivariate_normal(factor.mean, factor.cov, size=N)
+        return _compose(src, X) if target == labels[1] else _compose_inv(src, X)
+    if isinstance(factor, Pose2Point2BearingRange):
+        b = factor.bearing[0] + factor.bearing[1] * rng.standard_normal(N)
+        r = factor.range[0] + factor.range[1] * rng.standard_normal(N)
+        if target == labels[1]:  # pose -> landmark
+            return np.c_[src[:, 0] + r * np.cos(src[:, 2] + b), src[:, 1] + r * np.sin(src[:, 2] + b)]
+        # landmark -> pose: two constraints on three coordinates; the heading comes from the pose's current belief
+        th = _resample(fg.variables[target].belief.pts, N, rng)[:, 2]
+        return np.c_[src[:, 0] - r * np.cos(th + b), src[:, 1] - r * np.sin(th + b), th]
+    raise TypeError(f"unsupported factor {type(factor).__name__}")
+
+
+def _colouring(fg):
+    """Greedy colouring: variables of one colour share no factor and are updated in one batched product call."""
+    colour, order = {}, list(fg.variables)
+    for v in order:
+        nb = {l for ls, _ in fg.factors_of(v) for l in ls if l != v}
+        used = {colour[n] for n in nb if n in colour}
+        colour[v] = next(c for c in range(len(order)) if c not in used)
+    groups = {}
+    for v, c in colour.items():
+        groups.setdefault(c, []).append(v)
+    return [groups[c] for c in sorted(groups)]
+
+
+def solveGraph(fg, backend, gibbs_iters=3, seed=0, stats=None):
+    """backend: object with manikde_batch(vartype, [pts]) -> [MKD] and products(vartype, [[MKD]], N, seed, streams) -> [MKD].
+    Returns stats: wall seconds, number and shapes of products issued."""
+    rng = np.random.default_rng(seed)
+    stats = stats if stats is not None else {}
+    stats.update(products=0, shapes={}, product_calls=0, t_products=0.0, t_bandwidth=0.0)
+    t0 = time.perf_counter()
+    # forward initialisation (initAll!): a variable is initialised from the first factor whose other end already is
+    pending = list(fg.variables)
+    while pending:
+        progressed = False
+        for v in list(pending):
+            for ls, f in fg.factors_of(v):
+                others = [l for l in ls if l != v]
+                if all(fg.variables[o].belief is not None for o in others) and not (
+                        isinstance(f, Pose2Point2BearingRange) and v == ls[0]):
+                    pts = approx_conv(fg, ls, f, v, rng)
+                    fg.variables[v].belief = backend.manikde_batch(fg.variables[v].vartype, [pts])[0]
+                    pending.remove(v)
+                    progressed = True
+                    break
+        if not progressed:
+            raise RuntimeError(f"cannot initialise {pending}")
+    colours = _colouring(fg)
+    stream = 0
+    for it in range(gibbs_iters):
+        for group in colours:
+            for vartype in ("Pose2", "Point2"):
+                vs = [v for v in group if fg.variables[v].vartype == vartype]
+                if not vs:
+                    continue
+                props, counts = [], []
+                for v in vs:
+                    ps = [approx_conv(fg, ls, f, v, rng) for ls, f in fg.factors_of(v)]
+                    props += ps
+                    counts.append(len(ps))
+                tb = time.perf_counter()
+                mkds = backend.manikde_batch(vartype, props)
+                stats["t_bandwidth"] += time.perf_counter() - tb
+                groups, k = [], 0
+                for c in counts:
+                    groups.append(mkds[k:k + c])
+                    k += c
+                tp = time.perf_counter()
+                res = backend.products(vartype, groups, fg.N, seed * 100003 + it, list(range(stream, stream + len(vs))))
+                stats["t_products"] += time.perf_counter() - tp
+                stream += len(vs)
+                stats["product_calls"] += 1
+                for v, g, r in zip(vs, groups, res):
+                    fg.variables[v].belief = r
+                    if len(g) > 1:
+                        stats["products"] += 1
+                        key = f"D={len(g)},N={fg.N},d={r.d}"
+                        stats["shapes"][key] = stats["shapes"].get(key, 0) + 1
+    stats["seconds"] = time.perf_counter() - t0
+    return stats
+
+
+def getPPE(belief):
+    """Point estimate: Euclidean mean, circular mean on wrapped coordinates."""
+    out = []
+    for i, c in enumerate(belief.circular):
+        x = belief.pts[:, i]
+        out.append(np.arctan2(np.sin(x).mean(), np.cos(x).mean()) if c else x.mean())
+    return np.array(out)
+
+
+class DeviceBackend:
+    """Products and bandwidths through libcaesar_b200.so (the path under test)."""
+
+    def __init__(self, cb, ctx=None):
+        self.cb, self.ctx = cb, ctx or cb.context()
+
+    def manikde_batch(self, vartype, pts_list):
+        bws = self.cb.kde_bandwidth_batch(pts_list, vartype, ctx=self.ctx)
+        return [self.cb.ManifoldKernelDensity(vartype, p, b) for p, b in zip(pts_list, bws)]
+
+    def products(self, vartype, groups, N, seed, streams):
+        return self.cb.manifoldProducts(groups, vartype, N=N, Niter=1, seed=seed, streams=streams, bw="loo", ctx=self.ctx)

@@ -1,0 +1,62 @@
+"""BASELINE config C2: hexagonal Pose2 SLAM (generateGraph_Hexagonal, N=100 particles) solved through the batched
+device product path, compared with the same caller harness running on the CPU oracle."""
+import numpy as np
+import pytest
+
+from __graft_entry__ import build, load_package
+
+HEX_TRUTH = {"x0": (0, 0, 0), "x1": (10, 0, np.pi / 3), "x2": (15, 8.660254, 2 * np.pi / 3), "x3": (10, 17.320508, np.pi),
+             "x4": (0, 17.320508, -2 * np.pi / 3), "x5": (-5, 8.660254, -np.pi / 3), "x6": (0, 0, 0), "l1": (20, 0)}
+
+
+def _errors(solver, fg):
+    err = {}
+    for k, t in HEX_TRUTH.items():
+        ppe = solver.getPPE(fg.variables[k].belief)
+        e = ppe - np.array(t, dtype=float)
+        if len(t) == 3:
+            e[2] = (e[2] + np.pi) % (2 * np.pi) - np.pi
+        err[k] = e
+    return err
+
+
+def test_hex_solve_on_oracle_backend_recovers_hexagon():
+    """The caller harness itself (CPU oracle products): poses within the reference's own loose bands
+    (R:test/ICRA2022_tests/simple_graph.jl style PPE checks)."""
+    from importlib import import_module
+    load_package()
+    solver = import_module("caesar_jl_b200.solver")
+    from oracle.solver_backend import OracleBackend
+    fg = solver.generateGraph_Hexagonal(N=100)
+    st = solver.solveGraph(fg, OracleBackend(), gibbs_iters=3, seed=1)
+    err = _errors(solver, fg)
+    for k, e in err.items():
+        assert np.abs(e[:2]).max() < 1.5, (k, e)
+        if len(e) == 3:
+            assert abs(e[2]) < 0.2, (k, e)
+    assert st["products"] >= 3 * 7 and set(st["shapes"]) <= {"D=2,N=100,d=3", "D=3,N=100,d=3", "D=2,N=100,d=2"}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_hex_solve_on_device_matches_oracle_solve(precision):
+    from importlib import import_module
+    build()
+    cb = load_package()
+    solver = import_module("caesar_jl_b200.solver")
+    from oracle.solver_backend import OracleBackend
+    ctx = cb.Context(0, precision)
+    fg = solver.generateGraph_Hexagonal(N=100)
+    st = solver.solveGraph(fg, solver.DeviceBackend(cb, ctx), gibbs_iters=3, seed=1)
+    err = _errors(solver, fg)
+    for k, e in err.items():
+        assert np.abs(e[:2]).max() < 1.5, (k, e)
+        if len(e) == 3:
+            assert abs(e[2]) < 0.2, (k, e)
+    # same harness, same host RNG, products on the oracle: beliefs agree under the reference's mmd tolerance
+    fgo = solver.generateGraph_Hexagonal(N=100)
+    solver.solveGraph(fgo, OracleBackend(ubits=53 if precision == "fp64" else 24), gibbs_iters=3, seed=1)
+    for k in HEX_TRUTH:
+        a, b = fg.variables[k].belief, fgo.variables[k].belief
+        assert cb.mmd(a.pts[:, :2], b.pts[:, :2], bw=0.001, ctx=ctx) < 0.01, k  # insufficient_data.jl's tightest atol
+    assert st["products"] == 24 and st["product_calls"] <= 3 * 6
