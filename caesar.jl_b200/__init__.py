@@ -352,5 +352,6 @@ def tree_levels(pts, bw, w=None, ctx=None):
     return depth.value, perm, levels
 
 
-from .factors import ScatterAlign, ScatterAlignPose2, ScatterAlignPose3, CalcFactor, preambleCache, getSample  # noqa: E402
+from .factors import (ScatterAlign, ScatterAlignPose2, ScatterAlignPose3, CalcFactor, preambleCache, getSample,  # noqa: E402
+                      HeatmapGridDensity, ScatterAlignPose2_from_images)
 from .serialization import packDistribution, unpackDistribution  # noqa: E402

@@ -92,3 +92,40 @@ def getSample(cf, K=1, seed=0, x0=None, max_iter=200, g_tol=1e-8, ctx=None, retu
     if return_info:
         return coords, score, iters
     return coords
+
+
+class HeatmapGridDensity:
+    """IIF.HeatmapGridDensity(img, (x, y); N) as ScatterAlignPose2 uses it (R:ext/Images/ScatterAlignPose2.jl:23-24,
+    R:test/testScatterAlignPose2.jl:22-53): a grid image turned into a sampled belief.  Construction only (SURVEY
+    sec. 8a row a10): N points are drawn from the grid cells in proportion to the image values (jittered by the grid
+    spacing) with the device sampler, then wrapped as a ManifoldKernelDensity (`densityFnc`) with a LOO bandwidth."""
+
+    def __init__(self, img, domain, N=1000, seed=0, ctx=None):
+        from . import ManifoldKernelDensity, manikde, sample
+        img = np.asarray(img, dtype=np.float64)
+        x, y = (np.asarray(v, dtype=np.float64) for v in domain)
+        if img.shape != (len(x), len(y)):
+            raise ValueError("image shape does not match the domain")
+        w = np.clip(img, 0.0, None).ravel()
+        if not w.sum() > 0:
+            raise ValueError("heatmap has no positive mass")
+        keep = w > w.max() * 1e-9
+        gx, gy = np.meshgrid(x, y, indexing="ij")
+        cells = np.c_[gx.ravel()[keep], gy.ravel()[keep]]
+        spacing = np.array([np.mean(np.diff(x)), np.mean(np.diff(y))])
+        grid = ManifoldKernelDensity("Point2", cells, spacing / 2.0, weights=w[keep])
+        pts, = sample(grid, int(N), seed=seed, ctx=ctx)
+        self.data, self.domain, self.N = img, (x, y), int(N)
+        self.densityFnc = manikde("Point2", pts, ctx=ctx)
+
+    # the factor treats a heatmap cloud exactly like the MKD it wraps
+    def __getattr__(self, name):
+        return getattr(self.__dict__["densityFnc"], name)
+
+
+def ScatterAlignPose2_from_images(im1, im2, domain, sample_count=75, bw=5e-5, N=1000, seed=0, ctx=None, **kw):
+    """ScatterAlignPose2(im1, im2, domain; sample_count, bw, N) -- the image constructor of the reference
+    (R:ext/Images/ScatterAlignPose2.jl:4-34; `cvt`/`rescale` image resizing is left to the caller)."""
+    c1 = HeatmapGridDensity(im1, domain, N=N, seed=seed, ctx=ctx)
+    c2 = HeatmapGridDensity(im2, domain, N=N, seed=seed + 1, ctx=ctx)
+    return ScatterAlignPose2(cloud1=c1.densityFnc, cloud2=c2.densityFnc, sample_count=sample_count, bw=bw, **kw)

@@ -1,0 +1,107 @@
+"""BASELINE.json configs as parity-test cases on the device: C1 heatmap ScatterAlignPose2, C3 ScatterAlignPose3 clouds
+(mmd + alignment), C4 multihypo four-mode products (N=1000)."""
+import numpy as np
+import pytest
+
+import oracle
+from __graft_entry__ import build, load_package
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb():
+    build()
+    return load_package()
+
+
+@pytest.fixture(scope="module", params=["fp32", "fp64"])
+def ctx(request, cb):
+    return cb.Context(0, request.param)
+
+
+def test_c1_heatmap_scatter_align_pose2(cb, ctx):
+    """R:test/testScatterAlignPose2.jl:19-69: 301x301 heatmaps of three Gaussians, true pCq = [5, 0, pi/8],
+    N=1000, sample_count=100, bw=1.0; recovery within 1.5 m / 0.2 rad (:68-69)."""
+    x = np.arange(-15, 15.0001, 0.1)
+    gx, gy = np.meshgrid(x, x, indexing="ij")
+
+    def g(px, py):
+        f = lambda cx, cy, s: np.exp(-0.5 * ((px - cx) ** 2 + (py - cy) ** 2) / s) / (2 * np.pi * s)
+        return f(3.0, 0.0, 0.1) + f(8.0, 0.0, 0.4) + f(0.0, 5.0, 0.1)
+
+    pCq = np.array([5.0, 0.0, np.pi / 8])
+    R, t = oracle.se_matrix(2, pCq, backward=True)  # qTp = inv(exp(pCq))
+    im1 = g(gx, gy)
+    im2 = g(R[0, 0] * gx + R[0, 1] * gy + t[0], R[1, 0] * gx + R[1, 1] * gy + t[1])
+    sap = cb.ScatterAlignPose2_from_images(im1, im2, (x, x), sample_count=100, bw=1.0, N=1000, ctx=ctx)
+    assert sap.align.cloud1.N == 1000 and sap.align.cloud1.d == 2
+    s, = cb.sample(sap.align.cloud1, 10, ctx=ctx)
+    assert s.shape == (10, 2)  # `sample(sap.align.cloud2,10)[1] isa AbstractArray` (:56-57)
+    cf = cb.CalcFactor(sap, cb.preambleCache(None, [], sap))
+    rng = np.random.default_rng(0)
+    x0 = pCq + np.c_[0.7 * rng.normal(size=(24, 2)), 0.1 * rng.normal(size=24)]
+    coords, score, iters = cb.getSample(cf, x0=x0, seed=3, ctx=ctx, return_info=True)
+    best = coords[np.argmin(score)]
+    assert np.abs(best[:2] - pCq[:2]).max() < 1.5 and abs(best[2] - pCq[2]) < 0.2
+    assert np.abs(np.median(coords, axis=0) - pCq).max() < 0.5
+
+
+def test_c3_scatter_align_pose3_clouds(cb, ctx):
+    """R:test/testScatterAlignPose3.jl:29-30 / testScatterAlignPose2.jl:271-299: randn(P,3) clouds, moved cloud offset
+    pCq = [2,0,2,0,0,pi/10], kde bandwidth 0.1 per axis (testScatterAlignParched.jl:41-42), mmd bw = 1."""
+    rng = np.random.default_rng(1)
+    P = 10000
+    X = rng.normal(size=(P, 3)) * [3.0, 1.5, 0.7]
+    pCq = np.array([2.0, 0, 2.0, 0, 0, np.pi / 10])
+    Xm = oracle.transform_points(3, pCq, X + 0.02 * rng.normal(size=X.shape), backward=False)
+    # full mmd on the 1e4-point clouds against the oracle (3e8 pairs: seconds on the CPU)
+    want, sums = oracle.mmd(X, Xm, 1.0, return_sums=True)
+    got = cb.mmd_sums(X, Xm, 1.0, ctx=ctx)
+    assert np.allclose(got, sums, rtol=1e-5 if ctx.precision == "fp32" else 1e-12)
+    # alignment from sampled subsets (sample_count = 500)
+    c1 = cb.MKD("Point3", X, [0.1, 0.1, 0.1])
+    c2 = cb.MKD("Point3", Xm, [0.1, 0.1, 0.1])
+    sap = cb.ScatterAlignPose3(cloud1=c1, cloud2=c2, sample_count=500, bw=1.0)
+    cf = cb.CalcFactor(sap, cb.preambleCache(None, [], sap))
+    x0 = pCq + np.c_[0.3 * rng.normal(size=(8, 3)), 0.05 * rng.normal(size=(8, 3))]
+    coords, score, iters = cb.getSample(cf, x0=x0, seed=4, ctx=ctx, return_info=True)
+    est = np.median(coords, axis=0)
+    assert np.abs(est[:3] - pCq[:3]).max() < 0.3 and np.abs(est[3:] - pCq[3:]).max() < 0.1
+    # 12-element SE(3) point from the coordinates (reference: the Pose3 sample is a 12-element ArrayPartition, :314-317)
+    R, t = oracle.se_matrix(3, est, backward=False)
+    assert R.size + t.size == 12 and np.allclose(R @ R.T, np.eye(3), atol=1e-12)
+
+
+def _four_mode_message(rng, N, centres, spread):
+    comp = rng.integers(0, len(centres), size=N)
+    pts = centres[comp] + rng.normal(size=(N, 3)) * spread
+    pts[:, 2] = (pts[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    return pts, 1.06 * pts.std(0) * N ** -0.2 * 0.5
+
+
+def test_c4_multihypo_four_mode_products(cb, ctx):
+    """Standalone C4 product: D=3 messages, each a 4-component mixture in (x, y, theta), N=1000;
+    only one corner is common to all three, so the product must concentrate there.  Device vs oracle: mode masses."""
+    rng = np.random.default_rng(2)
+    corners = np.array([[0, 0, 0.0], [10, 0, 1.5], [10, 10, 3.0], [0, 10, -1.5]])
+    spread = np.array([0.4, 0.4, 0.1])
+    msgs = []
+    for j in range(3):
+        cs = corners.copy()
+        cs[1:] += rng.normal(size=(3, 3)) * [3.0, 3.0, 0.5] * (j + 1)  # the other hypotheses disagree between messages
+        msgs.append(_four_mode_message(rng, 1000, cs, spread))
+    N = 1000
+    pts, lab = cb.product_points(msgs, (0, 0, 1), N, seed=6, ctx=ctx)
+    opts, olab = oracle.product(msgs, N, seed=6, circular=[0, 0, 1], ubits=53 if ctx.precision == "fp64" else 24)
+    near = lambda p: (np.linalg.norm(p[:, :2] - corners[0, :2], axis=1) < 2.0).mean()
+    assert near(pts) > 0.9 and abs(near(pts) - near(opts)) < 0.05
+    assert (lab == olab).all(axis=1).mean() > (0.99 if ctx.precision == "fp64" else 0.85)
+    # belief-level agreement under the reference's mmd metric (multihypo_corners.jl:201-202 uses < 0.25)
+    assert cb.mmd(pts, opts, bw=0.001, ctx=ctx) < 0.01
+    # density thresholds at the mode / away from it (multihypo_corners.jl:66-90: > 0.15 at modes, < 0.02 elsewhere)
+    m = cb.manikde("Pose2", pts, ctx=ctx)
+    # evaluated on the position marginal: rebuild a Point2 belief from the first two coordinates
+    m2 = cb.manikde("Point2", pts[:, :2], ctx=ctx)
+    assert m2(np.array([[0.0, 0.0]]), ctx=ctx)[0] > 0.15 and m2(np.array([[10.0, 10.0]]), ctx=ctx)[0] < 0.02
+    assert m.d == 3 and (m.bw > 0).all()
