@@ -261,7 +261,7 @@ __device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta*
 }
 
 template <typename T, int DIM, uint32_t CIRC>
-__global__ void __launch_bounds__(kS, 2)
+__global__ void __launch_bounds__(kS, 4)
 gibbs_kernel(const GibbsArgs a) {
   constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
   constexpr int TILE_BYTES = kTileBytesF32 * (int)(sizeof(T) / 4);

@@ -26,9 +26,9 @@ namespace {
 
 constexpr int kMaxLev = 15;        // depth <= 14 for N <= 16384
 constexpr int kTreeThreads = 1024;
-constexpr int kS = 256;            // chains (threads) per Gibbs CTA
+constexpr int kS = 128;            // chains (threads) per Gibbs CTA
 constexpr int kNCH = 32;           // chunk partial sums per chain
-constexpr int kTileBytesF32 = 16384;
+constexpr int kTileBytesF32 = 8192;
 constexpr int kG = 8;              // candidates scored together by one chain (ILP); tiles and chunks are multiples of kG
 
 __host__ __device__ inline int recn_of(int d) { return (2 * d + 1 + 3) / 4 * 4; }  // [mu(d), var(d), log2 w]
