@@ -11,6 +11,7 @@
 // sub-tiles of CT records read as warp-broadcast 128-bit loads.  Every tile writes its own partial (no
 // atomics); a second kernel reduces the partials in a fixed order in FP64, so results are deterministic.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -23,7 +24,7 @@ template <int DIM> struct RecOf { static constexpr int value = DIM <= 3 ? 4 : 8;
 
 template <typename T, int REC> struct alignas(16) Rec { T v[REC]; };
 
-struct Tile { int sub, rb, cb; };
+struct Tile { int sub, rb, cb, c0, c1, weight; };  // columns [c0,c1); weight 2 = strictly upper block of a symmetric pair sum
 
 template <typename T> struct PairSub {
   const T* rows;  // records
@@ -104,8 +105,7 @@ pair_tiles_kernel(const PairSub<T>* __restrict__ subs, const Tile* __restrict__ 
     }
   }
 
-  const int c0 = tl.cb * kCB;
-  const int c1 = min(c0 + kCB, sb.ncols);
+  const int c0 = tl.c0, c1 = tl.c1;
   for (int cs = c0; cs < c1; cs += kCT) {
     __syncthreads();
     for (int j = tid; j < kCT; j += kThreads) {
@@ -191,7 +191,7 @@ pair_tiles_kernel(const PairSub<T>* __restrict__ subs, const Tile* __restrict__ 
   if (tid < NV) {
     double s = 0;
     for (int w = 0; w < kThreads / 32; ++w) s += sred[w][tid];
-    tile_out[(size_t)blockIdx.x * 8 + tid] = s;
+    tile_out[(size_t)blockIdx.x * 8 + tid] = s * tl.weight;
   }
 }
 
@@ -318,9 +318,20 @@ int run_pairs_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev,
   for (size_t s = 0; s < specs.size(); ++s) {
     sub_tile0.push_back((int)tiles.size());
     int nr = specs[s].row1 - specs[s].row0;
-    int nrb = (nr + kThreads * kRI - 1) / (kThreads * kRI), ncb = (specs[s].ncols + kCB - 1) / kCB;
-    for (int rb = 0; rb < nrb; ++rb)
-      for (int cb = 0; cb < ncb; ++cb) tiles.push_back({(int)s, rb, cb});
+    const int RB = kThreads * kRI;
+    int nrb = (nr + RB - 1) / RB, ncb = (specs[s].ncols + kCB - 1) / kCB;
+    // k(p,q) = k(q,p): a full self pair sum (aa, bb) only needs the diagonal blocks once and the blocks above them twice
+    const bool sym = MODE == 0 && specs[s].rows_is_b == specs[s].cols_is_b && specs[s].row0 == 0 && specs[s].col0 == 0 &&
+                     specs[s].row1 == specs[s].ncols && specs[s].xf < 0;
+    for (int rb = 0; rb < nrb; ++rb) {
+      if (!sym) {
+        for (int cb = 0; cb < ncb; ++cb) tiles.push_back({(int)s, rb, cb, cb * kCB, std::min((cb + 1) * kCB, specs[s].ncols), 1});
+      } else {
+        const int r0 = rb * RB, r1 = std::min(r0 + RB, specs[s].ncols);
+        tiles.push_back({(int)s, rb, 0, r0, r1, 1});
+        for (int c = r1; c < specs[s].ncols; c += kCB) tiles.push_back({(int)s, rb, 0, c, std::min(c + kCB, specs[s].ncols), 2});
+      }
+    }
   }
   sub_tile0.push_back((int)tiles.size());
   const int ntiles = (int)tiles.size(), nsub = (int)specs.size();
@@ -645,7 +656,7 @@ static int kde_eval_impl(cb2_ctx* ctx, const double* mu_dev, const double* sigma
   const int nrb = (Q + kThreads * kRI - 1) / (kThreads * kRI), ncb = (N + kCB - 1) / kCB;
   std::vector<Tile> tiles;
   for (int rb = 0; rb < nrb; ++rb)
-    for (int cb = 0; cb < ncb; ++cb) tiles.push_back({0, rb, cb});
+    for (int cb = 0; cb < ncb; ++cb) tiles.push_back({0, rb, cb, cb * kCB, std::min((cb + 1) * kCB, N), 1});
   const int ntiles = (int)tiles.size();
   size_t need = cb2_align(sizeof(T) * rec * (size_t)N) + cb2_align(sizeof(T) * rec * (size_t)Q) + cb2_align(sizeof(PairSub<T>)) +
                 cb2_align(sizeof(Tile) * (size_t)ntiles) + cb2_align(sizeof(T) * (size_t)ncb * Q) + 4096;
