@@ -318,9 +318,78 @@ def manifoldProducts(groups, manifold=None, N=None, Niter=1, seed=0, streams=Non
 
 
 def manifoldProduct(ff, manifold=None, Niter=1, N=None, seed=0, stream=0, return_labels=False, bw="loo", ctx=None):
-    """`manifoldProduct(ff, M; Niter=1, N)`: Gibbs-sampled product of the beliefs in `ff`."""
-    r = manifoldProducts([list(ff)], manifold, N, Niter, seed, [stream], None, return_labels, bw, ctx)
+    """`manifoldProduct(ff, M; Niter=1, N)`: Gibbs-sampled product of the beliefs in `ff`.  Inputs that carry a
+    `partial` (informative coordinates only, 1-based as in the packed format) are multiplied dimension-wise, as
+    upstream does."""
+    ff = list(ff)
+    if len(ff) > 1 and any(m.partial is not None for m in ff):
+        return _manifoldProductPartial(ff, manifold, Niter, N, seed, stream, ctx)
+    r = manifoldProducts([ff], manifold, N, Niter, seed, [stream], None, return_labels, bw, ctx)
     return r[0]
+
+
+def _manifoldProductPartial(ff, manifold, Niter, N, seed, stream, ctx):
+    """Dimension-wise product: coordinate i is the 1-D product of the marginals of every input that informs it."""
+    first = ff[0]
+    d = first.d
+    manifold = manifold if manifold is not None else first.manifold
+    topo = _topology(manifold, d)
+    N = int(N) if N is not None else max(m.N for m in ff)
+    rng = np.random.default_rng(seed)
+    cols, bws = [None] * d, np.zeros(d)
+    batches = {0: [], 1: []}  # 1-D products grouped by topology (one circular mask per batched call)
+    for i in range(d):
+        use = [m for m in ff if m.partial is None or (i + 1) in tuple(m.partial)]
+        if not use:
+            use = [first]
+        marg = [ManifoldKernelDensity((topo[i],), m.pts[:, i:i + 1], m.bw[i:i + 1], m.weights) for m in use]
+        if len(marg) == 1:  # a single informed input: its own samples (resampled to N), upstream early-out per dimension
+            src = marg[0].pts[:, 0]
+            cols[i] = src if len(src) == N else src[rng.integers(0, len(src), size=N)]
+            bws[i] = marg[0].bw[0]
+        else:
+            batches[topo[i]].append((i, marg))
+    for c, items in batches.items():
+        if not items:
+            continue
+        res = manifoldProducts([m for _, m in items], (c,), N=N, Niter=Niter, seed=seed,
+                               streams=[stream * 16 + i for i, _ in items], bw="loo", ctx=ctx)
+        for (i, _), r in zip(items, res):
+            cols[i], bws[i] = r.pts[:, 0], r.bw[0]
+    return ManifoldKernelDensity(manifold, np.stack(cols, axis=1), bws)
+
+
+class PendingProducts:
+    """Ticket of an asynchronous batch (`cb2_product_batch_submit`): the call returned as soon as the work was
+    enqueued; `wait()` blocks until the results are in the host buffers (`cb2_wait`)."""
+
+    def __init__(self, ctx, ticket, groups, manifold, outs, labels, bws, keep):
+        self.ctx, self.ticket, self._groups, self._manifold = ctx, ticket, groups, manifold
+        self._outs, self._labels, self._bws, self._keep = outs, labels, bws, keep
+
+    def wait(self):
+        self.ctx.check(_capi.lib().cb2_wait(self.ctx._h, self.ticket))
+        return [ManifoldKernelDensity(self._manifold, o, b) for o, b in zip(self._outs, self._bws)]
+
+
+def manifoldProducts_submit(groups, manifold=None, N=None, Niter=1, seed=0, streams=None, ctx=None):
+    """Asynchronous flavour of `manifoldProducts` for cooperative callers (one Julia Task per clique): every group
+    must hold at least two messages (the single-input early-out needs no device work)."""
+    ctx = ctx or context()
+    first = groups[0][0]
+    d = first.d
+    manifold = manifold if manifold is not None else first.manifold
+    topo = _topology(manifold, d)
+    if any(len(g) < 2 for g in groups):
+        raise ValueError("submit: every product needs at least two messages")
+    B = len(groups)
+    Nouts = [int(N) if N is not None else max(m.N for m in g) for g in groups]
+    streams = list(range(B)) if streams is None else streams
+    descs, keep, outs, labels, bws = _pack_products(groups, Nouts, Niter, streams, [0] * B, False, True, d)
+    circ = circ_arr(topo, d)
+    ticket = C.c_int64()
+    ctx.check(_capi.lib().cb2_product_batch_submit(ctx._h, descs, B, ptr(circ), d, int(seed), C.byref(ticket)))
+    return PendingProducts(ctx, ticket.value, groups, manifold, outs, labels, bws, (keep, descs, circ))
 
 
 def product_points(dens, circular, Nout, seed=0, niter=1, stream=0, sample_offset=0, ctx=None):

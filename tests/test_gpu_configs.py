@@ -105,3 +105,35 @@ def test_c4_multihypo_four_mode_products(cb, ctx):
     m2 = cb.manikde("Point2", pts[:, :2], ctx=ctx)
     assert m2(np.array([[0.0, 0.0]]), ctx=ctx)[0] > 0.15 and m2(np.array([[10.0, 10.0]]), ctx=ctx)[0] < 0.02
     assert m.d == 3 and (m.bw > 0).all()
+
+
+def test_partial_dimension_product(cb, ctx):
+    """AMP multiplies inputs that inform only some coordinates dimension-wise: a full Pose2
+    belief times a partial prior on (x, y) only must tighten x, y and leave theta's spread untouched."""
+    rng = np.random.default_rng(7)
+    full = cb.manikde("Pose2", np.c_[rng.normal(size=(400, 2)) * 2.0, 0.3 * rng.normal(size=400)], ctx=ctx)
+    prior_pts = np.c_[1.0 + 0.5 * rng.normal(size=(400, 2)), np.zeros(400)]
+    prior = cb.ManifoldKernelDensity("Pose2", prior_pts, [0.2, 0.2, 1.0], partial=(1, 2))
+    p = cb.manifoldProduct([full, prior], N=400, seed=3, ctx=ctx)
+    assert p.pts.shape == (400, 3) and (p.bw > 0).all()
+    # x, y: product of N(0, 2^2) and N(1, 0.5^2) -> mean ~ 0.94, std ~ 0.49 (plus KDE smoothing)
+    assert np.abs(p.pts[:, :2].mean(0) - 0.94).max() < 0.2 and np.abs(p.pts[:, :2].std(0) - 0.5).max() < 0.15
+    # theta: only `full` informs it -> its samples are passed through
+    assert abs(p.pts[:, 2].std() - full.pts[:, 2].std()) < 0.05
+    o, _ = oracle.product([(full.pts[:, :1], full.bw[:1]), (prior.pts[:, :1], prior.bw[:1])], 400, seed=3, stream=0,
+                          ubits=53 if ctx.precision == "fp64" else 24)
+    assert abs(o.mean() - p.pts[:, 0].mean()) < 0.1
+
+
+def test_async_ticket_matches_synchronous_batch(cb, ctx):
+    rng = np.random.default_rng(8)
+    groups = [[cb.MKD("Point2", rng.normal(size=(120, 2)) + j, np.array([0.3, 0.3])) for j in range(D)] for D in (2, 3)]
+    sync = cb.manifoldProducts(groups, N=120, seed=11, streams=[5, 6], ctx=ctx)
+    pend = cb.manifoldProducts_submit(groups, N=120, seed=11, streams=[5, 6], ctx=ctx)
+    other = cb.mmd(groups[0][0], groups[0][1], ctx=ctx)  # the context stays usable while a ticket is outstanding
+    res = pend.wait()
+    for a, b in zip(sync, res):
+        assert np.array_equal(a.pts, b.pts) and np.allclose(a.bw, b.bw, rtol=1e-12)
+    assert np.isfinite(other)
+    with pytest.raises(cb.CB2Error):
+        pend.wait()  # a ticket can be waited on once
