@@ -306,3 +306,30 @@ def test_errors_are_codes_not_crashes(cb, ctx):
     assert e.value.code == -1 and "bandwidth" in str(e.value)
     # the context is still usable afterwards
     assert np.isfinite(cb.mmd(np.zeros((3, 2)), np.ones((3, 2)), 1.0, ctx=ctx))
+
+
+# ------------------------------------------------------------------------------------------------ limits
+def test_product_at_compiled_limits(cb, ctx64):
+    """Maximum sizes the library accepts: N = 16384 kernels per message, D = 16 messages, generic d = 5 mask path."""
+    rng = np.random.default_rng(77)
+    # N = 16384 (largest tree: 213 KB of shared memory, 15 levels), D = 2, d = 2; the oracle re-runs a slice of the chains
+    dens = [(rng.normal(size=(16384, 2)) * [2, 1] + [j, 0], np.array([0.08, 0.05])) for j in range(2)]
+    pts, lab = cb.product_points(dens, (0, 0), 512, seed=3, ctx=ctx64)
+    opts, olab = oracle.product(dens, 64, seed=3, circular=[0, 0], ubits=53, sample_offset=300)
+    same = (lab[300:364] == olab).all(axis=1)
+    assert same.mean() >= 0.95 and np.allclose(pts[300:364][same], opts[same], atol=1e-8)
+    depth, perm, levels = cb.tree_levels(dens[0][0], dens[0][1], ctx=ctx64)
+    assert depth == 14 and sorted(perm.tolist()) == list(range(16384))
+    # D = 16 messages, ragged sizes, d = 5 with a mixed circular mask (run-time mask kernel)
+    dens = [(rng.normal(size=(40 + 3 * j, 5)) * 0.5, np.full(5, 0.3)) for j in range(16)]
+    circ = (0, 1, 0, 0, 1)
+    pts, lab = cb.product_points(dens, circ, 200, seed=4, ctx=ctx64)
+    opts, olab = oracle.product(dens, 200, seed=4, circular=list(circ), ubits=53)
+    assert (lab == olab).all(axis=1).mean() >= 0.98
+    # one output sample, one kernel per message
+    pts, lab = cb.product_points([(np.array([[1.0, 2.0]]), np.array([0.5, 0.5])), (np.array([[2.0, 2.0]]), np.array([0.5, 0.5]))],
+                                 (0, 0), 1, seed=1, ctx=ctx64)
+    assert pts.shape == (1, 2) and (lab == 0).all() and abs(pts[0, 0] - 1.5) < 2.0
+    # bandwidth search at the largest supported N
+    x = rng.normal(size=(16384, 1))
+    assert np.allclose(cb.kde_bandwidth(x, ctx=ctx64), oracle.kde_bw_loo(x), rtol=1e-6)
