@@ -5,10 +5,12 @@
 // lives on the device; each iteration is two launches for the whole batch (no host round trip):
 //   loo_sort_init_kernel : once: sorts the coordinate (shared-memory bitonic sort, FP64), derives the bracket from
 //                          the smallest neighbour gap and the range
-//   loo_rows_kernel      : for every active problem, sum_i log( sum_{j != i} exp2(-(x_i-x_j)^2 c(h)) ), one CTA per
+//   loo_rows_kernel      : for every active problem the row sums sum_{j != i} exp2(-(x_i-x_j)^2 c(h)), one CTA per
 //                          (problem, block of 1024 sorted rows), rows in registers, columns broadcast from shared
 //                          memory.  On sorted data a column tile that is farther than the flush-to-zero radius from
-//                          the whole row block contributes exactly 0 and is skipped (bit-identical result).
+//                          the whole row block contributes exactly 0 and is skipped (bit-identical result).  The
+//                          kernel is symmetric, so a row block only visits the column tiles at or above its own and
+//                          hands the column sums down to the later row blocks (loo_finish_kernel adds them, takes logs).
 //   golden_step_kernel   : one thread per problem folds the row-block partials in fixed order, turns them into
 //                          the objective value and advances that problem's bracket.
 // The bracket and the update rule follow Ihler's `ksize(..., 'lcv')` / `golden` as restated in oracle/cb2_oracle.c.
@@ -27,9 +29,11 @@ struct LooProblem {
   int stride;       // distance between consecutive points (= d)
   int N;
   int circular;
-  int part0;        // first slot in the row-block partial array
+  int part0;        // slot of this problem in the partial array
   int nrb;
-  long long xs_off; // offset of this problem's sorted copy in the xs scratch
+  long long xs_off; // offset of this problem's sorted copy in the xs scratch (also of its row sums)
+  int nstride;      // padded N: stride of one row block's column-sum slice
+  long long cp_off; // offset of this problem's column-sum slices [nrb][nstride]
 };
 
 struct LooState {
@@ -97,18 +101,39 @@ template <typename T> struct ZeroRadius;  // |scaled difference| beyond which ex
 template <> struct ZeroRadius<float> { static constexpr double value = 11.4; };   // d^2 > 129: below FP32 min normal (ftz)
 template <> struct ZeroRadius<double> { static constexpr double value = 33.0; };  // d^2 > 1089: below FP64 denormals
 
+// sum over the 32 lanes of 32 per-lane values in 31 shuffles: afterwards lane L holds the total of v[L]
+template <typename T> __device__ __forceinline__ T lane_transpose_sum(T (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int off = 16 >> s;
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      T send = hi ? v[k] : v[k + off];
+      T keep = hi ? v[k + off] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// k(x_i, x_j) is symmetric: the CTA of row block I only visits column tiles J >= I.  The diagonal tile is evaluated in
+// full; for a tile above the diagonal every kernel value is added to its row (registers) AND to its column (lane
+// transpose + per-warp shared-memory slots, summed in fixed order), and the column sums are handed to the rows of
+// block J through `colpart`.  Half the MUFU work of the plain row pass; deterministic (no atomics).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict__ st, const int2* __restrict__ cta_map,
-                const double* __restrict__ xs_all, double* __restrict__ partial) {
+                const double* __restrict__ xs_all, T* __restrict__ rowsum_all, T* __restrict__ colpart_all) {
   const int2 cm = cta_map[blockIdx.x];  // (problem, row block)
   const LooState s = st[cm.x];
   if (s.phase == 3) return;
   const LooProblem pr = probs[cm.x];
   const double* __restrict__ xs = xs_all + pr.xs_off;
-  __shared__ T sx[kCT];
-  __shared__ double sred[kThreads / 32];
-  const int tid = threadIdx.x, N = pr.N;
+  extern __shared__ __align__(16) unsigned char loo_smem[];
+  T* sx = reinterpret_cast<T*>(loo_smem);           // [kCT]
+  T* colacc = sx + kCT;                              // [kThreads/32][kCT]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, N = pr.N;
   // exponent in base 2: (x_i - x_j)^2 * 0.5*log2e/h^2 -> pre-scale the coordinates by sc
   const double sc = sqrt(0.5 * CB2_LOG2E) / s.h_eval;
   const bool circ = pr.circular != 0;
@@ -118,8 +143,9 @@ loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict
   const T period = (T)(CB2_TWO_PI * sc);
   T xi[kRI], acc[kRI];
   int rowi[kRI];
-  const int rbase = cm.y * (kThreads * kRI);
-  const int rend = min(rbase + kThreads * kRI, N);
+  const int RB = kThreads * kRI;
+  const int rbase = cm.y * RB;
+  const int rend = min(rbase + RB, N);
 #pragma unroll
   for (int r = 0; r < kRI; ++r) {
     int row = rbase + r * kThreads + tid;
@@ -128,13 +154,16 @@ loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict
     xi[r] = (T)(((circ ? wrap_pi(v) : v) - x_mid) * sc);
     acc[r] = T(0);
   }
-  const double row_lo = xs[rbase], row_hi = xs[rend - 1];
+  const double row_hi = xs[rend - 1];
   const double zero_r = ZeroRadius<T>::value / sc;
-  for (int cs = 0; cs < N; cs += kCT) {
+  T* colpart = colpart_all + pr.cp_off + (size_t)cm.y * pr.nstride;  // this row block's slice: [nstride]
+  for (int cs = rbase; cs < N; cs += kCT) {
     const int cend = min(cs + kCT, N);
-    if (!circ) {  // sorted data: tiles entirely beyond the flush-to-zero radius contribute exactly 0
-      double gap = fmax(xs[cs] - row_hi, row_lo - xs[cend - 1]);
-      if (gap > zero_r) continue;
+    const bool diag = cs == rbase;
+    if (!circ && !diag && xs[cs] - row_hi > zero_r) {
+      // sorted data: a tile entirely beyond the flush-to-zero radius contributes exactly 0 (and so do all later ones)
+      for (int j = tid; j < cend - cs; j += kThreads) colpart[cs + j] = T(0);
+      continue;
     }
     __syncthreads();
     for (int j = tid; j < kCT; j += kThreads) {
@@ -143,56 +172,78 @@ loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict
       else sx[j] = T(1e18);
     }
     __syncthreads();
-    // the diagonal (j == i) only meets this tile if it overlaps the CTA's rows
-    const bool has_diag = cs < rbase + kThreads * kRI && cs + kCT > rbase;
     const int jn = cend - cs;
-    if (circ) {
-      for (int j = 0; j < jn; ++j) {
-        const T q = sx[j];
-#pragma unroll
-        for (int r = 0; r < kRI; ++r) {
-          T ad = fabs(xi[r] - q);
-          T v = fmin(ad, period - ad);
-          T kv = fast_exp2(-(v * v));
-          acc[r] += (has_diag && cs + j == rowi[r]) ? T(0) : kv;
-        }
-      }
-    } else if (has_diag) {
+    if (diag) {  // all ordered pairs inside the block, self term excluded
       for (int j = 0; j < jn; ++j) {
         const T q = sx[j];
 #pragma unroll
         for (int r = 0; r < kRI; ++r) {
           T df = xi[r] - q;
+          if (circ) { T ad = fabs(df); df = fmin(ad, period - ad); }
           T kv = fast_exp2(-(df * df));
           acc[r] += (cs + j == rowi[r]) ? T(0) : kv;
         }
       }
-    } else {
-#pragma unroll 8
-      for (int j = 0; j < kCT; ++j) {
-        const T q = sx[j];
+    } else {  // tile above the diagonal: the row block is complete (1024 valid rows); columns may be ragged
+      for (int j0 = 0; j0 < kCT; j0 += 32) {
+        T v[32];
 #pragma unroll
-        for (int r = 0; r < kRI; ++r) {
-          T df = xi[r] - q;
-          acc[r] += fast_exp2(-(df * df));
+        for (int c = 0; c < 32; ++c) {
+          const T q = sx[j0 + c];
+          T kv[kRI];
+#pragma unroll
+          for (int r = 0; r < kRI; ++r) {
+            T df = xi[r] - q;
+            if (circ) { T ad = fabs(df); df = fmin(ad, period - ad); }
+            kv[r] = fast_exp2(-(df * df));
+            if (circ && j0 + c >= jn) kv[r] = T(0);  // padding column (the wrap would fold the sentinel back)
+            acc[r] += kv[r];
+          }
+          v[c] = (kv[0] + kv[1]) + (kv[2] + kv[3]);
         }
+        colacc[warp * kCT + j0 + lane] = lane_transpose_sum(v, lane);
+      }
+      __syncthreads();
+      for (int j = tid; j < jn; j += kThreads) {
+        T t = T(0);
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) t += colacc[w * kCT + j];
+        colpart[cs + j] = t;
       }
     }
   }
-  double v = 0;
+  T* rowsum = rowsum_all + pr.xs_off;
 #pragma unroll
   for (int r = 0; r < kRI; ++r)
-    if (rowi[r] < N) {
-      double a = (double)acc[r];
-      v += log(a > 2.2250738585072014e-308 ? a : 2.2250738585072014e-308);
-    }
+    if (rowi[r] < N) rowsum[rowi[r]] = acc[r];
+}
+
+// row totals = own row pass + the column sums handed down by the row blocks above; then sum_i log(.)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+loo_finish_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict__ st, const T* __restrict__ rowsum_all,
+                  const T* __restrict__ colpart_all, double* __restrict__ partial) {
+  const int p = blockIdx.x;
+  if (st[p].phase == 3) return;
+  const LooProblem pr = probs[p];
+  __shared__ double sred[kThreads / 32];
+  const T* rowsum = rowsum_all + pr.xs_off;
+  const T* colpart = colpart_all + pr.cp_off;
+  const int RB = kThreads * kRI;
+  double v = 0;
+  for (int r = threadIdx.x; r < pr.N; r += kThreads) {
+    double a = (double)rowsum[r];
+    const int I = r / RB;
+    for (int b = 0; b < I; ++b) a += (double)colpart[(size_t)b * pr.nstride + r];
+    v += log(a > 2.2250738585072014e-308 ? a : 2.2250738585072014e-308);
+  }
   v = warp_sum(v);
-  if ((tid & 31) == 0) sred[tid >> 5] = v;
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
   __syncthreads();
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     double t = 0;
     for (int w = 0; w < kThreads / 32; ++w) t += sred[w];
-    partial[pr.part0 + cm.y] = t;
+    partial[p] = t;
   }
 }
 
@@ -204,7 +255,7 @@ __global__ void golden_step_kernel(const LooProblem* __restrict__ probs, int P, 
   if (s.phase == 3) return;
   const LooProblem pr = probs[p];
   double t = 0;
-  for (int b = 0; b < pr.nrb; ++b) t += partial[pr.part0 + b];
+  t = partial[p];
   const double h = s.h_eval;
   // nll(h) = -(1/N) sum_i [ log(sum_{j!=i} k_ij) - 0.5 log(2 pi h^2) - log(N-1) ]
   const double f = -(t / pr.N - 0.5 * log(CB2_TWO_PI * h * h) - log((double)(pr.N - 1)));
@@ -241,24 +292,29 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
   const int P = B * d;
   std::vector<LooProblem> probs(P);
   std::vector<int2> cta_map;
-  int nparts = 0, maxN = 2;
-  long long xs_elems = 0;
+  int maxN = 2;
+  long long xs_elems = 0, cp_elems = 0;
   for (int b = 0; b < B; ++b)
     for (int k = 0; k < d; ++k) {
       LooProblem& pr = probs[(size_t)b * d + k];
       pr.x = mu_dev[b] + k; pr.stride = d; pr.N = N[b];
       pr.circular = circular ? circular[k] : 0;
       pr.nrb = (N[b] + kThreads * kRI - 1) / (kThreads * kRI);
-      pr.part0 = nparts;
+      pr.part0 = b * d + k;
+      pr.nstride = (N[b] + 31) / 32 * 32;
       pr.xs_off = xs_elems;
-      xs_elems += (N[b] + 31) / 32 * 32;
-      nparts += pr.nrb;
+      pr.cp_off = cp_elems;
+      xs_elems += pr.nstride;
+      cp_elems += (long long)pr.nstride * pr.nrb;
       if (N[b] > maxN) maxN = N[b];
       for (int rb = 0; rb < pr.nrb; ++rb) cta_map.push_back(make_int2(b * d + k, rb));
     }
   if (maxN > CB2_MAX_PRODUCT_N) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "bandwidth search supports N <= %d (got %d)", CB2_MAX_PRODUCT_N, maxN);
+  const bool f64 = ctx->precision == CB2_FP64;
+  const size_t tsz = f64 ? sizeof(double) : sizeof(float);
   size_t need = cb2_align(sizeof(LooProblem) * P) + cb2_align(sizeof(LooState) * P) + cb2_align(sizeof(int2) * cta_map.size()) +
-                cb2_align(sizeof(double) * nparts) + cb2_align(sizeof(int) * 64) + cb2_align(sizeof(double) * (size_t)xs_elems) + 1024;
+                cb2_align(sizeof(double) * P) + cb2_align(sizeof(int) * 64) + cb2_align(sizeof(double) * (size_t)xs_elems) +
+                cb2_align(tsz * (size_t)xs_elems) + cb2_align(tsz * (size_t)cp_elems) + 1024;
   if (scratch_needed) *scratch_needed = need;
   if (!scratch) return CB2_OK;  // sizing query
   if (scratch_bytes < need) return cb2_fail(ctx, CB2_ERR_NOMEM, "loo scratch too small");
@@ -268,9 +324,11 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
   LooProblem* probs_dev = (LooProblem*)take(sizeof(LooProblem) * P);
   LooState* st_dev = (LooState*)take(sizeof(LooState) * P);
   int2* map_dev = (int2*)take(sizeof(int2) * cta_map.size());
-  double* partial = (double*)take(sizeof(double) * nparts);
+  double* partial = (double*)take(sizeof(double) * P);
   int* counters = (int*)take(sizeof(int) * 64);
   double* xs_dev = (double*)take(sizeof(double) * (size_t)xs_elems);
+  void* rowsum = take(tsz * (size_t)xs_elems);
+  void* colpart = take(tsz * (size_t)cp_elems);
   CB2_CUDA(ctx, cudaMemcpyAsync(probs_dev, probs.data(), sizeof(LooProblem) * P, cudaMemcpyHostToDevice, ctx->stream));
   CB2_CUDA(ctx, cudaMemcpyAsync(map_dev, cta_map.data(), sizeof(int2) * cta_map.size(), cudaMemcpyHostToDevice, ctx->stream));
   CB2_CUDA(ctx, cudaMemsetAsync(counters, 0, sizeof(int) * 64, ctx->stream));
@@ -281,13 +339,22 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
   if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "loo sort smem attribute: %s", cudaGetErrorString(e));
   loo_sort_init_kernel<<<P, kSortThreads, sort_smem, ctx->stream>>>(probs_dev, st_dev, xs_dev);
   CB2_CHECK_LAUNCH(ctx, "loo_sort_init_kernel");
+  const size_t rows_smem = tsz * (size_t)kCT * (1 + kThreads / 32);
+  e = f64 ? cudaFuncSetAttribute(loo_rows_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem)
+          : cudaFuncSetAttribute(loo_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem);
+  if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "loo rows smem attribute: %s", cudaGetErrorString(e));
   const int max_iter = 64, check_every = 8;
   for (int it = 0; it < max_iter; ++it) {
-    if (ctx->precision == CB2_FP64)
-      loo_rows_kernel<double><<<(int)cta_map.size(), kThreads, 0, ctx->stream>>>(probs_dev, st_dev, map_dev, xs_dev, partial);
-    else
-      loo_rows_kernel<float><<<(int)cta_map.size(), kThreads, 0, ctx->stream>>>(probs_dev, st_dev, map_dev, xs_dev, partial);
-    CB2_CHECK_LAUNCH(ctx, "loo_rows_kernel");
+    if (f64) {
+      loo_rows_kernel<double><<<(int)cta_map.size(), kThreads, rows_smem, ctx->stream>>>(probs_dev, st_dev, map_dev, xs_dev, (double*)rowsum, (double*)colpart);
+      CB2_CHECK_LAUNCH(ctx, "loo_rows_kernel");
+      loo_finish_kernel<double><<<P, kThreads, 0, ctx->stream>>>(probs_dev, st_dev, (const double*)rowsum, (const double*)colpart, partial);
+    } else {
+      loo_rows_kernel<float><<<(int)cta_map.size(), kThreads, rows_smem, ctx->stream>>>(probs_dev, st_dev, map_dev, xs_dev, (float*)rowsum, (float*)colpart);
+      CB2_CHECK_LAUNCH(ctx, "loo_rows_kernel");
+      loo_finish_kernel<float><<<P, kThreads, 0, ctx->stream>>>(probs_dev, st_dev, (const float*)rowsum, (const float*)colpart, partial);
+    }
+    CB2_CHECK_LAUNCH(ctx, "loo_finish_kernel");
     golden_step_kernel<<<(P + 127) / 128, 128, 0, ctx->stream>>>(probs_dev, P, partial, st_dev, counters + it);
     CB2_CHECK_LAUNCH(ctx, "golden_step_kernel");
     if ((it + 1) % check_every == 0) {
