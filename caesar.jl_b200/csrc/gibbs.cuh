@@ -207,11 +207,23 @@ __device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, in
   constexpr int REC = MODE == 0 ? RECN : RECL;
   int pick = -1, lastpos = z0;
   const T nm = -m;
-  for (int z = z0; z < z1; ++z) {
-    T p = fast_exp2(score_any_g<T, DIM, MODE>(lrec + (size_t)z * REC, cc, circ, nm));
-    cum += p;
-    if (p > T(0)) lastpos = z;
-    if (cum >= tgt) { pick = z; break; }
+  // four candidates per round: their (divergent, L2-resident) record loads are in flight together; the cumulative
+  // sum is still taken strictly in candidate order, so the draw is the same as a one-by-one scan
+  for (int z = z0; z < z1 && pick < 0; z += 4) {
+    T p[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int zz = min(z + g, z1 - 1);
+      p[g] = fast_exp2(score_any_g<T, DIM, MODE>(lrec + (size_t)zz * REC, cc, circ, nm));
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (pick < 0 && z + g < z1) {
+        cum += p[g];
+        if (p[g] > T(0)) lastpos = z + g;
+        if (cum >= tgt) pick = z + g;
+      }
+    }
   }
   return pick < 0 ? lastpos : pick;
 }
@@ -225,8 +237,10 @@ __device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta*
   T lam[DIM], s1[DIM], s2[DIM];
 #pragma unroll
   for (int i = 0; i < DIM; ++i) { lam[i] = T(0); s1[i] = T(0); s2[i] = T(0); }
-  for (int k = 0; k < D; ++k) {
-    if (k == skip) continue;
+  const int nk = skip >= 0 ? D - 1 : D;
+#pragma unroll 4
+  for (int kk = 0; kk < nk; ++kk) {  // branch-free skip so that the independent gathers of several messages overlap
+    const int k = kk + ((skip >= 0 && kk >= skip) ? 1 : 0);
     const SMeta& dm = sm[k];
     const int lev = min(step, dm.depth);
     const int node = ind_s[k * kS + tid];

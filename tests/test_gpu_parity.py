@@ -333,3 +333,23 @@ def test_product_at_compiled_limits(cb, ctx64):
     # bandwidth search at the largest supported N
     x = rng.normal(size=(16384, 1))
     assert np.allclose(cb.kde_bandwidth(x, ctx=ctx64), oracle.kde_bw_loo(x), rtol=1e-6)
+
+
+def test_product_with_weighted_kernels(cb, ctx64, ctx32):
+    """Per-kernel weights (the non-uniform leaf path): FP64 chains reproduce the oracle, FP32 agrees in distribution."""
+    rng = np.random.default_rng(55)
+    dens = []
+    for j in range(3):
+        pts = rng.normal(size=(150 + j, 3)) * [1.0, 0.7, 0.2] + [0.2 * j, 0, 0]
+        w = rng.uniform(0.05, 1.0, size=len(pts))
+        w[::7] = 0.0  # some kernels carry no mass at all
+        dens.append((pts, np.array([0.3, 0.25, 0.08]), w))
+    opts, olab = oracle.product(dens, 400, seed=8, circular=[0, 0, 1], ubits=53)
+    pts, lab = cb.product_points(dens, (0, 0, 1), 400, seed=8, ctx=ctx64)
+    same = (lab == olab).all(axis=1)
+    assert same.mean() >= 0.99 and np.allclose(pts[same], opts[same], atol=1e-9)
+    for j in range(3):
+        assert (dens[j][2][lab[:, j]] > 0).all()  # zero-weight kernels are never selected
+    pts32, lab32 = cb.product_points(dens, (0, 0, 1), 400, seed=8, ctx=ctx32)
+    o24, l24 = oracle.product(dens, 400, seed=8, circular=[0, 0, 1], ubits=24)
+    assert (lab32 == l24).all(axis=1).mean() > 0.9 and np.allclose(pts32.mean(0), o24.mean(0), atol=0.1)
