@@ -31,3 +31,24 @@ def unpackDistribution(packed):
     if partial is not None and list(partial) == list(range(1, pts.shape[1] + 1)):
         partial = None
     return ManifoldKernelDensity(vt, pts, packed["bw"], None, partial, packed.get("infoPerCoord"))
+
+
+def multiplyDistributions(requestDict, seed=0, ctx=None):
+    """The ZMQ verb `multiplyDistributions` (R:ext/services/additional.jl:11-32) on the device product path:
+    every input `Packed_BallTreeDensity` (R:ext/models/distributions.jl:26-32; 1-D, points stacked in a flat list) gets
+    a fresh LOO bandwidth (the reference recomputes it too, :18-20), the beliefs are multiplied with
+    `manifoldProduct(ContinuousScalar, funcs)` and the reply carries `bw`, equal weights and the new points."""
+    from . import manikde, manifoldProduct
+    payload = requestDict["payload"]
+    funcs = []
+    for pbd in payload["weights"]:
+        dim = int(pbd.get("dim", 1))
+        if dim != 1:
+            raise ValueError("multiplyDistributions assumes 1-D Euclidean beliefs, as the reference does")
+        pts = np.asarray(pbd["points"], dtype=np.float64).reshape(-1, 1)
+        funcs.append(manikde("ContinuousScalar", pts, ctx=ctx))
+    pqr = manifoldProduct(funcs, "ContinuousScalar", seed=seed, ctx=ctx)
+    n = pqr.N
+    resObj = {"dim": 1, "kernelType": "Gaussian", "bandwidth": [float(b) for b in pqr.bw],
+              "weights": [1.0 / n] * n, "points": [float(x) for x in pqr.pts[:, 0]]}
+    return {"status": "OK", "payload": resObj}

@@ -137,3 +137,23 @@ def test_async_ticket_matches_synchronous_batch(cb, ctx):
     assert np.isfinite(other)
     with pytest.raises(cb.CB2Error):
         pend.wait()  # a ticket can be waited on once
+
+
+def test_zmq_multiply_distributions_verb(cb, ctx):
+    """The request example shipped with the reference (R:ext/services/additional.jl:34)."""
+    import json
+    from importlib import import_module
+    t2 = ('{"payload":{"weights":[{"distType":"BallTreeDensity","kernelType":"Gaussian","weights":[1.0,1.0,1.0,1.0,1.0,1.0,1.0,1.0,1.0,1.0],'
+          '"bandwidth":[0.0,0.0,0.0,0.0,0.0,0.0,0.0,0.0,0.0,0.0],"points":[-0.8272759752535751,1.90340735325013,0.5617238720356695,'
+          '-1.2610130840544629,-0.5196580171571705,0.47808234574398156,-0.5034354386657888,-0.1289061606999511,-0.6283440136328498,'
+          '-0.04520468574277743],"dim":1},{"distType":"BallTreeDensity","kernelType":"Gaussian","weights":[1.0,1.0,1.0,1.0,1.0,1.0,1.0,1.0,1.0,1.0],'
+          '"bandwidth":[0.0,0.0,0.0,0.0,0.0,0.0,0.0,0.0,0.0,0.0],"points":[0.6986754683541115,0.4206784705438769,-0.01798641761511103,'
+          '0.2862258908507545,0.5021835960347083,-1.4424531814460273,0.7667313775874391,0.13048774810077268,-0.004778323705883176,'
+          '-0.6408606329686699],"dim":1}]},"request":"multiplyDistributions"}')
+    ser = import_module("caesar_jl_b200.serialization")
+    reply = ser.multiplyDistributions(json.loads(t2), seed=1, ctx=ctx)
+    assert reply["status"] == "OK"
+    p = reply["payload"]
+    assert p["dim"] == 1 and p["kernelType"] == "Gaussian" and len(p["points"]) == 10 and len(p["weights"]) == 10
+    assert abs(sum(p["weights"]) - 1.0) < 1e-12 and p["bandwidth"][0] > 0 and np.isfinite(p["points"]).all()
+    json.dumps(reply)  # serialisable as is
