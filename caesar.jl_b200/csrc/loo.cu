@@ -23,6 +23,7 @@ constexpr int kRI = 4;
 constexpr int kCT = 1024;
 constexpr int kSortThreads = 1024;
 constexpr double kTol = 1e-2;
+constexpr int kSmallN = 1024;
 
 struct LooProblem {
   const double* x;  // first scalar of this coordinate
@@ -34,6 +35,7 @@ struct LooProblem {
   long long xs_off; // offset of this problem's sorted copy in the xs scratch (also of its row sums)
   int nstride;      // padded N: stride of one row block's column-sum slice
   long long cp_off; // offset of this problem's column-sum slices [nrb][nstride]
+  int small;        // N <= kSmallN: solved by the single-CTA kernel
 };
 
 struct LooState {
@@ -44,12 +46,15 @@ struct LooState {
   double result;
 };
 
+__device__ __forceinline__ void loo_bracket(LooState& s, double min_gap, double range);
+
 // one CTA per problem: sorted copy + golden-section bracket
 __global__ void __launch_bounds__(kSortThreads)
 loo_sort_init_kernel(const LooProblem* __restrict__ probs, LooState* __restrict__ st, double* __restrict__ xs_all) {
   extern __shared__ __align__(16) double skey[];
   __shared__ double sred[kSortThreads / 32];
   const LooProblem pr = probs[blockIdx.x];
+  if (pr.small) return;  // handled entirely by loo_small_kernel
   const int N = pr.N, tid = threadIdx.x, nthr = blockDim.x;
   int P2 = 1;
   while (P2 < N) P2 <<= 1;
@@ -80,19 +85,7 @@ loo_sort_init_kernel(const LooProblem* __restrict__ probs, LooState* __restrict_
   if (tid == 0) {
     for (int w = 1; w < nthr / 32; ++w) mn = fmin(mn, sred[w]);
     LooState s;
-    double m = mn < 1e-6 ? 1e-6 : mn;
-    double range = skey[N - 1] - skey[0];
-    if (!(range >= 1e-6)) {
-      s.phase = 3; s.result = 1e-6; s.h_eval = 1.0;
-      s.x0 = s.x1 = s.x2 = s.x3 = s.f1 = s.f2 = 0; s.slot = 0;
-    } else {
-      const double C = (3.0 - sqrt(5.0)) / 2.0;
-      double ax = 2.0 * m / (1.0 + sqrt(5.0)), bx = m, cx = 2.0 * range;
-      s.x0 = ax; s.x3 = cx;
-      if (fabs(cx - bx) > fabs(bx - ax)) { s.x1 = bx; s.x2 = bx + C * (cx - bx); }
-      else { s.x2 = bx; s.x1 = bx - C * (bx - ax); }
-      s.f1 = s.f2 = 0; s.phase = 0; s.slot = 1; s.h_eval = s.x1; s.result = 0;
-    }
+    loo_bracket(s, mn, skey[N - 1] - skey[0]);
     st[blockIdx.x] = s;
   }
 }
@@ -247,39 +240,146 @@ loo_finish_kernel(const LooProblem* __restrict__ probs, const LooState* __restri
   }
 }
 
+// one golden-section step (Numerical-Recipes form used by Ihler's `golden`): f is the objective at s.h_eval
+__device__ __forceinline__ void golden_advance(LooState& s, double f) {
+  const double C = (3.0 - sqrt(5.0)) / 2.0, R = 1.0 - C;
+  if (s.phase == 0) { s.f1 = f; s.phase = 1; s.h_eval = s.x2; return; }
+  if (s.phase == 1) { s.f2 = f; s.phase = 2; }
+  else if (s.slot == 2) s.f2 = f;
+  else s.f1 = f;
+  if (fabs(s.x3 - s.x0) > kTol * (fabs(s.x1) + fabs(s.x2))) {
+    if (s.f2 < s.f1) { s.x0 = s.x1; s.x1 = s.x2; s.x2 = R * s.x1 + C * s.x3; s.f1 = s.f2; s.h_eval = s.x2; s.slot = 2; }
+    else { s.x3 = s.x2; s.x2 = s.x1; s.x1 = R * s.x2 + C * s.x0; s.f2 = s.f1; s.h_eval = s.x1; s.slot = 1; }
+  } else {
+    s.result = s.f1 < s.f2 ? s.x1 : s.x2;
+    s.phase = 3;
+  }
+}
+
+// nll(h) = -(1/N) sum_i [ log(sum_{j!=i} k_ij) - 0.5 log(2 pi h^2) - log(N-1) ]
+__device__ __forceinline__ double loo_objective(double sum_log_rows, int N, double h) {
+  return -(sum_log_rows / N - 0.5 * log(CB2_TWO_PI * h * h) - log((double)(N - 1)));
+}
+
+__device__ __forceinline__ void loo_bracket(LooState& s, double min_gap, double range) {
+  double m = min_gap < 1e-6 ? 1e-6 : min_gap;
+  if (!(range >= 1e-6)) {
+    s.phase = 3; s.result = 1e-6; s.h_eval = 1.0;
+    s.x0 = s.x1 = s.x2 = s.x3 = s.f1 = s.f2 = 0; s.slot = 0;
+    return;
+  }
+  const double C = (3.0 - sqrt(5.0)) / 2.0;
+  double ax = 2.0 * m / (1.0 + sqrt(5.0)), bx = m, cx = 2.0 * range;
+  s.x0 = ax; s.x3 = cx;
+  if (fabs(cx - bx) > fabs(bx - ax)) { s.x1 = bx; s.x2 = bx + C * (cx - bx); }
+  else { s.x2 = bx; s.x1 = bx - C * (bx - ax); }
+  s.f1 = s.f2 = 0; s.phase = 0; s.slot = 1; s.h_eval = s.x1; s.result = 0;
+}
+
 __global__ void golden_step_kernel(const LooProblem* __restrict__ probs, int P, const double* __restrict__ partial,
                                    LooState* __restrict__ st, int* __restrict__ n_active) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   LooState s = st[p];
   if (s.phase == 3) return;
-  const LooProblem pr = probs[p];
-  double t = 0;
-  t = partial[p];
-  const double h = s.h_eval;
-  // nll(h) = -(1/N) sum_i [ log(sum_{j!=i} k_ij) - 0.5 log(2 pi h^2) - log(N-1) ]
-  const double f = -(t / pr.N - 0.5 * log(CB2_TWO_PI * h * h) - log((double)(pr.N - 1)));
-  const double C = (3.0 - sqrt(5.0)) / 2.0, R = 1.0 - C;
-  if (s.phase == 0) { s.f1 = f; s.phase = 1; s.h_eval = s.x2; }
-  else {
-    if (s.phase == 1) { s.f2 = f; s.phase = 2; }
-    else if (s.slot == 2) s.f2 = f;
-    else s.f1 = f;
-    if (fabs(s.x3 - s.x0) > kTol * (fabs(s.x1) + fabs(s.x2))) {
-      if (s.f2 < s.f1) { s.x0 = s.x1; s.x1 = s.x2; s.x2 = R * s.x1 + C * s.x3; s.f1 = s.f2; s.h_eval = s.x2; s.slot = 2; }
-      else { s.x3 = s.x2; s.x2 = s.x1; s.x1 = R * s.x2 + C * s.x0; s.f2 = s.f1; s.h_eval = s.x1; s.slot = 1; }
-    } else {
-      s.result = s.f1 < s.f2 ? s.x1 : s.x2;
-      s.phase = 3;
-    }
-  }
+  golden_advance(s, loo_objective(partial[p], probs[p].N, s.h_eval));
   st[p] = s;
   if (s.phase != 3) atomicAdd(n_active, 1);
 }
 
+// Small problems (N <= kSmallN, the usual solver particle counts 100..1000): the whole search -- sort, bracket, every
+// golden-section step -- runs inside ONE CTA per problem, no per-iteration launches (latency: microseconds, not ~0.4 ms).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+loo_small_kernel(const LooProblem* __restrict__ probs, const int* __restrict__ ids, LooState* __restrict__ st) {
+  const int p = ids[blockIdx.x];
+  const LooProblem pr = probs[p];
+  const int N = pr.N, tid = threadIdx.x;
+  __shared__ double sk[kSmallN];
+  __shared__ T sxs[kSmallN];
+  __shared__ double sred[kThreads / 32];
+  __shared__ LooState ss;
+  int P2 = 1;
+  while (P2 < N) P2 <<= 1;
+  for (int i = tid; i < P2; i += kThreads) sk[i] = i < N ? pr.x[(size_t)i * pr.stride] : 1.7976931348623157e308;
+  __syncthreads();
+  for (int k = 2; k <= P2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P2; i += kThreads) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          double a = sk[i], b = sk[ixj];
+          if ((b < a) == ((i & k) == 0)) { sk[i] = b; sk[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  double mn = 1e300;
+  for (int i = tid; i + 1 < N; i += kThreads) mn = fmin(mn, sk[i + 1] - sk[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if ((tid & 31) == 0) sred[tid >> 5] = mn;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < kThreads / 32; ++w) mn = fmin(mn, sred[w]);
+    LooState s0;
+    loo_bracket(s0, mn, sk[N - 1] - sk[0]);
+    ss = s0;
+  }
+  const bool circ = pr.circular != 0;
+  const double x_mid = circ ? 0.0 : sk[N >> 1];
+  for (int it = 0; it < 96; ++it) {
+    __syncthreads();
+    if (ss.phase == 3) break;
+    const double h = ss.h_eval;
+    const double sc = sqrt(0.5 * CB2_LOG2E) / h;
+    const T period = (T)(CB2_TWO_PI * sc);
+    for (int j = tid; j < N; j += kThreads) sxs[j] = (T)(((circ ? wrap_pi(sk[j]) : sk[j]) - x_mid) * sc);
+    __syncthreads();
+    T xi[kRI], acc[kRI];
+#pragma unroll
+    for (int r = 0; r < kRI; ++r) { int row = tid + r * kThreads; xi[r] = sxs[row < N ? row : 0]; acc[r] = T(0); }
+    for (int j = 0; j < N; ++j) {
+      const T q = sxs[j];
+#pragma unroll
+      for (int r = 0; r < kRI; ++r) {
+        T df = xi[r] - q;
+        if (circ) { T ad = fabs(df); df = fmin(ad, period - ad); }
+        T kv = fast_exp2(-(df * df));
+        acc[r] += (j == tid + r * kThreads) ? T(0) : kv;
+      }
+    }
+    double v = 0;
+#pragma unroll
+    for (int r = 0; r < kRI; ++r)
+      if (tid + r * kThreads < N) {
+        double a = (double)acc[r];
+        v += log(a > 2.2250738585072014e-308 ? a : 2.2250738585072014e-308);
+      }
+    v = warp_sum(v);
+    if ((tid & 31) == 0) sred[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0;
+      for (int w = 0; w < kThreads / 32; ++w) t += sred[w];
+      LooState s1 = ss;
+      golden_advance(s1, loo_objective(t, N, h));
+      ss = s1;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    LooState s1 = ss;
+    if (s1.phase != 3) { s1.result = s1.f1 < s1.f2 ? s1.x1 : s1.x2; s1.phase = 3; }  // iteration cap: best point so far
+    st[p] = s1;
+  }
+}
+
 __global__ void loo_collect_kernel(const LooState* __restrict__ st, int P, double* __restrict__ out) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P) out[p] = st[p].result;
+  if (p >= P) return;
+  const LooState s = st[p];
+  out[p] = s.phase == 3 ? s.result : (s.f1 < s.f2 ? s.x1 : s.x2);  // iteration cap hit: best point so far
 }
 
 }  // namespace
@@ -292,6 +392,7 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
   const int P = B * d;
   std::vector<LooProblem> probs(P);
   std::vector<int2> cta_map;
+  std::vector<int> small_ids;
   int maxN = 2;
   long long xs_elems = 0, cp_elems = 0;
   for (int b = 0; b < B; ++b)
@@ -301,18 +402,20 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
       pr.circular = circular ? circular[k] : 0;
       pr.nrb = (N[b] + kThreads * kRI - 1) / (kThreads * kRI);
       pr.part0 = b * d + k;
+      pr.small = N[b] <= kSmallN;
       pr.nstride = (N[b] + 31) / 32 * 32;
       pr.xs_off = xs_elems;
       pr.cp_off = cp_elems;
       xs_elems += pr.nstride;
       cp_elems += (long long)pr.nstride * pr.nrb;
       if (N[b] > maxN) maxN = N[b];
-      for (int rb = 0; rb < pr.nrb; ++rb) cta_map.push_back(make_int2(b * d + k, rb));
+      if (pr.small) small_ids.push_back(b * d + k);
+      else for (int rb = 0; rb < pr.nrb; ++rb) cta_map.push_back(make_int2(b * d + k, rb));
     }
   if (maxN > CB2_MAX_PRODUCT_N) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "bandwidth search supports N <= %d (got %d)", CB2_MAX_PRODUCT_N, maxN);
   const bool f64 = ctx->precision == CB2_FP64;
   const size_t tsz = f64 ? sizeof(double) : sizeof(float);
-  size_t need = cb2_align(sizeof(LooProblem) * P) + cb2_align(sizeof(LooState) * P) + cb2_align(sizeof(int2) * cta_map.size()) +
+  size_t need = cb2_align(sizeof(LooProblem) * P) + cb2_align(sizeof(LooState) * P) + cb2_align(sizeof(int2) * (cta_map.size() + 1)) + cb2_align(sizeof(int) * (small_ids.size() + 1)) +
                 cb2_align(sizeof(double) * P) + cb2_align(sizeof(int) * 64) + cb2_align(sizeof(double) * (size_t)xs_elems) +
                 cb2_align(tsz * (size_t)xs_elems) + cb2_align(tsz * (size_t)cp_elems) + 1024;
   if (scratch_needed) *scratch_needed = need;
@@ -323,15 +426,25 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
   auto take = [&](size_t bytes) { void* p = base + off; off += cb2_align(bytes); return p; };
   LooProblem* probs_dev = (LooProblem*)take(sizeof(LooProblem) * P);
   LooState* st_dev = (LooState*)take(sizeof(LooState) * P);
-  int2* map_dev = (int2*)take(sizeof(int2) * cta_map.size());
+  int2* map_dev = (int2*)take(sizeof(int2) * (cta_map.size() + 1));
+  int* small_dev = (int*)take(sizeof(int) * (small_ids.size() + 1));
   double* partial = (double*)take(sizeof(double) * P);
   int* counters = (int*)take(sizeof(int) * 64);
   double* xs_dev = (double*)take(sizeof(double) * (size_t)xs_elems);
   void* rowsum = take(tsz * (size_t)xs_elems);
   void* colpart = take(tsz * (size_t)cp_elems);
   CB2_CUDA(ctx, cudaMemcpyAsync(probs_dev, probs.data(), sizeof(LooProblem) * P, cudaMemcpyHostToDevice, ctx->stream));
-  CB2_CUDA(ctx, cudaMemcpyAsync(map_dev, cta_map.data(), sizeof(int2) * cta_map.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (!cta_map.empty())
+    CB2_CUDA(ctx, cudaMemcpyAsync(map_dev, cta_map.data(), sizeof(int2) * cta_map.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (!small_ids.empty())
+    CB2_CUDA(ctx, cudaMemcpyAsync(small_dev, small_ids.data(), sizeof(int) * small_ids.size(), cudaMemcpyHostToDevice, ctx->stream));
   CB2_CUDA(ctx, cudaMemsetAsync(counters, 0, sizeof(int) * 64, ctx->stream));
+  if (!small_ids.empty()) {
+    if (f64) loo_small_kernel<double><<<(int)small_ids.size(), kThreads, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
+    else loo_small_kernel<float><<<(int)small_ids.size(), kThreads, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
+    CB2_CHECK_LAUNCH(ctx, "loo_small_kernel");
+  }
+  if (!cta_map.empty()) {
   int P2 = 1;
   while (P2 < maxN) P2 <<= 1;
   size_t sort_smem = sizeof(double) * P2;
@@ -364,6 +477,7 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
       if (active == 0) break;
     }
   }
+  }  // large problems
   loo_collect_kernel<<<(P + 127) / 128, 128, 0, ctx->stream>>>(st_dev, P, sigma_out_dev);
   CB2_CHECK_LAUNCH(ctx, "loo_collect_kernel");
   return CB2_OK;
