@@ -7,6 +7,9 @@
 //                   three over a common denominator (1 MUFU.RCP + 1 MUFU.LG2 per group instead of 3 + 3).
 // Circular coordinates are stored wrapped to [-pi, pi] (tree_build_kernel) and the chain mean comes out of atan2,
 // so |mu - M| <= 2 pi and the wrapped distance is min(|df|, 2 pi - |df|): no rounding instruction needed.
+// When every chain of a warp can prove from the message's coordinate range (tree_build_kernel) that no candidate is
+// more than pi away from its mean, the warp takes the all-Euclidean loop (`warp_nowrap`): identical values, 2
+// instructions per circular dimension fewer.  Beliefs that do not straddle the +-pi cut always qualify.
 
 template <typename T, int N> struct alignas(16) VecRec { T v[N]; };
 
@@ -18,6 +21,8 @@ struct GibbsArgs {
   const void* node_pool;
   uint32_t k0, k1;
   uint32_t circ_mask;
+  const double* stat;   // per-message statistics scratch of the tree build; its last 16 doubles = circular ranges
+  size_t stat_stride;
 };
 
 // what the kernel needs of each message, staged once per CTA in shared memory
@@ -27,6 +32,7 @@ struct SMeta {
   float bw2[CB2_MAX_DIM];
   double bw2d[CB2_MAX_DIM];
   double cen[CB2_MAX_DIM];  // offset to add back to Euclidean output coordinates
+  float cmin[CB2_MAX_DIM], cmax[CB2_MAX_DIM];  // range of the stored circular coordinates over all levels
   int N, depth, uniform;
 };
 
@@ -317,6 +323,10 @@ gibbs_kernel(const GibbsArgs a) {
       m.cen[i] = (i < DIM && !(circ >> i & 1)) ? dm.center[i] : 0.0;
     }
     m.N = dm.N; m.depth = dm.depth; m.uniform = dm.w == nullptr;
+    {
+      const double* rg = a.stat + (size_t)prp->dens[tid] * a.stat_stride + (a.stat_stride - 16);
+      for (int i = 0; i < CB2_MAX_DIM; ++i) { m.cmin[i] = (float)rg[i] - 1e-3f; m.cmax[i] = (float)rg[8 + i] + 1e-3f; }
+    }
     sm[tid] = m;
   }
   for (int k = 0; k < D; ++k) ind_s[k * kS + tid] = 0;
@@ -348,9 +358,16 @@ gibbs_kernel(const GibbsArgs a) {
         while (CH * kNCH < cnt) CH <<= 1;
 
         ChainConst<T, DIM> cc;
+        bool nowrap = true;
         {
           T M[DIM], C[DIM];
           if (!single) combine<T, DIM>(pool, sm, D, ind_s, tid, step, j, circ, M, C);
+          // the wrap is a no-op for this chain if every stored coordinate of message j lies within pi of its mean
+          if (circ != 0u && !single) {
+#pragma unroll
+            for (int i = 0; i < DIM; ++i)
+              if (circ >> i & 1) nowrap = nowrap && ((float)M[i] - 3.14159f <= dj.cmin[i]) && (dj.cmax[i] <= (float)M[i] + 3.14159f);
+          }
           cc.qs = single ? T(0) : HL;
           cc.cmul = single ? T(0) : T(1);
 #pragma unroll
@@ -365,6 +382,8 @@ gibbs_kernel(const GibbsArgs a) {
           }
         }
 
+        // warp-uniform choice of the scoring loop (all chains of the warp must agree)
+        const bool warp_nowrap = circ != 0u && __all_sync(0xffffffffu, nowrap);
         // ---- pass 1: chunk partial sums of exp2(e - m), m = running (lazily raised) reference maximum
         T m = -INFINITY, csum = T(0);
         int cidx = 0;
@@ -385,9 +404,15 @@ gibbs_kernel(const GibbsArgs a) {
           if (b) ++use1; else ++use0;
           const int nt = min(TN, cnt - t * TN);
           const T* tb = reinterpret_cast<const T*>(smem_raw + b * TILE_BYTES);
-          if (!leaf) tile_pass<T, DIM, 0>(tb, nt, t * TN, CH, cc, circ, chunk, tid, m, csum, cidx);
-          else if (!dj.uniform) tile_pass<T, DIM, 1>(tb, nt, t * TN, CH, cc, circ, chunk, tid, m, csum, cidx);
-          else tile_pass<T, DIM, 2>(tb, nt, t * TN, CH, cc, circ, chunk, tid, m, csum, cidx);
+          if (warp_nowrap) {  // Euclidean arithmetic on every coordinate: same values, 2 instructions per dim less
+            if (!leaf) tile_pass<T, DIM, 0>(tb, nt, t * TN, CH, cc, 0u, chunk, tid, m, csum, cidx);
+            else if (!dj.uniform) tile_pass<T, DIM, 1>(tb, nt, t * TN, CH, cc, 0u, chunk, tid, m, csum, cidx);
+            else tile_pass<T, DIM, 2>(tb, nt, t * TN, CH, cc, 0u, chunk, tid, m, csum, cidx);
+          } else {
+            if (!leaf) tile_pass<T, DIM, 0>(tb, nt, t * TN, CH, cc, circ, chunk, tid, m, csum, cidx);
+            else if (!dj.uniform) tile_pass<T, DIM, 1>(tb, nt, t * TN, CH, cc, circ, chunk, tid, m, csum, cidx);
+            else tile_pass<T, DIM, 2>(tb, nt, t * TN, CH, cc, circ, chunk, tid, m, csum, cidx);
+          }
           __syncthreads();  // everyone is done with tile[b] before it is refilled
         }
         if (cnt & (CH - 1)) { chunk[cidx * kS + tid] = csum; ++cidx; }

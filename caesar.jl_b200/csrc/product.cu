@@ -180,6 +180,11 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
   auto lvl_off = [&](int l) { return l < depth ? ((1 << l) - 1) : ((1 << depth) - 1); };
   const int nd = 2 * d + 1;
   const int RECN = recn_of(d), RECL = recl_of(d);
+  // range of the stored circular coordinates over every level: lets a Gibbs chain prove that no candidate of this message
+  // is more than pi away from its current mean, i.e. that the wrap is a no-op (gibbs.cuh, `nowrap`)
+  double cmn[CB2_MAX_DIM], cmx[CB2_MAX_DIM];
+#pragma unroll
+  for (int i = 0; i < CB2_MAX_DIM; ++i) { cmn[i] = 1e300; cmx[i] = -1e300; }
   {
     double* sl = sbase + (size_t)lvl_off(depth) * nd;
     T* rec = node_pool + m.rec_off[depth];
@@ -190,7 +195,9 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
         double v = m.pts[(size_t)idx * d + i];
         sl[(size_t)p * nd + i] = v;
         sl[(size_t)p * nd + d + i] = m.bw[i] * m.bw[i];
-        rec[(size_t)p * RECL + i] = (T)((circ_mask >> i & 1) ? wrap_pi(v) : v - m.center[i]);
+        const double rv = (circ_mask >> i & 1) ? wrap_pi(v) : v - m.center[i];
+        rec[(size_t)p * RECL + i] = (T)rv;
+        if (circ_mask >> i & 1) { cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv); }
       }
       sl[(size_t)p * nd + 2 * d] = wt;
       for (int i = d; i < RECL; ++i) rec[(size_t)p * RECL + i] = T(0);
@@ -221,13 +228,32 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
         v /= ws;
         sl[(size_t)k * nd + i] = mm;
         sl[(size_t)k * nd + d + i] = v;
-        rec[(size_t)k * RECN + i] = (T)((circ_mask >> i & 1) ? wrap_pi(mm) : mm - m.center[i]);
+        const double rv = (circ_mask >> i & 1) ? wrap_pi(mm) : mm - m.center[i];
+        rec[(size_t)k * RECN + i] = (T)rv;
+        if (circ_mask >> i & 1) { cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv); }
         rec[(size_t)k * RECN + d + i] = (T)v;
       }
       for (int i = 2 * d; i < RECN; ++i) rec[(size_t)k * RECN + i] = T(0);
       rec[(size_t)k * RECN + 2 * d] = (T)(ws > 0 ? log2(ws) : -1e30);
     }
     __syncthreads();
+  }
+  // block-wide min / max of the circular record values -> last 16 doubles of this message's statistics scratch
+  for (int i = 0; i < d; ++i) {
+    double a = cmn[i], b = cmx[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = fmin(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { s_red[tid >> 5] = a; }
+    __syncthreads();
+    if (tid == 0) { for (int w = 1; w < (nthr >> 5); ++w) a = fmin(a, s_red[w]); sbase[stat_stride - 16 + i] = a; }
+    __syncthreads();
+    if ((tid & 31) == 0) { s_red[tid >> 5] = b; }
+    __syncthreads();
+    if (tid == 0) { for (int w = 1; w < (nthr >> 5); ++w) b = fmax(b, s_red[w]); sbase[stat_stride - 8 + i] = b; }
   }
 }
 
@@ -366,7 +392,7 @@ int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const
                        uint32_t mask, int d, uint64_t seed, BatchPlan& pl, char* base, size_t bytes, size_t* needed,
                        DevLayout* lay_out) {
   const int nd = 2 * d + 1;
-  const size_t stat_stride = (size_t)pl.max_nodes * nd;
+  const size_t stat_stride = (size_t)pl.max_nodes * nd + 16;  // + circular coordinate ranges (min[8], max[8])
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += cb2_align(n); return o; };
   size_t o_metas = take(sizeof(DensMeta) * pl.metas.size());
@@ -412,6 +438,7 @@ int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const
   GibbsArgs ga;
   ga.metas = lay.metas; ga.prods = lay.prods; ga.work = lay.work; ga.int_pool = lay.int_pool; ga.node_pool = lay.node_pool;
   ga.k0 = (uint32_t)seed; ga.k1 = (uint32_t)(seed >> 32); ga.circ_mask = mask;
+  ga.stat = lay.stat; ga.stat_stride = stat_stride;
   int rc = launch_gibbs<T>(ctx, d, mask, (int)pl.work.size(), ga);
   if (rc) return rc;
   CB2_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
