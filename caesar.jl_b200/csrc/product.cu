@@ -11,7 +11,7 @@
 //                       of a CTA advance in lock step through (level, sweep, message).  The candidate nodes of
 //                       the current (message, level) are streamed once per CTA through shared memory with 1-D
 //                       TMA bulk copies (cp.async.bulk + mbarrier, double buffered) and read as warp-broadcast
-//                       128-bit loads, so every candidate record is fetched once per 256 chains.  The categorical
+//                       128-bit loads, so every candidate record is fetched once per 128 chains.  The categorical
 //                       draw is a two-pass inverse CDF: pass 1 keeps per-chunk partial sums (running-max
 //                       rescaled, log-sum-exp safe), pass 2 re-scores only the selected chunk.
 //   Randomness: counter-based Philox4x32-10 keyed by (seed; sample, draw, stream, tag): results do not depend on
@@ -257,6 +257,19 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
   }
 }
 
+// vals[i*d .. i*d+d) = *ptrs[i]  (device-resident bandwidth vectors of a batch, fetched with one copy)
+__global__ void gather_small_vectors_kernel(const double* const* __restrict__ ptrs, int n, int d, double* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < d; ++k) vals[(size_t)i * d + k] = ptrs[i][k];
+}
+// *ptrs[i] = vals[i*d .. i*d+d)  (fresh bandwidths written back to the caller's device buffers)
+__global__ void scatter_small_vectors_kernel(double* const* __restrict__ ptrs, int n, int d, const double* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < d; ++k) ptrs[i][k] = vals[(size_t)i * d + k];
+}
+
 // copies one level of the FP64 statistics scratch out for cb2_tree_debug
 __global__ void tree_debug_copy_kernel(const double* __restrict__ sbase, int d, int level_node0, int cnt,
                                        double* __restrict__ mean, double* __restrict__ var, double* __restrict__ wt) {
@@ -470,9 +483,18 @@ int product_batch_dev_locked(cb2_ctx* ctx, const cb2_product_desc* descs, int B,
     size_t nd = pl.metas.size();
     bw_store.resize(nd * d);
     size_t mi = 0;
+    // one gather kernel + one copy instead of one tiny D2H copy per message
+    std::vector<const double*> ptrs(nd);
     for (int b = 0; b < B; ++b)
-      for (int j = 0; j < descs[b].D; ++j, ++mi)
-        CB2_CUDA(ctx, cudaMemcpyAsync(&bw_store[mi * d], descs[b].dens[j].bw, sizeof(double) * d, cudaMemcpyDeviceToHost, ctx->stream));
+      for (int j = 0; j < descs[b].D; ++j, ++mi) ptrs[mi] = descs[b].dens[j].bw;
+    char* io = (char*)cb2_io_block(ctx, cb2_align(sizeof(double*) * nd) + sizeof(double) * nd * d);
+    if (!io) return CB2_ERR_NOMEM;
+    const double** ptrs_dev = (const double**)io;
+    double* vals_dev = (double*)(io + cb2_align(sizeof(double*) * nd));
+    CB2_CUDA(ctx, cudaMemcpyAsync(ptrs_dev, ptrs.data(), sizeof(double*) * nd, cudaMemcpyHostToDevice, ctx->stream));
+    gather_small_vectors_kernel<<<(int)((nd + 127) / 128), 128, 0, ctx->stream>>>(ptrs_dev, (int)nd, d, vals_dev);
+    CB2_CHECK_LAUNCH(ctx, "gather_small_vectors_kernel");
+    CB2_CUDA(ctx, cudaMemcpyAsync(bw_store.data(), vals_dev, sizeof(double) * nd * d, cudaMemcpyDeviceToHost, ctx->stream));
     CB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     bw_host.resize(B);
     mi = 0;
@@ -497,7 +519,7 @@ int product_batch_dev_locked(cb2_ctx* ctx, const cb2_product_desc* descs, int B,
     rc = cb2_bw_loo_dev_core(ctx, bw_mu.data(), bw_N.data(), (int)bw_mu.size(), d, circular, nullptr, nullptr, 0, &need_loo);
     if (rc) return rc;
   }
-  size_t bw_out_bytes = cb2_align(sizeof(double) * d * (bw_mu.size() + 1));
+  size_t bw_out_bytes = cb2_align(sizeof(double) * d * (bw_mu.size() + 1)) + cb2_align(sizeof(double*) * (bw_mu.size() + 1));
   rc = cb2_arena_reserve(ctx, need_prod + need_loo + bw_out_bytes + 8192);
   if (rc) return rc;
   char* base = (char*)cb2_arena_alloc(ctx, need_prod);
@@ -511,8 +533,13 @@ int product_batch_dev_locked(cb2_ctx* ctx, const cb2_product_desc* descs, int B,
     if (!bw_dev || !scratch) return cb2_fail(ctx, CB2_ERR_NOMEM, "bandwidth scratch exhausted");
     rc = cb2_bw_loo_dev_core(ctx, bw_mu.data(), bw_N.data(), (int)bw_mu.size(), d, circular, bw_dev, scratch, need_loo, nullptr);
     if (rc) return rc;
-    for (size_t i = 0; i < bw_idx.size(); ++i)
-      CB2_CUDA(ctx, cudaMemcpyAsync(descs[bw_idx[i]].bw_out, bw_dev + i * d, sizeof(double) * d, cudaMemcpyDeviceToDevice, ctx->stream));
+    // hand the fresh bandwidths to the callers' device buffers with one scatter kernel
+    std::vector<double*> outp(bw_idx.size());
+    for (size_t i = 0; i < bw_idx.size(); ++i) outp[i] = descs[bw_idx[i]].bw_out;
+    double** outp_dev = (double**)((char*)bw_dev + cb2_align(sizeof(double) * d * (bw_mu.size() + 1)));
+    CB2_CUDA(ctx, cudaMemcpyAsync(outp_dev, outp.data(), sizeof(double*) * outp.size(), cudaMemcpyHostToDevice, ctx->stream));
+    scatter_small_vectors_kernel<<<(int)((outp.size() + 127) / 128), 128, 0, ctx->stream>>>(outp_dev, (int)outp.size(), d, bw_dev);
+    CB2_CHECK_LAUNCH(ctx, "scatter_small_vectors_kernel");
     CB2_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
   }
   ctx->stage_ms.erase("tree"); ctx->stage_ms.erase("gibbs"); ctx->stage_ms.erase("bw");
