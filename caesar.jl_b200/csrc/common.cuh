@@ -20,12 +20,8 @@ struct cb2_arena {  // grow-only device scratch; reset at the start of each publ
   size_t cap = 0, off = 0;
 };
 
-struct cb2_pending {  // one submitted async product batch: what to copy back at cb2_wait
+struct cb2_pending {  // one submitted async product batch: completion event + the device block it owns until cb2_wait
   cudaEvent_t done = nullptr;
-  std::vector<void*> host_dst;
-  std::vector<const void*> pinned_src;
-  std::vector<size_t> bytes;
-  void* pinned_block = nullptr;
   void* dev_block = nullptr;
 };
 
@@ -37,8 +33,9 @@ struct cb2_ctx {
   cudaStream_t stream = nullptr;
   cb2_arena arena;       // device scratch
   cb2_arena io;          // grow-only device block for the host-pointer API's staged inputs / outputs
-  char* pinned = nullptr;  // pinned host staging
+  char* pinned = nullptr;  // pinned host staging (small batches are packed here: one H2D and one D2H copy per call)
   size_t pinned_cap = 0;
+  double* small_dev = nullptr;  // 64 doubles of persistent device scratch (scalar results of nested calls)
   uint64_t launches = 0;
   std::string err;
   std::mutex mu;

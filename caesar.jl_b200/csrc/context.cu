@@ -56,6 +56,12 @@ extern "C" int cb2_create(int device, int precision, cb2_ctx** out) {
   }
   ctx->stream = ctx->own_stream;
   for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
+  e = cudaMalloc((void**)&ctx->small_dev, 64 * sizeof(double));
+  if (e != cudaSuccess) {
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return cb2_fail(nullptr, CB2_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+  }
   *out = ctx;
   return CB2_OK;
 }
@@ -66,13 +72,13 @@ extern "C" void cb2_destroy(cb2_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->pending) {
     if (kv.second.done) cudaEventDestroy(kv.second.done);
-    if (kv.second.pinned_block) cudaFreeHost(kv.second.pinned_block);
     if (kv.second.dev_block) cudaFree(kv.second.dev_block);
   }
   for (int i = 0; i < 8; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->io.base) cudaFree(ctx->io.base);
+  if (ctx->small_dev) cudaFree(ctx->small_dev);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;

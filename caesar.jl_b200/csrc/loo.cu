@@ -503,11 +503,21 @@ extern "C" int cb2_kde_bw_loo_batch(cb2_ctx* ctx, const double* const* mu, const
   rc = cb2_arena_reserve(ctx, total + loo_need + out_bytes + 4096);
   if (rc) return rc;
   std::vector<const double*> dev(B);
+  // small batches: pack every input into pinned staging and upload with one copy
+  const bool packed = total <= ((size_t)4 << 20) && cb2_pinned_reserve(ctx, total + 256) == CB2_OK;
+  char* first = nullptr;
   for (int b = 0; b < B; ++b) {
-    double* p = (double*)cb2_arena_alloc(ctx, (size_t)N[b] * d * sizeof(double));
+    const size_t nb = (size_t)N[b] * d * sizeof(double);
+    double* p = (double*)cb2_arena_alloc(ctx, nb);
     if (!p) return cb2_fail(ctx, CB2_ERR_NOMEM, "loo scratch exhausted");
-    CB2_CUDA(ctx, cudaMemcpyAsync(p, mu[b], (size_t)N[b] * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (!first) first = (char*)p;
+    if (packed) memcpy(ctx->pinned + ((char*)p - first), mu[b], nb);
+    else CB2_CUDA(ctx, cudaMemcpyAsync(p, mu[b], nb, cudaMemcpyHostToDevice, ctx->stream));
     dev[b] = p;
+  }
+  if (packed) {
+    const size_t span = (size_t)((const char*)dev[B - 1] - first) + (size_t)N[B - 1] * d * sizeof(double);
+    CB2_CUDA(ctx, cudaMemcpyAsync(first, ctx->pinned, span, cudaMemcpyHostToDevice, ctx->stream));
   }
   double* out_dev = (double*)cb2_arena_alloc(ctx, sizeof(double) * B * d);
   void* scratch = cb2_arena_alloc(ctx, loo_need);

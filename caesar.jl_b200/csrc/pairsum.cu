@@ -613,8 +613,7 @@ extern "C" int cb2_mmd_se_batch_dev(cb2_ctx* ctx, const double* a_dev, int N, co
   // aa, bb are invariant under a rigid transform of b: one mmd pass, then the K cross terms
   double a0[3] = {0, 0, 0}, s3[3];
   CB2_CUDA(ctx, cudaMemcpyAsync(a0, a_dev, sizeof(double) * dim, cudaMemcpyDeviceToHost, ctx->stream));
-  double* s3_dev = nullptr;
-  CB2_CUDA(ctx, cudaMalloc((void**)&s3_dev, 3 * sizeof(double)));
+  double* s3_dev = ctx->small_dev;
   rc = ctx->precision == CB2_FP64 ? mmd_sums_dev_impl<double>(ctx, a_dev, N, b_dev, M, dim, bw, 0, N, 0, M, s3_dev)
                                   : mmd_sums_dev_impl<float>(ctx, a_dev, N, b_dev, M, dim, bw, 0, N, 0, M, s3_dev);
   if (rc == CB2_OK) {
@@ -622,7 +621,6 @@ extern "C" int cb2_mmd_se_batch_dev(cb2_ctx* ctx, const double* a_dev, int N, co
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = cb2_fail(ctx, CB2_ERR_CUDA, "mmd readback: %s", cudaGetErrorString(e));
   }
-  cudaFree(s3_dev);
   if (rc) return rc;
   return ctx->precision == CB2_FP64
              ? cb2_se_batch_core<double>(ctx, a_dev, N, b_dev, M, dim, bw, a0, coords, K, backward, &s3[0], &s3[2], 0, 0, vals, grads)

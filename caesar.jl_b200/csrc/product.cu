@@ -605,23 +605,39 @@ static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B
   std::vector<std::vector<cb2_density>> ddens(B);
   std::vector<std::vector<const double*>> bw_host(B);
   int rc = CB2_OK;
+  // Small synchronous batches (the solver's usual N = 100..1000 particles) are packed into pinned staging: ONE H2D copy of
+  // all inputs and ONE D2H copy of all outputs instead of one copy per array.  Large batches copy array by array straight
+  // from / to the caller's memory (an extra host memcpy of tens of MB would cost more than the copy calls).
+  const bool packed = !own && total <= ((size_t)4 << 20) && cb2_pinned_reserve(ctx, total + 256) == CB2_OK;
+  char* stage = packed ? ctx->pinned : nullptr;
   cudaEventRecord(ctx->ev[4], ctx->stream);
+  // device block layout: every input of every product first, then every output (so that each side is one contiguous range)
   for (int b = 0; b < B && rc == CB2_OK; ++b) {
     ddens[b].assign(descs[b].dens, descs[b].dens + descs[b].D);
     for (int j = 0; j < descs[b].D; ++j) {
       const cb2_density& dn = descs[b].dens[j];
-      double* dp = (double*)take(sizeof(double) * (size_t)dn.N * d);
-      e = cudaMemcpyAsync(dp, dn.pts, sizeof(double) * (size_t)dn.N * d, cudaMemcpyHostToDevice, ctx->stream);
+      const size_t pb = sizeof(double) * (size_t)dn.N * d, wb = sizeof(double) * (size_t)dn.N;
+      double* dp = (double*)take(pb);
+      if (packed) memcpy(stage + ((char*)dp - p), dn.pts, pb);
+      else e = cudaMemcpyAsync(dp, dn.pts, pb, cudaMemcpyHostToDevice, ctx->stream);
       ddens[b][j].pts = dp;
       if (dn.w && e == cudaSuccess) {
-        double* wp = (double*)take(sizeof(double) * (size_t)dn.N);
-        e = cudaMemcpyAsync(wp, dn.w, sizeof(double) * (size_t)dn.N, cudaMemcpyHostToDevice, ctx->stream);
+        double* wp = (double*)take(wb);
+        if (packed) memcpy(stage + ((char*)wp - p), dn.w, wb);
+        else e = cudaMemcpyAsync(wp, dn.w, wb, cudaMemcpyHostToDevice, ctx->stream);
         ddens[b][j].w = wp;
       }
       if (e != cudaSuccess) { rc = cb2_fail(ctx, CB2_ERR_CUDA, "H2D copy: %s", cudaGetErrorString(e)); break; }
       bw_host[b].push_back(dn.bw);
     }
     dd[b].dens = ddens[b].data();
+  }
+  const size_t in_bytes = off;
+  if (rc == CB2_OK && packed && in_bytes) {
+    e = cudaMemcpyAsync(p, stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) rc = cb2_fail(ctx, CB2_ERR_CUDA, "H2D copy: %s", cudaGetErrorString(e));
+  }
+  for (int b = 0; b < B; ++b) {
     dd[b].pts_out = (double*)take(sizeof(double) * (size_t)descs[b].Nout * d);
     dd[b].labels_out = descs[b].labels_out ? (int32_t*)take(sizeof(int32_t) * (size_t)descs[b].Nout * descs[b].D) : nullptr;
     dd[b].bw_out = descs[b].bw_out ? (double*)take(sizeof(double) * d) : nullptr;
@@ -629,13 +645,24 @@ static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B
   if (rc == CB2_OK) { cudaEventRecord(ctx->ev[5], ctx->stream); rc = product_batch_dev_locked(ctx, dd.data(), B, circular, d, seed, &bw_host, nullptr); }
   if (rc != CB2_OK) { cudaStreamSynchronize(ctx->stream); if (own) cudaFree(blk); return rc; }
   cudaEventRecord(ctx->ev[6], ctx->stream);
-  for (int b = 0; b < B; ++b) {
-    e = cudaMemcpyAsync(descs[b].pts_out, dd[b].pts_out, sizeof(double) * (size_t)descs[b].Nout * d, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && descs[b].labels_out)
-      e = cudaMemcpyAsync(descs[b].labels_out, dd[b].labels_out, sizeof(int32_t) * (size_t)descs[b].Nout * descs[b].D, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && descs[b].bw_out)
-      e = cudaMemcpyAsync(descs[b].bw_out, dd[b].bw_out, sizeof(double) * d, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e != cudaSuccess) { cudaStreamSynchronize(ctx->stream); if (own) cudaFree(blk); return cb2_fail(ctx, CB2_ERR_CUDA, "D2H copy: %s", cudaGetErrorString(e)); }
+  if (packed) {
+    e = cudaMemcpyAsync(stage + in_bytes, p + in_bytes, off - in_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "D2H copy: %s", cudaGetErrorString(e));
+    for (int b = 0; b < B; ++b) {
+      memcpy(descs[b].pts_out, stage + ((char*)dd[b].pts_out - p), sizeof(double) * (size_t)descs[b].Nout * d);
+      if (descs[b].labels_out) memcpy(descs[b].labels_out, stage + ((char*)dd[b].labels_out - p), sizeof(int32_t) * (size_t)descs[b].Nout * descs[b].D);
+      if (descs[b].bw_out) memcpy(descs[b].bw_out, stage + ((char*)dd[b].bw_out - p), sizeof(double) * d);
+    }
+  } else {
+    for (int b = 0; b < B; ++b) {
+      e = cudaMemcpyAsync(descs[b].pts_out, dd[b].pts_out, sizeof(double) * (size_t)descs[b].Nout * d, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess && descs[b].labels_out)
+        e = cudaMemcpyAsync(descs[b].labels_out, dd[b].labels_out, sizeof(int32_t) * (size_t)descs[b].Nout * descs[b].D, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess && descs[b].bw_out)
+        e = cudaMemcpyAsync(descs[b].bw_out, dd[b].bw_out, sizeof(double) * d, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e != cudaSuccess) { cudaStreamSynchronize(ctx->stream); if (own) cudaFree(blk); return cb2_fail(ctx, CB2_ERR_CUDA, "D2H copy: %s", cudaGetErrorString(e)); }
+    }
   }
   cudaEventRecord(ctx->ev[7], ctx->stream);
   if (pend) {  // asynchronous: hand the block to the ticket
