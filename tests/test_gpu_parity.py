@@ -353,3 +353,56 @@ def test_product_with_weighted_kernels(cb, ctx64, ctx32):
     pts32, lab32 = cb.product_points(dens, (0, 0, 1), 400, seed=8, ctx=ctx32)
     o24, l24 = oracle.product(dens, 400, seed=8, circular=[0, 0, 1], ubits=24)
     assert (lab32 == l24).all(axis=1).mean() > 0.9 and np.allclose(pts32.mean(0), o24.mean(0), atol=0.1)
+
+
+def test_product_random_shapes_reproduce_oracle(cb, ctx64):
+    """Randomised shape sweep (ragged message sizes, every dimension 1..6, random circular masks, optional weights,
+    Niter 0..2): FP64 device chains must select the oracle's labels."""
+    rng = np.random.default_rng(2024)
+    for case in range(24):
+        d = int(rng.integers(1, 7))
+        D = int(rng.integers(2, 7))
+        circ = tuple(int(c) for c in rng.integers(0, 2, size=d))
+        dens = []
+        for j in range(D):
+            N = int(rng.choice([1, 2, 3, 5, 17, 64, 100, 129, 300]))
+            pts = rng.normal(size=(N, d)) * rng.uniform(0.2, 1.0, size=d) + rng.normal(size=d) * 0.3
+            for i, c in enumerate(circ):
+                if c:
+                    pts[:, i] = (pts[:, i] + rng.uniform(-3, 3) + np.pi) % (2 * np.pi) - np.pi  # may straddle the cut
+            bw = rng.uniform(0.1, 0.5, size=d)
+            w = rng.uniform(0.1, 1.0, size=N) if rng.uniform() < 0.3 else None
+            dens.append((pts, bw, w))
+        Nout, niter = int(rng.choice([1, 7, 130, 257])), int(rng.integers(0, 3))
+        pts, lab = cb.product_points(dens, circ, Nout, seed=case, niter=niter, stream=case, ctx=ctx64)
+        opts, olab = oracle.product(dens, Nout, seed=case, circular=list(circ), niter=niter, stream=case, ubits=53)
+        same = (lab == olab).all(axis=1)
+        assert same.mean() >= 0.97, (case, d, D, circ, [len(x[0]) for x in dens], Nout, niter, same.mean())
+        assert np.allclose(pts[same], opts[same], atol=1e-8), case
+
+
+def test_pair_kernels_random_shapes(cb, ctx):
+    """Randomised sizes around the tile boundaries (1024 rows, 512/4096 columns) for mmd, evaluate, bandwidth."""
+    rng = np.random.default_rng(99)
+    tol = RTOL[ctx.precision]
+    for case in range(10):
+        d = int(rng.integers(1, 7))
+        N, M = (int(rng.choice([1, 2, 511, 512, 513, 1023, 1024, 1025, 4095, 4097, 6000])) for _ in range(2))
+        a, b = rng.normal(size=(N, d)) + 3.0, rng.normal(size=(M, d)) * 0.8 + 3.2
+        bw = float(rng.uniform(0.05, 2.0))
+        _, sums = oracle.mmd(a, b, bw, return_sums=True)
+        assert np.allclose(cb.mmd_sums(a, b, bw, ctx=ctx), sums, rtol=tol), (case, d, N, M)
+        sig = rng.uniform(0.3, 1.2, size=d)
+        Q = int(rng.choice([1, 300, 1025]))
+        q = rng.normal(size=(Q, d)) + 3.0
+        w = rng.uniform(0.2, 1.0, size=N) if case % 2 else None
+        got, want = cb.MKD([0] * d, a, sig, w)(q, ctx=ctx), oracle.kde_eval(a, sig, q, w)
+        bulk = want > 1e-12 * want.max()
+        assert np.allclose(got[bulk], want[bulk], rtol=3 * tol), (case, d, N, Q)
+        # far tails: the FP32 exponent itself carries ~|log2 p| * 2^-24 of error, so compare in the log domain there
+        tail = ~bulk & (want > (1e-30 if ctx.precision == "fp32" else 1e-300))  # FP32 sums flush to zero below 2^-126
+        assert np.allclose(np.log(np.maximum(got[tail], 1e-300)), np.log(want[tail]), rtol=0, atol=1e-3 if ctx.precision == "fp32" else 1e-9)
+    for N in (2, 3, 100, 1024, 1025, 2500):
+        x = np.c_[rng.normal(size=N) * 2.0, rng.uniform(-np.pi, np.pi, size=N)]
+        got, want = cb.kde_bandwidth(x, (0, 1), ctx=ctx), oracle.kde_bw_loo(x, circular=[0, 1])
+        assert np.allclose(got, want, rtol=1e-6 if ctx.precision == "fp64" else 3e-2), (N, got, want)
