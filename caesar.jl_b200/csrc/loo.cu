@@ -167,14 +167,33 @@ loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict
     __syncthreads();
     const int jn = cend - cs;
     if (diag) {  // all ordered pairs inside the block, self term excluded
-      for (int j = 0; j < jn; ++j) {
-        const T q = sx[j];
+      // a warp's rows are tid_base + lane + 256 r: its self terms sit in the 32-column groups with
+      // (j0 - tid_base) % 256 == 0 only; every other group runs without the per-pair predicate (warp-uniform branch)
+      const int tid_base = tid & ~31;
+      for (int j0 = 0; j0 < jn; j0 += 32) {
+        const int je = min(j0 + 32, jn);
+        if (((j0 - tid_base) & (kThreads - 1)) == 0) {
+          for (int j = j0; j < je; ++j) {
+            const T q = sx[j];
 #pragma unroll
-        for (int r = 0; r < kRI; ++r) {
-          T df = xi[r] - q;
-          if (circ) { T ad = fabs(df); df = fmin(ad, period - ad); }
-          T kv = fast_exp2(-(df * df));
-          acc[r] += (cs + j == rowi[r]) ? T(0) : kv;
+            for (int r = 0; r < kRI; ++r) {
+              T df = xi[r] - q;
+              if (circ) { T ad = fabs(df); df = fmin(ad, period - ad); }
+              T kv = fast_exp2(-(df * df));
+              acc[r] += (cs + j == rowi[r]) ? T(0) : kv;
+            }
+          }
+        } else {
+#pragma unroll 8
+          for (int j = j0; j < je; ++j) {
+            const T q = sx[j];
+#pragma unroll
+            for (int r = 0; r < kRI; ++r) {
+              T df = xi[r] - q;
+              if (circ) { T ad = fabs(df); df = fmin(ad, period - ad); }
+              acc[r] += fast_exp2(-(df * df));
+            }
+          }
         }
       }
     } else {  // tile above the diagonal: the row block is complete (1024 valid rows); columns may be ragged
@@ -410,8 +429,11 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
       cp_elems += (long long)pr.nstride * pr.nrb;
       if (N[b] > maxN) maxN = N[b];
       if (pr.small) small_ids.push_back(b * d + k);
-      else for (int rb = 0; rb < pr.nrb; ++rb) cta_map.push_back(make_int2(b * d + k, rb));
     }
+  // row block rb of a problem visits nrb - rb column tiles: launch the heavy CTAs first (largest-first list scheduling)
+  for (int rb = 0; rb < (maxN + kThreads * kRI - 1) / (kThreads * kRI); ++rb)
+    for (int p = 0; p < P; ++p)
+      if (!probs[p].small && rb < probs[p].nrb) cta_map.push_back(make_int2(p, rb));
   if (maxN > CB2_MAX_PRODUCT_N) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "bandwidth search supports N <= %d (got %d)", CB2_MAX_PRODUCT_N, maxN);
   const bool f64 = ctx->precision == CB2_FP64;
   const size_t tsz = f64 ? sizeof(double) : sizeof(float);
