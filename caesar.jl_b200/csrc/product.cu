@@ -25,7 +25,7 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
 namespace {
 
 constexpr int kMaxLev = 15;        // depth <= 14 for N <= 16384
-constexpr int kTreeThreads = 1024;
+constexpr int kTreeThreads = 512;
 constexpr int kS = 128;            // chains (threads) per Gibbs CTA
 constexpr int kNCH = 32;           // chunk partial sums per chain
 constexpr int kTileBytesF32 = 8192;
