@@ -229,9 +229,13 @@ template <typename T>
 __global__ void kde_sample_kernel(const double* __restrict__ mu, const double* __restrict__ cdf, int d, int N,
                                   double sig0, double sig1, double sig2, double sig3, double sig4, double sig5,
                                   uint32_t circ_mask, int n, uint32_t k0, uint32_t k1, uint32_t stream,
-                                  double* __restrict__ out) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
+                                  int per_stream, uint32_t stream_stride, double* __restrict__ out) {
+  // draw t of the launch is sample (t % per_stream) of Philox stream (stream + stream_stride * (t / per_stream)):
+  // many independent sample sets (one per alignment of a ScatterAlign batch) in one launch
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int s = t % per_stream;
+  stream += stream_stride * (uint32_t)(t / per_stream);
   const double sig[6] = {sig0, sig1, sig2, sig3, sig4, sig5};
   uint32_t o[4];
   philox4x32_10((uint32_t)s, 0u, stream, 2u, k0, k1, o);
@@ -258,7 +262,7 @@ __global__ void kde_sample_kernel(const double* __restrict__ mu, const double* _
     double z = (k & 1) ? r * sn : r * cs;
     double v = mu[(size_t)idx * d + k] + sig[k] * z;
     if (circ_mask >> k & 1) v = wrap_pi(v);
-    out[(size_t)s * d + k] = v;
+    out[(size_t)t * d + k] = v;
   }
 }
 
@@ -311,7 +315,10 @@ struct SubSpec { int rows_is_b, cols_is_b, row0, row1, ncols, xf, col0 = 0; };
 template <typename T, int MODE>
 int run_pairs_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev, int M, int d, double scale,
                   const std::vector<SubSpec>& specs, const std::vector<T>& xf_host, double** result_dev,
-                  size_t extra_bytes, void** extra_ptr) {
+                  size_t extra_bytes, void** extra_ptr, bool reuse_prev = false) {
+  // reuse_prev: the previous call on this context had the same clouds, sub-problems and sizes and nothing else touched
+  // the arena since (consecutive cost evaluations of one BFGS batch): the arena layout is a pure function of the
+  // sizes, so the converted records and the tile tables are still in place -- only the transforms are uploaded again.
   const int rec = rec_of(d);
   std::vector<Tile> tiles;
   std::vector<int> sub_tile0;
@@ -355,6 +362,7 @@ int run_pairs_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev,
   if (!ra || !rb || !subs_dev || !tiles_dev || !st0_dev || !xf_dev || !tile_out || !res)
     return cb2_fail(ctx, CB2_ERR_NOMEM, "pair scratch exhausted");
 
+  if (!reuse_prev) {
   ConvertArgs ca;
   memset(&ca, 0, sizeof(ca));
   for (int k = 0; k < 8; ++k) ca.scale[k] = scale;
@@ -375,6 +383,7 @@ int run_pairs_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev,
   if (ntiles)
     CB2_CUDA(ctx, cudaMemcpyAsync(tiles_dev, tiles.data(), sizeof(Tile) * (size_t)ntiles, cudaMemcpyHostToDevice, ctx->stream));
   CB2_CUDA(ctx, cudaMemcpyAsync(st0_dev, sub_tile0.data(), sizeof(int) * (nsub + 1), cudaMemcpyHostToDevice, ctx->stream));
+  }
   if (!xf_host.empty())
     CB2_CUDA(ctx, cudaMemcpyAsync(xf_dev, xf_host.data(), sizeof(T) * xf_host.size(), cudaMemcpyHostToDevice, ctx->stream));
   rc = launch_pair_tiles<T, MODE>(ctx, d, ntiles, subs_dev, tiles_dev, xf_dev, tile_out, nullptr, 0);
@@ -451,7 +460,7 @@ void se_matrix(int dim, const double* c, int backward, double* R, double* t) {
 template <typename T>
 int cb2_se_batch_core(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev, int M, int dim, double bw,
                       const double* a0_host, const double* coords, int K, int backward, const double* aa, const double* bb,
-                      int row_stride, int col_stride, double* vals, double* grads) {
+                      int row_stride, int col_stride, double* vals, double* grads, bool reuse_prev) {
   // sub-problem k pairs rows [k*row_stride, k*row_stride+N) of a with columns [k*col_stride, k*col_stride+M) of b
   // (strides 0: every candidate transform sees the same two clouds); aa/bb hold 1 (strides 0) or K self terms.
   const int nc = dim == 2 ? 3 : 6;
@@ -470,7 +479,7 @@ int cb2_se_batch_core(cb2_ctx* ctx, const double* a_dev, int N, const double* b_
   std::vector<SubSpec> specs(K);
   for (int k = 0; k < K; ++k) specs[k] = {0, 1, k * row_stride, k * row_stride + N, M, k, k * col_stride};
   double* res = nullptr;
-  int rc = run_pairs_dev<T, 1>(ctx, a_dev, N + (K - 1) * row_stride, b_dev, M + (K - 1) * col_stride, dim, s, specs, xf, &res, 0, nullptr);
+  int rc = run_pairs_dev<T, 1>(ctx, a_dev, N + (K - 1) * row_stride, b_dev, M + (K - 1) * col_stride, dim, s, specs, xf, &res, 0, nullptr, reuse_prev);
   if (rc) return rc;
   std::vector<double> h((size_t)K * 8);
   CB2_CUDA(ctx, cudaMemcpyAsync(h.data(), res, sizeof(double) * 8 * K, cudaMemcpyDeviceToHost, ctx->stream));
@@ -520,9 +529,9 @@ int cb2_se_batch_core(cb2_ctx* ctx, const double* a_dev, int N, const double* b_
   return CB2_OK;
 }
 template int cb2_se_batch_core<float>(cb2_ctx*, const double*, int, const double*, int, int, double, const double*,
-                                      const double*, int, int, const double*, const double*, int, int, double*, double*);
+                                      const double*, int, int, const double*, const double*, int, int, double*, double*, bool);
 template int cb2_se_batch_core<double>(cb2_ctx*, const double*, int, const double*, int, int, double, const double*,
-                                       const double*, int, int, const double*, const double*, int, int, double*, double*);
+                                       const double*, int, int, const double*, const double*, int, int, double*, double*, bool);
 
 // ---------------------------------------------------------------------------------------------------
 // C ABI
@@ -623,8 +632,8 @@ extern "C" int cb2_mmd_se_batch_dev(cb2_ctx* ctx, const double* a_dev, int N, co
   }
   if (rc) return rc;
   return ctx->precision == CB2_FP64
-             ? cb2_se_batch_core<double>(ctx, a_dev, N, b_dev, M, dim, bw, a0, coords, K, backward, &s3[0], &s3[2], 0, 0, vals, grads)
-             : cb2_se_batch_core<float>(ctx, a_dev, N, b_dev, M, dim, bw, a0, coords, K, backward, &s3[0], &s3[2], 0, 0, vals, grads);
+             ? cb2_se_batch_core<double>(ctx, a_dev, N, b_dev, M, dim, bw, a0, coords, K, backward, &s3[0], &s3[2], 0, 0, vals, grads, false)
+             : cb2_se_batch_core<float>(ctx, a_dev, N, b_dev, M, dim, bw, a0, coords, K, backward, &s3[0], &s3[2], 0, 0, vals, grads, false);
 }
 
 extern "C" int cb2_mmd_se_batch(cb2_ctx* ctx, const double* a, int N, const double* b, int M, int dim, double bw,
@@ -745,9 +754,9 @@ extern "C" int cb2_kde_sample(cb2_ctx* ctx, const double* mu, const double* sigm
   }
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   if (ctx->precision == CB2_FP64)
-    kde_sample_kernel<double><<<(n + 127) / 128, 128, 0, ctx->stream>>>(dev[0], cdf, d, N, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5], mask, n, k0, k1, stream, dev[3]);
+    kde_sample_kernel<double><<<(n + 127) / 128, 128, 0, ctx->stream>>>(dev[0], cdf, d, N, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5], mask, n, k0, k1, stream, n, 0u, dev[3]);
   else
-    kde_sample_kernel<float><<<(n + 127) / 128, 128, 0, ctx->stream>>>(dev[0], cdf, d, N, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5], mask, n, k0, k1, stream, dev[3]);
+    kde_sample_kernel<float><<<(n + 127) / 128, 128, 0, ctx->stream>>>(dev[0], cdf, d, N, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5], mask, n, k0, k1, stream, n, 0u, dev[3]);
   ctx->launches++;
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, dev[3], (size_t)n * d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
@@ -790,9 +799,12 @@ int scatter_align_impl(cb2_ctx* ctx, const double* sa_dev, const double* sb_dev,
 
   std::vector<Bfgs> st(K);
   std::vector<double> coords((size_t)K * nc), vals(K), grads((size_t)K * nc);
+  bool have_plan = false;  // after the first evaluation the converted records / tile tables are reused
   auto eval = [&]() {
-    return cb2_se_batch_core<T>(ctx, sa_dev, S, sb_dev, S, dim, bw, a0, coords.data(), K, 1, aa.data(), bb.data(), S, S,
-                                vals.data(), grads.data());
+    int r = cb2_se_batch_core<T>(ctx, sa_dev, S, sb_dev, S, dim, bw, a0, coords.data(), K, 1, aa.data(), bb.data(), S, S,
+                                 vals.data(), grads.data(), have_plan);
+    have_plan = true;
+    return r;
   };
   for (int k = 0; k < K; ++k) {
     Bfgs& b = st[k];
@@ -920,12 +932,12 @@ extern "C" int cb2_scatter_align(cb2_ctx* ctx, const cb2_density* cloud1, const 
     }
     double sg[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < dim; ++i) sg[i] = cl[c]->bw[i];
-    for (int k = 0; k < K; ++k) {
-      double* out = dev[6 + c] + (size_t)k * S * dim;
+    {  // alignment k draws from Philox stream 2k + c: all K sample sets of this cloud in one launch
+      const int nt = K * S;
       if (ctx->precision == CB2_FP64)
-        kde_sample_kernel<double><<<(S + 127) / 128, 128, 0, ctx->stream>>>(dev[c * 3], cdf, dim, cl[c]->N, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5], 0u, S, k0, k1, (uint32_t)(2 * k + c), out);
+        kde_sample_kernel<double><<<(nt + 127) / 128, 128, 0, ctx->stream>>>(dev[c * 3], cdf, dim, cl[c]->N, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5], 0u, nt, k0, k1, (uint32_t)c, S, 2u, dev[6 + c]);
       else
-        kde_sample_kernel<float><<<(S + 127) / 128, 128, 0, ctx->stream>>>(dev[c * 3], cdf, dim, cl[c]->N, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5], 0u, S, k0, k1, (uint32_t)(2 * k + c), out);
+        kde_sample_kernel<float><<<(nt + 127) / 128, 128, 0, ctx->stream>>>(dev[c * 3], cdf, dim, cl[c]->N, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5], 0u, nt, k0, k1, (uint32_t)c, S, 2u, dev[6 + c]);
       ctx->launches++;
     }
     cudaError_t e = cudaGetLastError();
