@@ -420,6 +420,34 @@ def mmd_extras(cb, ctx, torch, tstream, rank=0, world=1, dist=None):
                           "t_products_s": st["t_products"], "t_bandwidth_s": st["t_bandwidth"], "x6_ppe": [float(v) for v in x6],
                           "cpu_oracle_solve_s": sto["seconds"], "cpu_t_products_s": sto["t_products"], "cpu_t_bandwidth_s": sto["t_bandwidth"]}
     out["hex_pose2_solve"] = hexr
+    # C4: multihypo-shaped products: 256 variables, D=3 messages, each a 4-mode mixture in (x, y, theta), N = N_out = 1000
+    corners = np.array([[0, 0, 0.0], [10, 0, 1.5], [10, 10, 3.0], [0, 10, -1.5]])
+
+    def c4_group(v):
+        r = np.random.default_rng(4000 + v)
+        g = []
+        for j in range(3):
+            cs = corners.copy()
+            cs[1:] += r.normal(size=(3, 3)) * [3.0, 3.0, 0.5] * (j + 1)
+            pts = cs[r.integers(0, 4, size=1000)] + r.normal(size=(1000, 3)) * [0.4, 0.4, 0.1]
+            pts[:, 2] = (pts[:, 2] + np.pi) % (2 * np.pi) - np.pi
+            g.append(cb.ManifoldKernelDensity("Pose2", pts, 0.53 * pts.std(0) * 1000 ** -0.2))
+        return g
+    groups = [c4_group(v) for v in range(256)]
+    cb.manifoldProducts(groups[:8], "Pose2", N=1000, seed=1, ctx=ctx)
+    t0 = time.perf_counter()
+    res = cb.manifoldProducts(groups, "Pose2", N=1000, seed=2, ctx=ctx)
+    c4_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for g in groups[:4]:
+        o, _ = oracle.product([(m.pts, m.bw) for m in g], 1000, seed=2, circular=[0, 0, 1], ubits=24)
+        oracle.kde_bw_loo(o, circular=[0, 0, 1])
+    c4_cpu = time.perf_counter() - t0
+    near = float(np.mean([(np.linalg.norm(r.pts[:, :2], axis=1) < 2.0).mean() for r in res]))
+    out["c4_multihypo_products"] = {"products": 256, "D": 3, "N": 1000, "d": 3, "seconds_e2e": c4_s,
+                                    "samples_per_s_e2e": 256 * 1000 / c4_s, "cpu_samples_per_s": 4 * 1000 / c4_cpu,
+                                    "cpu_sample": "4 of the 256 products (product + LOO bandwidth), oracle on all host cores",
+                                    "mass_at_common_corner": near}
     return out
 
 
