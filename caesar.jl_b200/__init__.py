@@ -18,7 +18,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from ._capi import CB2_FP32, CB2_FP64, CB2Error, Density, ProductDesc, f64, ptr, circ_arr
+from ._capi import CB2_FP32, CB2_FP64, CB2Error, Density, ProductDesc, ConvDesc, f64, ptr, circ_arr
 
 # variable types -> per-coordinate topology: 1 = circular (wrap to (-pi, pi])
 MANIFOLDS = {
@@ -401,6 +401,42 @@ def product_points(dens, circular, Nout, seed=0, niter=1, stream=0, sample_offse
     circ = circ_arr(ms[0].circular, d)
     ctx.check(_capi.lib().cb2_product_batch(ctx._h, descs, 1, ptr(circ), d, int(seed)))
     return outs[0], labels[0]
+
+
+FACTOR_PRIOR_POSE2, FACTOR_POSE2POSE2, FACTOR_POSE2POINT2_BEARINGRANGE = 0, 1, 2
+
+
+def approxConvBatch(convs, seed=0, ctx=None):
+    """Closed-form `approxConvBelief` for a batch of factors in one device launch.
+    convs: list of dicts {kind, reverse, N, mean(3), chol(3x3 lower), stream, src (n x d) | None, aux (n x 3) | None}.
+    Returns the list of N x d_tgt sample arrays."""
+    ctx = ctx or context()
+    B = len(convs)
+    descs = (ConvDesc * B)()
+    keep, outs = [], []
+    for b, c in enumerate(convs):
+        kind, rev = int(c["kind"]), int(bool(c.get("reverse", False)))
+        dt = 2 if (kind == FACTOR_POSE2POINT2_BEARINGRANGE and not rev) else 3
+        out = np.zeros((int(c["N"]), dt))
+        src = None if c.get("src") is None else f64(c["src"])
+        aux = None if c.get("aux") is None else f64(c["aux"])
+        keep += [src, aux]
+        outs.append(out)
+        d = descs[b]
+        d.kind, d.reverse, d.N, d.stream = kind, rev, int(c["N"]), int(c.get("stream", b))
+        d.n_src = 0 if src is None else src.shape[0]
+        d.n_aux = 0 if aux is None else aux.shape[0]
+        d.src = None if src is None else src.ctypes.data
+        d.aux = None if aux is None else aux.ctypes.data
+        mean = np.resize(np.asarray(c["mean"], dtype=np.float64), 3)
+        chol = np.asarray(c["chol"], dtype=np.float64).reshape(9)
+        for i in range(3):
+            d.mean[i] = mean[i]
+        for i in range(9):
+            d.chol[i] = chol[i]
+        d.out = out.ctypes.data
+    ctx.check(_capi.lib().cb2_approx_conv_batch(ctx._h, descs, B, int(seed)))
+    return outs
 
 
 def tree_levels(pts, bw, w=None, ctx=None):

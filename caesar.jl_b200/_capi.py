@@ -30,6 +30,12 @@ class ProductDesc(C.Structure):
                 ("labels_out", C.c_void_p), ("bw_out", C.c_void_p)]
 
 
+class ConvDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reverse", C.c_int32), ("N", C.c_int32), ("n_src", C.c_int32), ("src", C.c_void_p),
+                ("aux", C.c_void_p), ("n_aux", C.c_int32), ("stream", C.c_uint32), ("mean", C.c_double * 3),
+                ("chol", C.c_double * 9), ("out", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -67,6 +73,7 @@ def lib():
             "cb2_product_batch_submit": (i32, [vp, C.POINTER(ProductDesc), i32, vp, i32, u64, C.POINTER(C.c_int64)]),
             "cb2_wait": (i32, [vp, C.c_int64]),
             "cb2_tree_debug": (i32, [vp, C.POINTER(Density), i32, i32, vp, vp, vp, vp, vp, vp]),
+            "cb2_approx_conv_batch": (i32, [vp, C.POINTER(ConvDesc), i32, u64]),
             "cb2_scatter_align": (i32, [vp, C.POINTER(Density), C.POINTER(Density), i32, i32, f64, vp, i32, u64, i32, f64,
                                         vp, vp, vp]),
         }
@@ -81,7 +88,7 @@ EXPORTS = ["cb2_create", "cb2_destroy", "cb2_last_error", "cb2_precision", "cb2_
            "cb2_kernel_launches", "cb2_device_sm_count", "cb2_last_stage_ms", "cb2_mmd", "cb2_mmd_sums",
            "cb2_mmd_sums_dev", "cb2_mmd_se_batch", "cb2_mmd_se_batch_dev", "cb2_kde_eval", "cb2_kde_bw_loo",
            "cb2_kde_bw_loo_batch", "cb2_kde_sample", "cb2_product", "cb2_product_batch", "cb2_product_batch_dev",
-           "cb2_product_batch_submit", "cb2_wait", "cb2_tree_debug", "cb2_scatter_align"]
+           "cb2_product_batch_submit", "cb2_wait", "cb2_tree_debug", "cb2_scatter_align", "cb2_approx_conv_batch"]
 
 
 def f64(x):

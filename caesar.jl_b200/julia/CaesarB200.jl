@@ -186,6 +186,31 @@ function ApproxManifoldProducts.manifoldProduct(ff::AbstractVector{<:ManifoldKer
   return manikde!(M, pts; bw = bws[1])
 end
 
+# ------------------------------------------------------------------------------------------------ approxConv (closed form)
+# Proposals of closed-form relative factors (PriorPose2, Pose2Pose2, Pose2Point2BearingRange), all factors of a Gibbs
+# colour in one launch; hook: IIF.approxConvBelief / sampleFactor for these factor types.
+struct CB2ConvDesc
+  kind::Int32
+  reverse::Int32
+  N::Int32
+  n_src::Int32
+  src::Ptr{Float64}
+  aux::Ptr{Float64}
+  n_aux::Int32
+  stream::UInt32
+  mean::NTuple{3,Float64}
+  chol::NTuple{9,Float64}      # lower Cholesky factor, row-major
+  out::Ptr{Float64}
+end
+
+function b200_approx_conv!(descs::Vector{CB2ConvDesc}; seed::UInt64 = rand(UInt64), ctx::Context = context())
+  lock(ctx.lk) do
+    _check(ctx, ccall((:cb2_approx_conv_batch, libcb2), Cint, (Ptr{Cvoid}, Ptr{CB2ConvDesc}, Cint, UInt64),
+                      ctx.h, descs, length(descs), seed))
+  end
+  return nothing
+end
+
 # ------------------------------------------------------------------------------------------------ ScatterAlign getSample
 # drop-in body for Caesar's getSample(cf::CalcFactor{<:ScatterAlignPose2/3}) (ext/Images/ScatterAlignPose2.jl:155-187):
 # K alignments (one per particle of the solver) as one batched BFGS on the device.

@@ -121,6 +121,32 @@ def approx_conv(fg, labels, factor, target, rng):
     raise TypeError(f"unsupported factor {type(factor).__name__}")
 
 
+def conv_desc(fg, labels, factor, target, stream):
+    """Descriptor of one closed-form convolution for `approxConvBatch` (device) / `oracle.approx_conv` (CPU)."""
+    N = fg.N
+    if isinstance(factor, PriorPose2):
+        return dict(kind=0, reverse=False, N=N, mean=factor.mean, chol=np.linalg.cholesky(factor.cov), stream=stream, src=None, aux=None)
+    other = labels[0] if labels[1] == target else labels[1]
+    src = fg.variables[other].belief.pts
+    if isinstance(factor, Pose2Pose2):
+        return dict(kind=1, reverse=target == labels[0], N=N, mean=factor.mean, chol=np.linalg.cholesky(factor.cov), stream=stream,
+                    src=src, aux=None)
+    if isinstance(factor, Pose2Point2BearingRange):
+        rev = target == labels[0]
+        return dict(kind=2, reverse=rev, N=N, mean=[factor.bearing[0], factor.range[0], 0.0],
+                    chol=np.diag([factor.bearing[1], factor.range[1], 0.0]), stream=stream, src=src,
+                    aux=fg.variables[target].belief.pts if rev else None)
+    raise TypeError(f"unsupported factor {type(factor).__name__}")
+
+
+def _convolve(fg, backend, items, rng, seed, stream0):
+    """items: [(labels, factor, target)].  Uses the backend's batched closed-form convolution when it has one
+    (device: one cb2_approx_conv_batch launch), else the NumPy fallback of this harness."""
+    if hasattr(backend, "approx_conv_batch"):
+        return backend.approx_conv_batch([conv_desc(fg, ls, f, t, stream0 + i) for i, (ls, f, t) in enumerate(items)], seed)
+    return [approx_conv(fg, ls, f, t, rng) for ls, f, t in items]
+
+
 def _colouring(fg):
     """Greedy colouring: variables of one colour share no factor and are updated in one batched product call."""
     colour, order = {}, list(fg.variables)
@@ -150,7 +176,7 @@ def solveGraph(fg, backend, gibbs_iters=3, seed=0, stats=None):
                 others = [l for l in ls if l != v]
                 if all(fg.variables[o].belief is not None for o in others) and not (
                         isinstance(f, Pose2Point2BearingRange) and v == ls[0]):
-                    pts = approx_conv(fg, ls, f, v, rng)
+                    pts = _convolve(fg, backend, [(ls, f, v)], rng, seed * 7919 + 1, 900000 + len(pending))[0]
                     fg.variables[v].belief = backend.manikde_batch(fg.variables[v].vartype, [pts])[0]
                     pending.remove(v)
                     progressed = True
@@ -159,17 +185,22 @@ def solveGraph(fg, backend, gibbs_iters=3, seed=0, stats=None):
             raise RuntimeError(f"cannot initialise {pending}")
     colours = _colouring(fg)
     stream = 0
+    conv_stream = 0
     for it in range(gibbs_iters):
         for group in colours:
             for vartype in ("Pose2", "Point2"):
                 vs = [v for v in group if fg.variables[v].vartype == vartype]
                 if not vs:
                     continue
-                props, counts = [], []
+                items, counts = [], []
                 for v in vs:
-                    ps = [approx_conv(fg, ls, f, v, rng) for ls, f in fg.factors_of(v)]
-                    props += ps
-                    counts.append(len(ps))
+                    fs = fg.factors_of(v)
+                    items += [(ls, f, v) for ls, f in fs]
+                    counts.append(len(fs))
+                tc = time.perf_counter()
+                props = _convolve(fg, backend, items, rng, seed * 7919 + 2 + it, conv_stream)
+                conv_stream += len(items)
+                stats["t_conv"] = stats.get("t_conv", 0.0) + time.perf_counter() - tc
                 tb = time.perf_counter()
                 mkds = backend.manikde_batch(vartype, props)
                 stats["t_bandwidth"] += time.perf_counter() - tb
@@ -213,3 +244,6 @@ class DeviceBackend:
 
     def products(self, vartype, groups, N, seed, streams):
         return self.cb.manifoldProducts(groups, vartype, N=N, Niter=1, seed=seed, streams=streams, bw="loo", ctx=self.ctx)
+
+    def approx_conv_batch(self, convs, seed):
+        return self.cb.approxConvBatch(convs, seed=seed, ctx=self.ctx)

@@ -155,6 +155,35 @@ int cb2_scatter_align(cb2_ctx* ctx, const cb2_density* cloud1, const cb2_density
                       int sample_count, double bw, const double* x0, int K, uint64_t seed,
                       int max_iter, double g_tol, double* coords_out, double* score_out, int32_t* iters_out);
 
+/* ---- approxConvBelief for closed-form relative factors ("next" row N1) ---------------------------
+ * Samples of the target variable implied by one factor and the current samples of its other variable -- the step IIF
+ * runs immediately before every product (R:docs/src/principles/approxConvDensities.md:25-34,107-113).  For the group
+ * factors below the per-particle solve is closed form: q = p o exp(z + noise) on SE(2) with the product exponential
+ * (same convention as ConsolidateRigidTransform.jl:32-36), l = t_p + r [cos(th_p + b), sin(th_p + b)] for bearing-range.
+ * Noise comes from Philox (seed; particle, draw, stream, tag 4): reproducible and independent of batching.
+ * B convolutions (all factors of all variables of one Gibbs colour) run as one launch. */
+typedef enum {
+  CB2_FACTOR_PRIOR_POSE2 = 0,               /* target ~ N(mean, L L^T), no source */
+  CB2_FACTOR_POSE2POSE2 = 1,                /* forward: x_j = x_i o exp(z);  reverse: x_i = x_j o exp(z)^-1 */
+  CB2_FACTOR_POSE2POINT2_BEARINGRANGE = 2   /* forward: landmark from pose;  reverse: pose position from landmark, heading from aux */
+} cb2_factor_kind;
+
+typedef struct {
+  int32_t kind;        /* cb2_factor_kind */
+  int32_t reverse;     /* 0: solve the factor's second variable from its first; 1: the other way round */
+  int32_t N;           /* particles to produce */
+  int32_t n_src;       /* samples available in src (particle i uses src[i % n_src]) */
+  const double* src;   /* d_src x n_src samples of the known variable; NULL for a prior */
+  const double* aux;   /* reverse bearing-range only: 3 x n_aux current samples of the target pose (heading is kept) */
+  int32_t n_aux;
+  uint32_t stream;     /* Philox stream id of this convolution */
+  double mean[3];      /* Pose2 prior / Pose2Pose2: [x, y, theta]; bearing-range: [bearing, range, 0] */
+  double chol[9];      /* lower Cholesky factor L of the 3x3 noise covariance, row-major; bearing-range: L = diag(sigma_b, sigma_r, 0) */
+  double* out;         /* d_tgt x N (Pose2: 3, Point2: 2) */
+} cb2_conv_desc;
+
+int cb2_approx_conv_batch(cb2_ctx* ctx, const cb2_conv_desc* descs, int B, uint64_t seed);
+
 #ifdef __cplusplus
 }
 #endif

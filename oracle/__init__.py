@@ -205,3 +205,16 @@ class Tree:
             self.var.append(np.ctypeslib.as_array(C.cast(L.cb2o_tree_level_var(h, l), dp), (n, self.d)).copy())
             self.wt.append(np.ctypeslib.as_array(C.cast(L.cb2o_tree_level_wt(h, l), dp), (n,)).copy())
         L.cb2o_tree_free(h)
+
+
+def approx_conv(kind, reverse, N, mean, chol, seed, stream=0, src=None, aux=None):
+    """Closed-form approxConv (kind 0 Pose2 prior, 1 Pose2Pose2, 2 Pose2Point2BearingRange); returns N x d_tgt."""
+    mean, chol = _f64(np.resize(np.asarray(mean, dtype=np.float64), 3)), _f64(np.asarray(chol, dtype=np.float64).reshape(9))
+    src = None if src is None else _f64(src)
+    aux = None if aux is None else _f64(aux)
+    dt = 2 if (kind == 2 and not reverse) else 3
+    out = np.zeros((N, dt))
+    rc = lib().cb2o_approx_conv(kind, int(reverse), N, _p(src), 0 if src is None else src.shape[0], _p(aux),
+                                0 if aux is None else aux.shape[0], stream, _p(mean), _p(chol), C.c_uint64(seed), _p(out))
+    assert rc == 0
+    return out

@@ -534,3 +534,43 @@ void cb2o_set_num_threads(int n) {
   (void)n;
 #endif
 }
+
+/* ------------------------------------------------------------------ approxConv for closed-form factors
+ * Restates the closed-form per-particle solves of R:docs/src/principles/approxConvDensities.md:25-34 for Pose2 priors,
+ * Pose2Pose2 and Pose2Point2BearingRange; same Philox draws (tag 4) as caesar.jl_b200/csrc/conv.cu. */
+int cb2o_approx_conv(int kind, int reverse, int N, const double* src, int n_src, const double* aux, int n_aux,
+                     uint32_t stream, const double* mean, const double* chol, uint64_t seed, double* out) {
+  if (kind < 0 || kind > 2 || N <= 0) return -1;
+  for (int i = 0; i < N; ++i) {
+    double z[3], nz[3];
+    for (int k = 0; k < 3; ++k) z[k] = cb2o_normal(seed, (uint32_t)i, (uint32_t)k, stream, 4, 53);
+    for (int r = 0; r < 3; ++r) nz[r] = mean[r] + chol[r * 3] * z[0] + chol[r * 3 + 1] * z[1] + chol[r * 3 + 2] * z[2];
+    if (kind == 0) {
+      out[(size_t)i * 3] = nz[0]; out[(size_t)i * 3 + 1] = nz[1]; out[(size_t)i * 3 + 2] = wrap_pi(nz[2]);
+    } else if (kind == 1) {
+      const double* p = src + (size_t)(i % n_src) * 3;
+      if (!reverse) {
+        double sn = sin(p[2]), cs = cos(p[2]);
+        out[(size_t)i * 3] = p[0] + cs * nz[0] - sn * nz[1];
+        out[(size_t)i * 3 + 1] = p[1] + sn * nz[0] + cs * nz[1];
+        out[(size_t)i * 3 + 2] = wrap_pi(p[2] + nz[2]);
+      } else {
+        double th = wrap_pi(p[2] - nz[2]), sn = sin(th), cs = cos(th);
+        out[(size_t)i * 3] = p[0] - (cs * nz[0] - sn * nz[1]);
+        out[(size_t)i * 3 + 1] = p[1] - (sn * nz[0] + cs * nz[1]);
+        out[(size_t)i * 3 + 2] = th;
+      }
+    } else if (!reverse) {
+      const double* p = src + (size_t)(i % n_src) * 3;
+      out[(size_t)i * 2] = p[0] + nz[1] * cos(p[2] + nz[0]);
+      out[(size_t)i * 2 + 1] = p[1] + nz[1] * sin(p[2] + nz[0]);
+    } else {
+      const double* l = src + (size_t)(i % n_src) * 2;
+      double th = aux[(size_t)(i % n_aux) * 3 + 2];
+      out[(size_t)i * 3] = l[0] - nz[1] * cos(th + nz[0]);
+      out[(size_t)i * 3 + 1] = l[1] - nz[1] * sin(th + nz[0]);
+      out[(size_t)i * 3 + 2] = th;
+    }
+  }
+  return 0;
+}

@@ -86,6 +86,10 @@ const double* cb2o_tree_level_mean(const cb2o_tree* t, int level); /* cnt x d */
 const double* cb2o_tree_level_var(const cb2o_tree* t, int level);  /* cnt x d */
 const double* cb2o_tree_level_wt(const cb2o_tree* t, int level);   /* cnt */
 
+/* approxConv for closed-form factors; kinds as cb2_factor_kind in include/caesar_b200.h */
+int cb2o_approx_conv(int kind, int reverse, int N, const double* src, int n_src, const double* aux, int n_aux,
+                     uint32_t stream, const double* mean, const double* chol, uint64_t seed, double* out);
+
 int cb2o_num_threads(void);
 void cb2o_set_num_threads(int n);
 

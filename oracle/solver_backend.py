@@ -29,3 +29,7 @@ class OracleBackend:
             pts, _ = oracle.product([(m.pts, m.bw) for m in g], N, seed, circular=TOPO[vartype], stream=st, ubits=self.ubits)
             out.append(_Belief(vartype, pts, oracle.kde_bw_loo(pts, circular=TOPO[vartype])))
         return out
+
+    def approx_conv_batch(self, convs, seed):
+        return [oracle.approx_conv(c["kind"], c["reverse"], c["N"], c["mean"], c["chol"], seed, stream=c["stream"], src=c["src"], aux=c["aux"])
+                for c in convs]

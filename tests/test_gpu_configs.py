@@ -157,3 +157,32 @@ def test_zmq_multiply_distributions_verb(cb, ctx):
     assert p["dim"] == 1 and p["kernelType"] == "Gaussian" and len(p["points"]) == 10 and len(p["weights"]) == 10
     assert abs(sum(p["weights"]) - 1.0) < 1e-12 and p["bandwidth"][0] > 0 and np.isfinite(p["points"]).all()
     json.dumps(reply)  # serialisable as is
+
+
+def test_approx_conv_closed_form_factors_match_oracle(cb, ctx):
+    """per-particle factor solves for Pose2 prior, Pose2Pose2 (both directions) and
+    Pose2Point2BearingRange (both directions) -- same Philox draws on the device and in the oracle."""
+    rng = np.random.default_rng(12)
+    poses = np.c_[rng.normal(size=(100, 2)) * 3, rng.uniform(-np.pi, np.pi, size=100)]
+    lms = rng.normal(size=(57, 2)) * 5
+    L3 = np.linalg.cholesky(np.diag([0.1, 0.2, 0.05]) ** 2 + 0.001)
+    convs = [
+        dict(kind=cb.FACTOR_PRIOR_POSE2, reverse=False, N=300, mean=[1.0, -2.0, 3.1], chol=L3, stream=1, src=None, aux=None),
+        dict(kind=cb.FACTOR_POSE2POSE2, reverse=False, N=100, mean=[10.0, 0, np.pi / 3], chol=L3, stream=2, src=poses, aux=None),
+        dict(kind=cb.FACTOR_POSE2POSE2, reverse=True, N=250, mean=[10.0, 0, np.pi / 3], chol=L3, stream=3, src=poses, aux=None),
+        dict(kind=cb.FACTOR_POSE2POINT2_BEARINGRANGE, reverse=False, N=100, mean=[0.3, 20.0, 0], chol=np.diag([0.1, 1.0, 0]), stream=4,
+             src=poses, aux=None),
+        dict(kind=cb.FACTOR_POSE2POINT2_BEARINGRANGE, reverse=True, N=128, mean=[0.3, 20.0, 0], chol=np.diag([0.1, 1.0, 0]), stream=5,
+             src=lms, aux=poses),
+    ]
+    outs = cb.approxConvBatch(convs, seed=99, ctx=ctx)
+    for c, o in zip(convs, outs):
+        want = oracle.approx_conv(c["kind"], c["reverse"], c["N"], c["mean"], c["chol"], 99, stream=c["stream"], src=c["src"], aux=c["aux"])
+        assert o.shape == want.shape and np.allclose(o, want, atol=1e-12)
+    # closed-form sanity: a forward then a reverse convolution with zero noise returns the source pose
+    z = np.zeros((3, 3))
+    fwd = cb.approxConvBatch([dict(kind=1, reverse=False, N=100, mean=[10.0, 0, np.pi / 3], chol=z, stream=0, src=poses, aux=None)], ctx=ctx)[0]
+    back = cb.approxConvBatch([dict(kind=1, reverse=True, N=100, mean=[10.0, 0, np.pi / 3], chol=z, stream=0, src=fwd, aux=None)], ctx=ctx)[0]
+    d = back - poses
+    d[:, 2] = (d[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    assert np.abs(d).max() < 1e-12
