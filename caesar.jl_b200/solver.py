@@ -122,7 +122,7 @@ def approx_conv(fg, labels, factor, target, rng):
 
 
 def conv_desc(fg, labels, factor, target, stream):
-    """Descriptor of one closed-form convolution for `approxConvBatch` (device) / `oracle.approx_conv` (CPU)."""
+    """Descriptor of one closed-form convolution for a backend's `approx_conv_batch` (device: `approxConvBatch`)."""
     N = fg.N
     if isinstance(factor, PriorPose2):
         return dict(kind=0, reverse=False, N=N, mean=factor.mean, chol=np.linalg.cholesky(factor.cov), stream=stream, src=None, aux=None)
