@@ -172,13 +172,28 @@ def manikde(manifold, pts, bw=None, weights=None, partial=None, infoPerCoord=Non
     return ManifoldKernelDensity(manifold, pts, bw, weights, partial, infoPerCoord)
 
 
-def mmd(a, b, bw=None, ctx=None):
+def mmd_manifold(a, b, circular, bw, rot_weight=2.0, ctx=None):
+    """mmd with the product-manifold distance: wrapped differences on circular coordinates, weighted by `rot_weight`
+    (2 = Manifolds.jl's metric on SpecialEuclidean(2): d_SO(2) = sqrt(2) |dtheta|)."""
+    ctx = ctx or context()
+    a, b = f64(np.atleast_2d(a)), f64(np.atleast_2d(b))
+    circ = circ_arr(circular, a.shape[1])
+    out = C.c_double()
+    ctx.check(_capi.lib().cb2_mmd_manifold(ctx._h, ptr(a), a.shape[0], ptr(b), b.shape[0], a.shape[1], ptr(circ),
+                                           float(rot_weight), float(np.ravel(bw)[0]), C.byref(out)))
+    return out.value
+
+
+def mmd(a, b, bw=None, rot_weight=2.0, ctx=None):
     """`mmd(M, a, b, N, M; bw)` on point arrays, or `mmd(mkdA, mkdB; bw=[0.001])` on two beliefs.
-    Biased V-statistic MMD^2 with k = exp(-bw |p - q|^2)."""
+    Biased V-statistic MMD^2 with k = exp(-bw |p - q|^2).  Beliefs over variable types with circular
+    coordinates (Pose2, Pose3) use the manifold distance (`mmd_manifold`)."""
     ctx = ctx or context()
     if isinstance(a, ManifoldKernelDensity):
-        a, b = a.pts, b.pts
         bw = 0.001 if bw is None else bw
+        if any(a.circular):  # beliefs on SE(n): manifold distance (wrapped angles, product metric)
+            return mmd_manifold(a.pts, b.pts, a.circular, bw, rot_weight=rot_weight, ctx=ctx)
+        a, b = a.pts, b.pts
     if bw is None:
         raise ValueError("bw is required for point arrays")
     bw = float(np.ravel(bw)[0])

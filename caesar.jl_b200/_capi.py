@@ -59,6 +59,7 @@ def lib():
             "cb2_device_sm_count": (i32, [vp]),
             "cb2_last_stage_ms": (f64, [vp, C.c_char_p]),
             "cb2_mmd": (i32, [vp, vp, i32, vp, i32, i32, f64, vp]),
+            "cb2_mmd_manifold": (i32, [vp, vp, i32, vp, i32, i32, vp, f64, f64, vp]),
             "cb2_mmd_sums": (i32, [vp, vp, i32, vp, i32, i32, f64, i32, i32, i32, i32, vp]),
             "cb2_mmd_sums_dev": (i32, [vp, vp, i32, vp, i32, i32, f64, i32, i32, i32, i32, vp]),
             "cb2_mmd_se_batch": (i32, [vp, vp, i32, vp, i32, i32, f64, vp, i32, i32, vp, vp]),
@@ -88,7 +89,8 @@ EXPORTS = ["cb2_create", "cb2_destroy", "cb2_last_error", "cb2_precision", "cb2_
            "cb2_kernel_launches", "cb2_device_sm_count", "cb2_last_stage_ms", "cb2_mmd", "cb2_mmd_sums",
            "cb2_mmd_sums_dev", "cb2_mmd_se_batch", "cb2_mmd_se_batch_dev", "cb2_kde_eval", "cb2_kde_bw_loo",
            "cb2_kde_bw_loo_batch", "cb2_kde_sample", "cb2_product", "cb2_product_batch", "cb2_product_batch_dev",
-           "cb2_product_batch_submit", "cb2_wait", "cb2_tree_debug", "cb2_scatter_align", "cb2_approx_conv_batch"]
+           "cb2_product_batch_submit", "cb2_wait", "cb2_tree_debug", "cb2_scatter_align", "cb2_approx_conv_batch",
+           "cb2_mmd_manifold"]
 
 
 def f64(x):

@@ -39,6 +39,7 @@ struct ConvertArgs {
   double scale[8];
   double center[8];
   int use_center_ptr;  // take the centre from the first point of center_src (device) instead
+  int wrap[8];         // circular coordinate: wrapped to [-pi, pi] and not centred
 };
 
 template <typename T, int REC>
@@ -52,7 +53,8 @@ __global__ void convert_records_kernel(const double* __restrict__ src, int n, in
   for (int k = 0; k < REC; ++k) r.v[k] = T(0);
   for (int k = 0; k < d; ++k) {
     double c = a.use_center_ptr ? center_src[k] : a.center[k];
-    r.v[k] = (T)((src[(size_t)i * d + k] - c) * a.scale[k]);
+    double x = src[(size_t)i * d + k];
+    r.v[k] = (T)((a.wrap[k] ? wrap_pi(x) : x - c) * a.scale[k]);
   }
   if (w) r.v[REC - 1] = (T)log2(w[i] / wsum);
   reinterpret_cast<Rec<T, REC>*>(dst)[i] = r;
@@ -61,6 +63,8 @@ __global__ void convert_records_kernel(const double* __restrict__ src, int n, in
 // ---------------------------------------------------------------------------------------------------
 // MODE 0: total sum per tile (mmd).  MODE 1: total + gradient moments per tile (rigid-transform batch).
 // MODE 2: per-row partial sums with per-column log2 offsets (KDE evaluate).
+// MODE 3: total sum with a manifold distance: per-coordinate periods in xforms[0..DIM) (+inf = Euclidean coordinate);
+//         the wrapped difference is min(|d|, period - |d|) on coordinates already wrapped to [-pi, pi] * scale.
 template <typename T, int DIM, int MODE>
 __global__ void __launch_bounds__(kThreads)
 pair_tiles_kernel(const PairSub<T>* __restrict__ subs, const Tile* __restrict__ tiles,
@@ -95,8 +99,13 @@ pair_tiles_kernel(const PairSub<T>* __restrict__ subs, const Tile* __restrict__ 
     for (int k = 0; k < (GRAD ? DIM : 1); ++k) g[r][k] = T(0);
   }
 
+  T per[DIM];
+  if (MODE == 3) {
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) per[k] = xforms[k];
+  }
   T R[9], t[3];
-  if (GRAD || sb.xf >= 0) {
+  if (MODE != 3 && (GRAD || sb.xf >= 0)) {
     if (sb.xf >= 0) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) R[k] = xforms[sb.xf * 12 + k];
@@ -113,7 +122,7 @@ pair_tiles_kernel(const PairSub<T>* __restrict__ subs, const Tile* __restrict__ 
       Rec<T, REC> q;
       if (col < c1) {
         q = cols[col];
-        if (DIM <= 3 && sb.xf >= 0) {
+        if (MODE != 3 && DIM <= 3 && sb.xf >= 0) {
           T x = q.v[0], y = q.v[1], z = DIM == 3 ? q.v[2] : T(0);
           if (DIM == 2) {
             q.v[0] = R[0] * x + R[1] * y + t[0];
@@ -138,10 +147,12 @@ pair_tiles_kernel(const PairSub<T>* __restrict__ subs, const Tile* __restrict__ 
 #pragma unroll
       for (int r = 0; r < kRI; ++r) {
         T d0 = p[r][0] - q.v[0];
+        if (MODE == 3) { T ad = fabs(d0); d0 = fmin(ad, per[0] - ad); }
         T r2 = d0 * d0;
 #pragma unroll
         for (int k = 1; k < DIM; ++k) {
           T dk = p[r][k] - q.v[k];
+          if (MODE == 3) { T ad = fabs(dk); dk = fmin(ad, per[k] - ad); }
           r2 = fma(dk, dk, r2);
         }
         T kv = OFFS ? fast_exp2(q.v[REC - 1] - r2) : fast_exp2(-r2);
@@ -315,7 +326,8 @@ struct SubSpec { int rows_is_b, cols_is_b, row0, row1, ncols, xf, col0 = 0; };
 template <typename T, int MODE>
 int run_pairs_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev, int M, int d, double scale,
                   const std::vector<SubSpec>& specs, const std::vector<T>& xf_host, double** result_dev,
-                  size_t extra_bytes, void** extra_ptr, bool reuse_prev = false) {
+                  size_t extra_bytes, void** extra_ptr, bool reuse_prev = false, const double* dim_scale = nullptr,
+                  uint32_t wrap_mask = 0) {
   // reuse_prev: the previous call on this context had the same clouds, sub-problems and sizes and nothing else touched
   // the arena since (consecutive cost evaluations of one BFGS batch): the arena layout is a pure function of the
   // sizes, so the converted records and the tile tables are still in place -- only the transforms are uploaded again.
@@ -328,7 +340,7 @@ int run_pairs_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev,
     const int RB = kThreads * kRI;
     int nrb = (nr + RB - 1) / RB, ncb = (specs[s].ncols + kCB - 1) / kCB;
     // k(p,q) = k(q,p): a full self pair sum (aa, bb) only needs the diagonal blocks once and the blocks above them twice
-    const bool sym = MODE == 0 && specs[s].rows_is_b == specs[s].cols_is_b && specs[s].row0 == 0 && specs[s].col0 == 0 &&
+    const bool sym = (MODE == 0 || MODE == 3) && specs[s].rows_is_b == specs[s].cols_is_b && specs[s].row0 == 0 && specs[s].col0 == 0 &&
                      specs[s].row1 == specs[s].ncols && specs[s].xf < 0;
     for (int rb = 0; rb < nrb; ++rb) {
       if (!sym) {
@@ -365,7 +377,7 @@ int run_pairs_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev,
   if (!reuse_prev) {
   ConvertArgs ca;
   memset(&ca, 0, sizeof(ca));
-  for (int k = 0; k < 8; ++k) ca.scale[k] = scale;
+  for (int k = 0; k < 8; ++k) { ca.scale[k] = dim_scale ? dim_scale[k] : scale; ca.wrap[k] = (wrap_mask >> k) & 1; }
   ca.use_center_ptr = 1;  // centre both clouds on a[0]: rigid-invariant, keeps FP32 differences exact
   rc = convert_async<T>(ctx, a_dev, N, d, ca, a_dev, nullptr, 1.0, ra);
   if (rc) return rc;
@@ -956,4 +968,58 @@ extern "C" int cb2_scatter_align(cb2_ctx* ctx, const cb2_density* cloud1, const 
   cudaStreamSynchronize(ctx->stream);
   cudaFree(block);
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// mmd between beliefs on a product of lines and circles (Pose2 / Pose3 beliefs as a test metric,
+// R:test/ICRA2022_tests/multihypo_corners.jl:201-202): k = exp(-bw * dist^2) with
+// dist^2 = sum_Euclid d_i^2 + rot_weight * sum_circular wrap(d_i)^2.  SURVEY App. A.1 item 4: Manifolds.jl's product
+// metric on SpecialEuclidean(2) gives rot_weight = 2 (Frobenius norm of the skew matrix); kept as a parameter.
+template <typename T>
+static int mmd_manifold_impl(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev, int M, int d, uint32_t mask,
+                             double rot_weight, double bw, double* sums3_dev) {
+  std::vector<SubSpec> specs = {{0, 0, 0, N, N, -1}, {0, 1, 0, N, M, -1}, {1, 1, 0, M, M, -1}};
+  double dim_scale[8];
+  std::vector<T> per(12, (T)INFINITY);
+  for (int k = 0; k < 8; ++k) {
+    const bool c = (mask >> k) & 1;
+    dim_scale[k] = sqrt(bw * CB2_LOG2E * (c ? rot_weight : 1.0));
+    if (c && k < d) per[k] = (T)(CB2_TWO_PI * dim_scale[k]);
+  }
+  double* res = nullptr;
+  int rc = run_pairs_dev<T, 3>(ctx, a_dev, N, b_dev, M, d, 0.0, specs, per, &res, 0, nullptr, false, dim_scale, mask);
+  if (rc) return rc;
+  gather_sums3_kernel<<<1, 32, 0, ctx->stream>>>(res, sums3_dev);
+  CB2_CHECK_LAUNCH(ctx, "gather_sums3_kernel");
+  return CB2_OK;
+}
+
+extern "C" int cb2_mmd_manifold(cb2_ctx* ctx, const double* a, int N, const double* b, int M, int d, const uint8_t* circular,
+                                double rot_weight, double bw, double* out) {
+  if (!ctx) return CB2_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  int rc = check_cloud_args(ctx, a, N, b, M, d);
+  if (rc) return rc;
+  CB2_REQUIRE(ctx, out, "null output");
+  CB2_REQUIRE(ctx, bw > 0 && isfinite(bw) && rot_weight > 0 && isfinite(rot_weight), "bw and rot_weight must be positive");
+  uint32_t mask = 0;
+  for (int k = 0; k < d; ++k) if (circular && circular[k]) mask |= 1u << k;
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<double*> dev;
+  double* block = nullptr;
+  rc = upload_block(ctx, {a, b, nullptr}, {(size_t)N * d, (size_t)M * d, 3}, dev, &block);
+  if (rc) return rc;
+  rc = ctx->precision == CB2_FP64 ? mmd_manifold_impl<double>(ctx, dev[0], N, dev[1], M, d, mask, rot_weight, bw, dev[2])
+                                  : mmd_manifold_impl<float>(ctx, dev[0], N, dev[1], M, d, mask, rot_weight, bw, dev[2]);
+  double s[3] = {0, 0, 0};
+  if (rc == CB2_OK) {
+    cudaError_t e = cudaMemcpyAsync(s, dev[2], 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = cb2_fail(ctx, CB2_ERR_CUDA, "mmd readback: %s", cudaGetErrorString(e));
+  } else {
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (rc) return rc;
+  *out = s[0] / ((double)N * N) - 2.0 * s[1] / ((double)N * M) + s[2] / ((double)M * M);
+  return CB2_OK;
 }

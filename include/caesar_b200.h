@@ -80,6 +80,13 @@ int cb2_mmd_sums(cb2_ctx* ctx, const double* a, int N, const double* b, int M, i
 int cb2_mmd_sums_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev, int M, int d, double bw,
                      int ra0, int ra1, int rb0, int rb1, double* sums3_dev);
 
+/* mmd between beliefs on a product of lines and circles (Pose2 / Pose3 beliefs as a test metric,
+ * R:test/ICRA2022_tests/multihypo_corners.jl:201-202): dist^2 = sum over Euclidean coordinates of d^2 plus
+ * rot_weight * sum over circular coordinates of wrap(d)^2.  Manifolds.jl's product metric on SpecialEuclidean(2)
+ * corresponds to rot_weight = 2; circular: d flags. */
+int cb2_mmd_manifold(cb2_ctx* ctx, const double* a, int N, const double* b, int M, int d, const uint8_t* circular,
+                     double rot_weight, double bw, double* out);
+
 /* ---- mmd under K candidate rigid transforms of b (K2) --------------------------------------------
  * dim = 2 (coords x,y,theta) or 3 (x,y,z,rotation vector); coords is K x ncoord row-major.
  * b'_j = T(c_k) b_j, or T(c_k)^-1 b_j when backward != 0 (ScatterAlign uses backward).

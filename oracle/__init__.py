@@ -218,3 +218,13 @@ def approx_conv(kind, reverse, N, mean, chol, seed, stream=0, src=None, aux=None
                                 0 if aux is None else aux.shape[0], stream, _p(mean), _p(chol), C.c_uint64(seed), _p(out))
     assert rc == 0
     return out
+
+
+def mmd_manifold(a, b, circular, bw, rot_weight=2.0):
+    a, b = _f64(a), _f64(b)
+    c = _circ(circular, a.shape[1])
+    out = C.c_double()
+    rc = lib().cb2o_mmd_manifold(_p(a), a.shape[0], _p(b), b.shape[0], a.shape[1], _p(c), C.c_double(rot_weight), C.c_double(bw),
+                                 C.byref(out))
+    assert rc == 0
+    return out.value

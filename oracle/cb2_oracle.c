@@ -574,3 +574,32 @@ int cb2o_approx_conv(int kind, int reverse, int N, const double* src, int n_src,
   }
   return 0;
 }
+
+/* mmd with a product-manifold distance: dist^2 = sum_E d^2 + rot_weight * sum_C wrap(d)^2 */
+int cb2o_mmd_manifold(const double* a, int N, const double* b, int M, int d, const uint8_t* circular, double rot_weight,
+                      double bw, double* out) {
+  if (N <= 0 || M <= 0 || d <= 0 || d > MAXD) return -1;
+  const double* P[3] = {a, a, b};
+  const double* Q[3] = {a, b, b};
+  int np[3] = {N, N, M}, nq[3] = {N, M, M};
+  double s[3];
+  for (int t = 0; t < 3; ++t) {
+    double tot = 0.0;
+#pragma omp parallel for reduction(+ : tot) schedule(static)
+    for (int i = 0; i < np[t]; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < nq[t]; ++j) {
+        double r2 = 0.0;
+        for (int k = 0; k < d; ++k) {
+          double df = P[t][(size_t)i * d + k] - Q[t][(size_t)j * d + k];
+          if (circular && circular[k]) { df = wrap_pi(df); r2 += rot_weight * df * df; } else r2 += df * df;
+        }
+        acc += exp(-bw * r2);
+      }
+      tot += acc;
+    }
+    s[t] = tot;
+  }
+  *out = s[0] / ((double)N * N) - 2.0 * s[1] / ((double)N * M) + s[2] / ((double)M * M);
+  return 0;
+}

@@ -186,3 +186,29 @@ def test_approx_conv_closed_form_factors_match_oracle(cb, ctx):
     d = back - poses
     d[:, 2] = (d[:, 2] + np.pi) % (2 * np.pi) - np.pi
     assert np.abs(d).max() < 1e-12
+
+
+def test_mmd_between_pose_beliefs_uses_manifold_distance(cb, ctx):
+    """mmd(X2_a, belief) on Pose2 beliefs (R:test/ICRA2022_tests/multihypo_corners.jl:201-202): wrapped angular
+    differences with the product-metric weight; identical beliefs across the +-pi cut must be at distance ~0."""
+    rng = np.random.default_rng(21)
+    a = np.c_[rng.normal(size=(300, 2)), np.pi - 0.05 + 0.1 * rng.normal(size=300)]
+    a[:, 2] = (a[:, 2] + np.pi) % (2 * np.pi) - np.pi           # straddles the cut
+    b = a + np.c_[0.01 * rng.normal(size=(300, 2)), 0.01 * rng.normal(size=300)]
+    b[:, 2] = (b[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    tol = 1e-5 if ctx.precision == "fp32" else 1e-12
+    for bw, circ, d in ((0.5, [0, 0, 1], 3), (0.001, [0, 0, 1], 3), (0.3, [0, 0, 0, 1, 1, 1], 6)):
+        A = a if d == 3 else np.c_[a, a[:, ::-1]]
+        B = b if d == 3 else np.c_[b, b[:, ::-1]]
+        A[:, 3:] = (A[:, 3:] + np.pi) % (2 * np.pi) - np.pi
+        B[:, 3:] = (B[:, 3:] + np.pi) % (2 * np.pi) - np.pi
+        want = oracle.mmd_manifold(A, B, circ, bw)
+        got = cb.mmd_manifold(A, B, circ, bw, ctx=ctx)
+        assert abs(got - want) <= tol * 4, (bw, d, got, want)
+    # two headings 0.04 rad apart on either side of the cut: close on the manifold, 2 pi apart in flat coordinates
+    xy = rng.normal(size=(300, 2))
+    pa = np.c_[xy, np.pi - 0.02 + 0.005 * rng.normal(size=300)]
+    pb = np.c_[xy, -np.pi + 0.02 + 0.005 * rng.normal(size=300)]
+    A, B = cb.MKD("Pose2", pa, [0.1, 0.1, 0.05]), cb.MKD("Pose2", pb, [0.1, 0.1, 0.05])
+    assert cb.mmd(A, B, bw=0.5, ctx=ctx) < 5e-3
+    assert cb.mmd(pa, pb, bw=0.5, ctx=ctx) > 0.1
