@@ -392,6 +392,20 @@ def mmd_extras(cb, ctx, torch, tstream, rank=0, world=1, dist=None):
                 "se_batch_note": "host-timed cb2_mmd_se_batch_dev: aa+bb pass, K cross terms with gradient moments, D2H of 8K doubles",
                 "se_batch_cpu_pairs_per_s": (Ps * Ps + Ps * P + float(P) * P) / cpu2,
                 "se_batch_cpu_sample": f"1 transform, a[:{Ps}] x b (value + gradient), oracle"})
+    # K3: KDE evaluate, Q = 1e5 queries against the same 1e5-point cloud (host buffers in, log-densities out)
+    kd = cb.ManifoldKernelDensity("Point3", a, np.array([0.2, 0.2, 0.2]))
+    cb.evaluate(kd, b[:1000], ctx=ctx)
+    t0 = time.perf_counter()
+    dens = cb.evaluate(kd, b, ctx=ctx)
+    ev_s = time.perf_counter() - t0
+    Qs = 1000
+    t0 = time.perf_counter()
+    dref = oracle.kde_eval(a, kd.bw, b[:Qs])
+    ev_cpu = time.perf_counter() - t0
+    big = dref > 1e-12
+    out.update({"kde_eval_pairs_per_s_e2e": float(P) * P / ev_s, "kde_eval_s": ev_s, "kde_eval_queries": P,
+                "kde_eval_max_rel_err_vs_oracle": float(np.max(np.abs(dens[:Qs][big] - dref[big]) / dref[big])) if big.any() else None,
+                "kde_eval_cpu_pairs_per_s": float(Qs) * P / ev_cpu, "kde_eval_cpu_sample": f"first {Qs} queries, oracle on all host cores"})
     # C1: ScatterAlignPose2 getSample on the 3-blob test clouds (sample_count=100), K=100 particles as one batched BFGS
     c = np.array([[3.0, 0], [8.0, 0], [0, 5.0]])
     p1 = np.concatenate([ci + 0.1 * rng.normal(size=(50, 2)) for ci in c])

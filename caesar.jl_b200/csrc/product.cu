@@ -80,6 +80,11 @@ __device__ __forceinline__ unsigned long long ordered_bits(double v) {
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
+__device__ __forceinline__ double from_ordered_bits(unsigned long long o) {
+  return __longlong_as_double((long long)((o & 0x8000000000000000ull) ? (o & 0x7fffffffffffffffull) : ~o));
+}
+constexpr int kCoopNodes = 32;  // tree levels with at most this many nodes find their split coordinate cooperatively
+
 __device__ __forceinline__ bool key_less(unsigned long long oa, uint32_t ta, unsigned long long ob, uint32_t tb) {
   uint32_t na = ta >> 14, nb = tb >> 14;
   if (na != nb) return na < nb;
@@ -101,6 +106,7 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
   unsigned char* seg_dim = reinterpret_cast<unsigned char*>(tag + P2);
   __shared__ double s_red[32];
   __shared__ double s_wsum;
+  __shared__ unsigned long long s_ext[2 * kCoopNodes * CB2_MAX_DIM];  // (min, max) per node and coordinate
   int* perm = int_pool + m.perm_off;
   const bool pow2 = (P2 == N);
 
@@ -109,26 +115,88 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
 
   for (int l = 0; l < depth; ++l) {
     const int cnt = 1 << l;
-    // widest coordinate of every node: one warp per node, lanes over its points
-    for (int k = tid >> 5; k < cnt; k += nthr >> 5) {
-      int lo, n;
-      node_range(N, l, k, lo, n);
-      int best = 0;
-      double bestr = -1.0;
-      for (int i = 0; i < d; ++i) {
-        double mn = 1e300, mx = -1e300;
-        for (int p = lo + (tid & 31); p < lo + n; p += 32) {
-          double v = m.pts[(size_t)perm[p] * d + i];
-          mn = fmin(mn, v); mx = fmax(mx, v);
+    if (cnt <= kCoopNodes) {
+      // shallow levels (few, large nodes): all threads sweep the points once, warp-reduce runs of lanes that sit in the
+      // same node, and fold into per-node extrema with shared atomics on the order-preserving bit pattern
+      for (int q = tid; q < 2 * kCoopNodes * CB2_MAX_DIM; q += nthr) s_ext[q] = (q & 1) ? 0ull : ~0ull;
+      __syncthreads();
+      for (int p0 = 0; p0 < N; p0 += nthr) {
+        const int p = p0 + tid;
+        const bool in = p < N;
+        const int k = in ? node_of(N, l, p) : -1;
+        const int k0 = __shfl_sync(0xffffffffu, k, 0);
+        const bool uni = __all_sync(0xffffffffu, k == k0);
+        const size_t row = in ? (size_t)perm[p] * d : 0;
+        unsigned long long lo[CB2_MAX_DIM], hi[CB2_MAX_DIM];
+#pragma unroll
+        for (int i = 0; i < CB2_MAX_DIM; ++i) {  // every coordinate of the point in flight before any reduction
+          lo[i] = (in && i < d) ? ordered_bits(m.pts[row + i]) : ~0ull;
+          hi[i] = (in && i < d) ? lo[i] : 0ull;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-          mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        for (int i = 0; i < CB2_MAX_DIM; ++i) {
+          if (i >= d) break;
+          if (uni) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo[i], o), h2 = __shfl_xor_sync(0xffffffffu, hi[i], o);
+              lo[i] = l2 < lo[i] ? l2 : lo[i]; hi[i] = h2 > hi[i] ? h2 : hi[i];
+            }
+            if ((tid & 31) == 0 && in) { atomicMin(&s_ext[(k * CB2_MAX_DIM + i) * 2], lo[i]); atomicMax(&s_ext[(k * CB2_MAX_DIM + i) * 2 + 1], hi[i]); }
+          } else if (in) {
+            atomicMin(&s_ext[(k * CB2_MAX_DIM + i) * 2], lo[i]); atomicMax(&s_ext[(k * CB2_MAX_DIM + i) * 2 + 1], hi[i]);
+          }
         }
-        if (mx - mn > bestr) { bestr = mx - mn; best = i; }
       }
-      if ((tid & 31) == 0) seg_dim[k] = (unsigned char)best;
+      __syncthreads();
+      if (tid < cnt) {
+        int best = 0;
+        double bestr = -1.0;
+        for (int i = 0; i < d; ++i) {
+          const double mn = from_ordered_bits(s_ext[(tid * CB2_MAX_DIM + i) * 2]), mx = from_ordered_bits(s_ext[(tid * CB2_MAX_DIM + i) * 2 + 1]);
+          if (mx - mn > bestr) { bestr = mx - mn; best = i; }
+        }
+        seg_dim[tid] = (unsigned char)best;
+      }
+    } else {
+      // deeper levels: one group of g lanes per node, each lane gathers at most 8 points with all their coordinates in
+      // flight together (a warp per node would leave most lanes idle and serialise one load latency per node and coordinate)
+      const int nmax = (N + cnt - 1) / cnt;
+      int g = 1;
+      while (g < 32 && g * 8 < nmax) g <<= 1;
+      const int ngroups = nthr / g, gid = tid / g, sub = tid & (g - 1);
+      for (int kb = 0; kb < cnt; kb += ngroups) {
+        const int k = kb + gid;
+        const bool valid = k < cnt;
+        int lo = 0, n = 0;
+        if (valid) node_range(N, l, k, lo, n);
+        double mn[CB2_MAX_DIM], mx[CB2_MAX_DIM];
+#pragma unroll
+        for (int i = 0; i < CB2_MAX_DIM; ++i) { mn[i] = 1e300; mx[i] = -1e300; }
+#pragma unroll 4
+        for (int p = lo + sub; p < lo + n; p += g) {
+          const size_t row = (size_t)perm[p] * d;
+#pragma unroll
+          for (int i = 0; i < CB2_MAX_DIM; ++i) {
+            if (i < d) { const double v = m.pts[row + i]; mn[i] = fmin(mn[i], v); mx[i] = fmax(mx[i], v); }
+          }
+        }
+        int best = 0;
+        double bestr = -1.0;
+#pragma unroll
+        for (int i = 0; i < CB2_MAX_DIM; ++i) {
+          if (i >= d) break;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            if (o < g) {
+              mn[i] = fmin(mn[i], __shfl_xor_sync(0xffffffffu, mn[i], o));
+              mx[i] = fmax(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], o));
+            }
+          }
+          if (mx[i] - mn[i] > bestr) { bestr = mx[i] - mn[i]; best = i; }
+        }
+        if (valid && sub == 0) seg_dim[k] = (unsigned char)best;
+      }
     }
     __syncthreads();
     for (int p = tid; p < P2; p += nthr) {
@@ -143,20 +211,30 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
     __syncthreads();
     // bitonic sort; when N is a power of two the nodes are aligned blocks of N>>l, sort inside blocks only
     const int kmax = pow2 ? (N >> l) : P2;
+    // one compare-exchange per thread and round: pair q = (i, i | j)
+    auto cmpx = [&](int q, int j, int k) {
+      const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1)), ixj = i | j;
+      const bool up = (i & k) == 0 || k == kmax;  // the last merge leaves every block ascending
+      const unsigned long long oa = ord[i], ob = ord[ixj];
+      const uint32_t ta = tag[i], tb = tag[ixj];
+      const bool lt = key_less(ob, tb, oa, ta);  // b < a
+      if (lt == up) { ord[i] = ob; ord[ixj] = oa; tag[i] = tb; tag[ixj] = ta; }
+    };
     for (int k = 2; k <= kmax; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < P2; i += nthr) {
-          int ixj = i ^ j;
-          if (ixj > i) {
-            bool up = (i & k) == 0 || k == kmax;  // the last merge leaves every block ascending
-            unsigned long long oa = ord[i], ob = ord[ixj];
-            uint32_t ta = tag[i], tb = tag[ixj];
-            bool lt = key_less(ob, tb, oa, ta);  // b < a
-            if (lt == up) { ord[i] = ob; ord[ixj] = oa; tag[i] = tb; tag[ixj] = ta; }
-          }
-        }
+      int j = k >> 1;
+      for (; j >= 64; j >>= 1) {
+        for (int q = tid; q < (P2 >> 1); q += nthr) cmpx(q, j, k);
         __syncthreads();
       }
+      // rounds with j <= 32: the 32 pairs of a warp stay inside one 64-element window, so a warp barrier is enough
+      for (int q0 = 0; q0 < (P2 >> 1); q0 += nthr) {
+        const int q = q0 + tid;
+        for (int jj = j; jj > 0; jj >>= 1) {
+          if (q < (P2 >> 1)) cmpx(q, jj, k);
+          __syncwarp();
+        }
+      }
+      __syncthreads();
     }
     // apply the permutation: position p now holds the element that sat at position tag&0x3fff
     int newp[CB2_MAX_PRODUCT_N / kTreeThreads];

@@ -88,8 +88,25 @@ function b200_mmd(a, b; bw::AbstractVector{<:Real} = SA[0.001;], ctx::Context = 
 end
 ApproxManifoldProducts.mmd(MF::AbstractManifold, a::AbstractVector, b::AbstractVector, N::Int = length(a), M::Int = length(b),
                            threads::Bool = true; bw::AbstractVector{<:Real} = SA[0.001;]) = b200_mmd(a, b; bw)
-ApproxManifoldProducts.mmd(a::ManifoldKernelDensity, b::ManifoldKernelDensity; bw::AbstractVector{<:Real} = SA[0.001;]) =
-  b200_mmd(getPoints(a.belief), getPoints(b.belief); bw)
+# beliefs over Pose2 / Pose3 (multihypo_corners.jl:201-202): product-manifold distance, wrapped on the circular coordinates;
+# rot_weight = 2 is Manifolds.distance on SpecialEuclidean(2) (d^2 = |dt|^2 + 2 dtheta^2)
+function b200_mmd_manifold(M, a, b; bw::AbstractVector{<:Real} = SA[0.001;], rot_weight::Real = 2.0, ctx::Context = context())
+  A, B = _flat(a), _flat(b)
+  out = Ref{Float64}(0.0)
+  circ = _circular(M)
+  lock(ctx.lk) do
+    _check(ctx, ccall((:cb2_mmd_manifold, libcb2), Cint,
+                      (Ptr{Cvoid}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Cint, Ptr{UInt8}, Float64, Float64, Ref{Float64}),
+                      ctx.h, A, size(A, 2), B, size(B, 2), size(A, 1), circ, Float64(rot_weight), Float64(bw[1]), out))
+  end
+  return out[]
+end
+# coordinates (vee of the log at the identity) of both beliefs; Euclidean variable types keep the flat kernel
+function ApproxManifoldProducts.mmd(a::ManifoldKernelDensity, b::ManifoldKernelDensity; bw::AbstractVector{<:Real} = SA[0.001;])
+  circ = _circular(a.manifold)
+  any(!iszero, circ) || return b200_mmd(getPoints(a.belief), getPoints(b.belief); bw)
+  return b200_mmd_manifold(a.manifold, getPoints(a.belief), getPoints(b.belief); bw)
+end
 
 # value + analytic gradient of cost(c) = mmd(a, T(c)^-1 b) for K coordinate vectors (columns of `coords`);
 # lets getSample call Optim.optimize(f, g!, x0, BFGS()) instead of finite differences (ScatterAlignPose2.jl:182)
