@@ -10,7 +10,8 @@ SRCS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")))
 DEPS = SRCS + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + [os.path.join(HERE, "..", "include", "caesar_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-         "-ccbin", "/usr/bin/g++", "-Xptxas", "-v" if os.environ.get("CB2_PTXAS_V") else "-O3"]
+         "-ccbin", "/usr/bin/g++", "-Xptxas", "-v" if os.environ.get("CB2_PTXAS_V") else "-O3"] + os.environ.get("CB2_NVCC_EXTRA", "").split()
+HDRS = [f for f in DEPS if not f.endswith(".cu")]
 
 
 def build(force=False, verbose=False):
@@ -22,6 +23,8 @@ def build(force=False, verbose=False):
     for src in SRCS:
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
+        if not force and os.path.exists(obj) and all(os.path.getmtime(obj) >= os.path.getmtime(f) for f in [src] + HDRS):
+            continue  # object is newer than its source and every header
         cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     ok = True

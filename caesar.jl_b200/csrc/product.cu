@@ -92,8 +92,14 @@ __device__ __forceinline__ bool key_less(unsigned long long oa, uint32_t ta, uns
   return ta < tb;
 }
 
+#ifdef CB2_TREE_PROF
+#define TREE_T(slot) do { __syncthreads(); long long t_ = clock64(); tprof[slot] += t_ - tlast; tlast = t_; } while (0)
+#else
+#define TREE_T(slot) do { } while (0)
+#endif
+
 template <typename T>
-__global__ void __launch_bounds__(kTreeThreads)
+__global__ void __launch_bounds__(kTreeThreads, 2)
 tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ int_pool, T* __restrict__ node_pool,
                   double* __restrict__ stat_scratch, size_t stat_stride, uint32_t circ_mask) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -112,6 +118,9 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
 
   for (int p = tid; p < N; p += nthr) perm[p] = p;
   __syncthreads();
+#ifdef CB2_TREE_PROF
+  long long tprof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
 
   for (int l = 0; l < depth; ++l) {
     const int cnt = 1 << l;
@@ -199,6 +208,7 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
       }
     }
     __syncthreads();
+    TREE_T(0);
     for (int p = tid; p < P2; p += nthr) {
       if (p < N) {
         int k = node_of(N, l, p);
@@ -209,6 +219,7 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
       }
     }
     __syncthreads();
+    TREE_T(1);
     // bitonic sort; when N is a power of two the nodes are aligned blocks of N>>l, sort inside blocks only
     const int kmax = pow2 ? (N >> l) : P2;
     // one compare-exchange per thread and round: pair q = (i, i | j)
@@ -220,28 +231,33 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
       const bool lt = key_less(ob, tb, oa, ta);  // b < a
       if (lt == up) { ord[i] = ob; ord[ixj] = oa; tag[i] = tb; tag[ixj] = ta; }
     };
+    // every warp owns a contiguous run of PW pairs, i.e. a window of 2 PW elements: rounds with j <= PW never leave the
+    // window and need a warp barrier only; whole merges k <= 2 PW run without any block barrier
+    const int npairs = P2 >> 1;
+    const int PW = max(32, npairs / (nthr >> 5));
+    const int wbase = (tid >> 5) * PW + (tid & 31);
     for (int k = 2; k <= kmax; k <<= 1) {
       int j = k >> 1;
-      for (; j >= 64; j >>= 1) {
-        for (int q = tid; q < (P2 >> 1); q += nthr) cmpx(q, j, k);
+      for (; j > PW; j >>= 1) {
+        for (int c = 0; c < PW; c += 32)
+          if (wbase + c < npairs) cmpx(wbase + c, j, k);
         __syncthreads();
       }
-      // rounds with j <= 32: the 32 pairs of a warp stay inside one 64-element window, so a warp barrier is enough
-      for (int q0 = 0; q0 < (P2 >> 1); q0 += nthr) {
-        const int q = q0 + tid;
-        for (int jj = j; jj > 0; jj >>= 1) {
-          if (q < (P2 >> 1)) cmpx(q, jj, k);
-          __syncwarp();
-        }
+      for (; j > 0; j >>= 1) {
+        for (int c = 0; c < PW; c += 32)
+          if (wbase + c < npairs) cmpx(wbase + c, j, k);
+        __syncwarp();
       }
-      __syncthreads();
+      if (k > PW || k == kmax) __syncthreads();
     }
+    TREE_T(2);
     // apply the permutation: position p now holds the element that sat at position tag&0x3fff
     int newp[CB2_MAX_PRODUCT_N / kTreeThreads];
     for (int p = tid, c = 0; p < N; p += nthr, ++c) newp[c] = perm[tag[p] & 0x3fffu];
     __syncthreads();
     for (int p = tid, c = 0; p < N; p += nthr, ++c) perm[p] = newp[c];
     __syncthreads();
+    TREE_T(3);
   }
 
   // ---- statistics, bottom-up in FP64 (global scratch: per level mean[cnt*d], var[cnt*d], wt[cnt])
@@ -263,17 +279,22 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
   double cmn[CB2_MAX_DIM], cmx[CB2_MAX_DIM];
 #pragma unroll
   for (int i = 0; i < CB2_MAX_DIM; ++i) { cmn[i] = 1e300; cmx[i] = -1e300; }
+  double cen[CB2_MAX_DIM];
+#pragma unroll
+  for (int i = 0; i < CB2_MAX_DIM; ++i) cen[i] = (i < d && !(circ_mask >> i & 1)) ? m.center[i] : 0.0;
   {
     double* sl = sbase + (size_t)lvl_off(depth) * nd;
     T* rec = node_pool + m.rec_off[depth];
     for (int p = tid; p < N; p += nthr) {
       int idx = perm[p];
       double wt = m.w ? m.w[idx] / wsum : 1.0 / N;
-      for (int i = 0; i < d; ++i) {
+#pragma unroll
+      for (int i = 0; i < CB2_MAX_DIM; ++i) {
+        if (i >= d) break;
         double v = m.pts[(size_t)idx * d + i];
         sl[(size_t)p * nd + i] = v;
         sl[(size_t)p * nd + d + i] = m.bw[i] * m.bw[i];
-        const double rv = (circ_mask >> i & 1) ? wrap_pi(v) : v - m.center[i];
+        const double rv = (circ_mask >> i & 1) ? wrap_pi(v) : v - cen[i];
         rec[(size_t)p * RECL + i] = (T)rv;
         if (circ_mask >> i & 1) { cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv); }
       }
@@ -283,6 +304,7 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
     }
   }
   __syncthreads();
+  TREE_T(4);
   for (int l = depth - 1; l >= 0; --l) {
     const int cnt = 1 << l;
     double* sl = sbase + (size_t)lvl_off(l) * nd;
@@ -291,22 +313,31 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
     for (int k = tid; k < cnt; k += nthr) {
       int c0, nch;
       if (l + 1 == depth) { node_range(N, l, k, c0, nch); } else { c0 = 2 * k; nch = 2; }
-      double ws = 0;
-      for (int c = 0; c < nch; ++c) ws += sc[(size_t)(c0 + c) * nd + 2 * d];
+      // both children (a node of the last split level may have one) are fetched before any arithmetic: the records were
+      // written by other threads of this CTA, so nothing can be kept in registers across levels, but all loads overlap
+      const double* r0 = sc + (size_t)c0 * nd;
+      const double* r1 = r0 + (nch > 1 ? nd : 0);
+      const double w0 = r0[2 * d], w1 = nch > 1 ? r1[2 * d] : 0.0;
+      double mu0[CB2_MAX_DIM], mu1[CB2_MAX_DIM], va0[CB2_MAX_DIM], va1[CB2_MAX_DIM];
+#pragma unroll
+      for (int i = 0; i < CB2_MAX_DIM; ++i) {
+        if (i < d) { mu0[i] = r0[i]; va0[i] = r0[d + i]; mu1[i] = r1[i]; va1[i] = r1[d + i]; }
+      }
+      const double ws = w0 + w1;
       sl[(size_t)k * nd + 2 * d] = ws;
-      for (int i = 0; i < d; ++i) {
-        double mm = 0;
-        for (int c = 0; c < nch; ++c) mm += sc[(size_t)(c0 + c) * nd + 2 * d] * sc[(size_t)(c0 + c) * nd + i];
+#pragma unroll
+      for (int i = 0; i < CB2_MAX_DIM; ++i) {
+        if (i >= d) break;
+        double mm = w0 * mu0[i];
+        mm += w1 * mu1[i];
         mm /= ws;
-        double v = 0;
-        for (int c = 0; c < nch; ++c) {
-          double dm = sc[(size_t)(c0 + c) * nd + i] - mm;
-          v += sc[(size_t)(c0 + c) * nd + 2 * d] * (sc[(size_t)(c0 + c) * nd + d + i] + dm * dm);
-        }
+        const double d0 = mu0[i] - mm, d1 = mu1[i] - mm;
+        double v = w0 * (va0[i] + d0 * d0);
+        v += w1 * (va1[i] + d1 * d1);
         v /= ws;
         sl[(size_t)k * nd + i] = mm;
         sl[(size_t)k * nd + d + i] = v;
-        const double rv = (circ_mask >> i & 1) ? wrap_pi(mm) : mm - m.center[i];
+        const double rv = (circ_mask >> i & 1) ? wrap_pi(mm) : mm - cen[i];
         rec[(size_t)k * RECN + i] = (T)rv;
         if (circ_mask >> i & 1) { cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv); }
         rec[(size_t)k * RECN + d + i] = (T)v;
@@ -316,8 +347,11 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
     }
     __syncthreads();
   }
+  TREE_T(5);
   // block-wide min / max of the circular record values -> last 16 doubles of this message's statistics scratch
-  for (int i = 0; i < d; ++i) {
+#pragma unroll
+  for (int i = 0; i < CB2_MAX_DIM; ++i) {
+    if (i >= d) break;
     double a = cmn[i], b = cmx[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -333,6 +367,12 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
     __syncthreads();
     if (tid == 0) { for (int w = 1; w < (nthr >> 5); ++w) b = fmax(b, s_red[w]); sbase[stat_stride - 8 + i] = b; }
   }
+#ifdef CB2_TREE_PROF
+  TREE_T(6);
+  if (tid == 0 && blockIdx.x == 0)
+    printf("tree prof (clk): range %lld fill %lld sort %lld perm %lld leafstat %lld upstat %lld final %lld\n", tprof[0], tprof[1], tprof[2],
+           tprof[3], tprof[4], tprof[5], tprof[6]);
+#endif
 }
 
 // vals[i*d .. i*d+d) = *ptrs[i]  (device-resident bandwidth vectors of a batch, fetched with one copy)
