@@ -138,22 +138,101 @@ __device__ __forceinline__ T score_node(const T* __restrict__ rec, const ChainCo
   return e;
 }
 
-// one scoring pass over the candidates of a level held in shared-memory tiles: chunk partial sums of exp2(e - m).
-// MODE 0: coarse level, 1: leaf level with per-kernel weights, 2: leaf level with uniform weights
-template <typename T, int DIM, int MODE>
-__device__ __forceinline__ T score_any_s(const T* rec, const ChainConst<T, DIM>& c, uint32_t circ, T nm) {
-  return MODE == 0 ? score_node<T, DIM, true>(rec, c, circ, nm)
-                   : (MODE == 1 ? score_leaf<T, DIM, true, false>(rec, c, circ, nm) : score_leaf<T, DIM, true, true>(rec, c, circ, nm));
-}
-template <typename T, int DIM, int MODE>
-__device__ __forceinline__ T score_any_g(const T* rec, const ChainConst<T, DIM>& c, uint32_t circ, T nm) {
-  return MODE == 0 ? score_node<T, DIM, false>(rec, c, circ, nm)
-                   : (MODE == 1 ? score_leaf<T, DIM, false, false>(rec, c, circ, nm) : score_leaf<T, DIM, false, true>(rec, c, circ, nm));
+// ---- packed FP32 pairs (fma.rn.f32x2 -> SASS FFMA2 on sm_100a): one issue slot for two lanes of arithmetic.  The kernel
+// is bound by the issue rate (gibbs_kernel: 72 % of issue slots vs 51 % of the FMA pipe), so the all-Euclidean scoring
+// loops of six-dimensional products pair the coordinates (0,1) (2,3) (4,5) exactly as LDS.128 delivers them.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+template <bool SHARED> __device__ __forceinline__ void load16p(const float* p, f32x2& lo, f32x2& hi) {
+  if (SHARED) asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(smem_u32(p)));
+  else asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p));
 }
 
-template <typename T, int DIM, int MODE>
+// per-chain constants of the packed loops (six dimensions as three pairs)
+struct PackedConst {
+  f32x2 a[3];  // leaf: sqrt(h)           coarse: -M
+  f32x2 b[3];  // leaf: -M sqrt(h)        coarse: C (1 for a single message)
+  f32x2 cmul;
+  float nqs;   // -qs
+};
+template <typename T, int DIM> __device__ __forceinline__ PackedConst make_packed(const ChainConst<T, DIM>& c, bool leaf) {
+  PackedConst p = {};
+  if constexpr (DIM == 6 && sizeof(T) == 4) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      p.a[k] = leaf ? pack2(c.a[2 * k], c.a[2 * k + 1]) : pack2(-c.a[2 * k], -c.a[2 * k + 1]);
+      p.b[k] = leaf ? pack2(-c.b[2 * k], -c.b[2 * k + 1]) : pack2(c.b[2 * k], c.b[2 * k + 1]);
+    }
+    p.cmul = pack2(c.cmul, c.cmul);
+    p.nqs = -c.qs;
+  }
+  return p;
+}
+
+// packed leaf score: same quantity as score_leaf without wrap; the squares are summed as (d0^2+d2^2+d4^2) + (d1^2+d3^2+d5^2)
+template <bool SHARED, bool UW>
+__device__ __forceinline__ float score_leaf_p(const float* __restrict__ rec, const PackedConst& c, float nm) {
+  f32x2 q0, q1, q2, q3;
+  load16p<SHARED>(rec, q0, q1);
+  load16p<SHARED>(rec + 4, q2, q3);
+  const f32x2 d0 = fma2(q0, c.a[0], c.b[0]), d1 = fma2(q1, c.a[1], c.b[1]), d2 = fma2(q2, c.a[2], c.b[2]);
+  f32x2 s = mul2(d0, d0);
+  s = fma2(d1, d1, s);
+  s = fma2(d2, d2, s);
+  float sx, sy, lw, pad;
+  unpack2(s, sx, sy);
+  unpack2(q3, lw, pad);
+  const float e = UW ? nm : lw + nm;
+  return (e - sx) - sy;
+}
+
+// packed coarse-node score: the two common-denominator groups are the even and the odd coordinates
+template <bool SHARED>
+__device__ __forceinline__ float score_node_p(const float* __restrict__ rec, const PackedConst& c, float nm) {
+  f32x2 m0, m1, m2, v0, v1, v2, w, pad;
+  load16p<SHARED>(rec, m0, m1);
+  load16p<SHARED>(rec + 4, m2, v0);
+  load16p<SHARED>(rec + 8, v1, v2);
+  load16p<SHARED>(rec + 12, w, pad);
+  const f32x2 d0 = add2(m0, c.a[0]), d1 = add2(m1, c.a[1]), d2 = add2(m2, c.a[2]);
+  const f32x2 t0 = mul2(d0, d0), t1 = mul2(d1, d1), t2 = mul2(d2, d2);
+  const f32x2 s0 = fma2(v0, c.cmul, c.b[0]), s1 = fma2(v1, c.cmul, c.b[1]), s2 = fma2(v2, c.cmul, c.b[2]);
+  const f32x2 s01 = mul2(s0, s1), s12 = mul2(s1, s2), s02 = mul2(s0, s2);
+  const f32x2 num = fma2(t0, s12, fma2(t1, s02, mul2(t2, s01)));
+  const f32x2 den = mul2(s01, s2);
+  float nx, ny, dx, dy, lw, p1;
+  unpack2(num, nx, ny);
+  unpack2(den, dx, dy);
+  unpack2(w, lw, p1);
+  float e = lw + nm;
+  e = fma(c.nqs * nx, fast_rcp(dx), e);
+  e = fma(-0.5f, fast_log2(dx), e);
+  e = fma(c.nqs * ny, fast_rcp(dy), e);
+  e = fma(-0.5f, fast_log2(dy), e);
+  return e;
+}
+
+// one scoring pass over the candidates of a level held in shared-memory tiles: chunk partial sums of exp2(e - m).
+// MODE 0: coarse level, 1: leaf level with per-kernel weights, 2: leaf level with uniform weights
+template <typename T, int DIM, int MODE, bool PACK, bool SHARED>
+__device__ __forceinline__ T score_any(const T* rec, const ChainConst<T, DIM>& c, const PackedConst& pc, uint32_t circ, T nm) {
+  if constexpr (PACK && DIM == 6 && sizeof(T) == 4) {
+    return MODE == 0 ? score_node_p<SHARED>(rec, pc, nm)
+                     : (MODE == 1 ? score_leaf_p<SHARED, false>(rec, pc, nm) : score_leaf_p<SHARED, true>(rec, pc, nm));
+  } else {
+    return MODE == 0 ? score_node<T, DIM, SHARED>(rec, c, circ, nm)
+                     : (MODE == 1 ? score_leaf<T, DIM, SHARED, false>(rec, c, circ, nm) : score_leaf<T, DIM, SHARED, true>(rec, c, circ, nm));
+  }
+}
+
+template <typename T, int DIM, int MODE, bool PACK>
 __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int zbase, int CH, const ChainConst<T, DIM>& cc,
-                                          uint32_t circ, T* __restrict__ chunk, int tid, T& m, T& csum, int& cidx) {
+                                          const PackedConst& pc, uint32_t circ, T* __restrict__ chunk, int tid, T& m, T& csum,
+                                          int& cidx) {
   constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
   constexpr int REC = MODE == 0 ? RECN : RECL;
   constexpr int G = kG;
@@ -162,14 +241,14 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
   for (int z = 0; z < ntg; z += G) {
     T e[G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) e[g] = score_any_s<T, DIM, MODE>(tb + (z + g) * REC, cc, circ, nm);
+    for (int g = 0; g < G; ++g) e[g] = score_any<T, DIM, MODE, PACK, true>(tb + (z + g) * REC, cc, pc, circ, nm);
     T gm = e[0];
 #pragma unroll
     for (int g = 1; g < G; ++g) gm = fmax(gm, e[g]);
     if (gm > T(60)) {  // rare: raise the reference by gm and rescale what has been summed so far
       if (nm == INFINITY) {  // first group of the pass: scores were computed against m = -inf, nothing summed yet
 #pragma unroll
-        for (int g = 0; g < G; ++g) e[g] = score_any_s<T, DIM, MODE>(tb + (z + g) * REC, cc, circ, T(0));
+        for (int g = 0; g < G; ++g) e[g] = score_any<T, DIM, MODE, PACK, true>(tb + (z + g) * REC, cc, pc, circ, T(0));
         gm = e[0];
 #pragma unroll
         for (int g = 1; g < G; ++g) gm = fmax(gm, e[g]);
@@ -189,9 +268,9 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
     if (((zbase + z + G) & (CH - 1)) == 0) { chunk[cidx * kS + tid] = csum; csum = T(0); ++cidx; }
   }
   for (int z = ntg; z < nt; ++z) {  // ragged tail of the level (count not a multiple of G)
-    T e = score_any_s<T, DIM, MODE>(tb + z * REC, cc, circ, nm);
+    T e = score_any<T, DIM, MODE, PACK, true>(tb + z * REC, cc, pc, circ, nm);
     if (e > T(60)) {
-      if (nm == INFINITY) { e = score_any_s<T, DIM, MODE>(tb + z * REC, cc, circ, T(0)); m = e; }
+      if (nm == INFINITY) { e = score_any<T, DIM, MODE, PACK, true>(tb + z * REC, cc, pc, circ, T(0)); m = e; }
       else {
         T sc = fast_exp2(-e);
         csum *= sc;
@@ -206,9 +285,9 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
 }
 
 // pass 2: re-score the selected chunk from global memory until the cumulative sum crosses the target
-template <typename T, int DIM, int MODE>
-__device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, int z1, const ChainConst<T, DIM>& cc, uint32_t circ,
-                                          T m, T cum, T tgt) {
+template <typename T, int DIM, int MODE, bool PACK>
+__device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, int z1, const ChainConst<T, DIM>& cc,
+                                          const PackedConst& pc, uint32_t circ, T m, T cum, T tgt) {
   constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
   constexpr int REC = MODE == 0 ? RECN : RECL;
   int pick = -1, lastpos = z0;
@@ -220,7 +299,7 @@ __device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, in
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int zz = min(z + g, z1 - 1);
-      p[g] = fast_exp2(score_any_g<T, DIM, MODE>(lrec + (size_t)zz * REC, cc, circ, nm));
+      p[g] = fast_exp2(score_any<T, DIM, MODE, PACK, false>(lrec + (size_t)zz * REC, cc, pc, circ, nm));
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -383,7 +462,9 @@ gibbs_kernel(const GibbsArgs a) {
         }
 
         // warp-uniform choice of the scoring loop (all chains of the warp must agree)
-        const bool warp_nowrap = circ != 0u && __all_sync(0xffffffffu, nowrap);
+        const bool flat = circ == 0u || __all_sync(0xffffffffu, nowrap);
+        constexpr bool kPack = DIM == 6 && sizeof(T) == 4;  // packed-pair scoring (see PackedConst)
+        const PackedConst pc = make_packed<T, DIM>(cc, leaf);
         // ---- pass 1: chunk partial sums of exp2(e - m), m = running (lazily raised) reference maximum
         T m = -INFINITY, csum = T(0);
         int cidx = 0;
@@ -404,14 +485,14 @@ gibbs_kernel(const GibbsArgs a) {
           if (b) ++use1; else ++use0;
           const int nt = min(TN, cnt - t * TN);
           const T* tb = reinterpret_cast<const T*>(smem_raw + b * TILE_BYTES);
-          if (warp_nowrap) {  // Euclidean arithmetic on every coordinate: same values, 2 instructions per dim less
-            if (!leaf) tile_pass<T, DIM, 0>(tb, nt, t * TN, CH, cc, 0u, chunk, tid, m, csum, cidx);
-            else if (!dj.uniform) tile_pass<T, DIM, 1>(tb, nt, t * TN, CH, cc, 0u, chunk, tid, m, csum, cidx);
-            else tile_pass<T, DIM, 2>(tb, nt, t * TN, CH, cc, 0u, chunk, tid, m, csum, cidx);
+          if (flat) {  // Euclidean arithmetic on every coordinate: same values as the wrapped form, fewer instructions
+            if (!leaf) tile_pass<T, DIM, 0, kPack>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
+            else if (!dj.uniform) tile_pass<T, DIM, 1, kPack>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
+            else tile_pass<T, DIM, 2, kPack>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
           } else {
-            if (!leaf) tile_pass<T, DIM, 0>(tb, nt, t * TN, CH, cc, circ, chunk, tid, m, csum, cidx);
-            else if (!dj.uniform) tile_pass<T, DIM, 1>(tb, nt, t * TN, CH, cc, circ, chunk, tid, m, csum, cidx);
-            else tile_pass<T, DIM, 2>(tb, nt, t * TN, CH, cc, circ, chunk, tid, m, csum, cidx);
+            if (!leaf) tile_pass<T, DIM, 0, false>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
+            else if (!dj.uniform) tile_pass<T, DIM, 1, false>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
+            else tile_pass<T, DIM, 2, false>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
           }
           __syncthreads();  // everyone is done with tile[b] before it is refilled
         }
@@ -433,9 +514,17 @@ gibbs_kernel(const GibbsArgs a) {
           cum += v;
         }
         const int z0 = sel * CH, z1 = min(cnt, z0 + CH);
-        const int pick = !leaf ? chunk_pick<T, DIM, 0>(lrec, z0, z1, cc, circ, m, cum, tgt)
-                               : (!dj.uniform ? chunk_pick<T, DIM, 1>(lrec, z0, z1, cc, circ, m, cum, tgt)
-                                              : chunk_pick<T, DIM, 2>(lrec, z0, z1, cc, circ, m, cum, tgt));
+        // pass 2 must reproduce the scores of pass 1 bit for bit, so it takes the same (packed or wrapped) scorer
+        int pick;
+        if (flat) {
+          pick = !leaf ? chunk_pick<T, DIM, 0, kPack>(lrec, z0, z1, cc, pc, 0u, m, cum, tgt)
+                       : (!dj.uniform ? chunk_pick<T, DIM, 1, kPack>(lrec, z0, z1, cc, pc, 0u, m, cum, tgt)
+                                      : chunk_pick<T, DIM, 2, kPack>(lrec, z0, z1, cc, pc, 0u, m, cum, tgt));
+        } else {
+          pick = !leaf ? chunk_pick<T, DIM, 0, false>(lrec, z0, z1, cc, pc, circ, m, cum, tgt)
+                       : (!dj.uniform ? chunk_pick<T, DIM, 1, false>(lrec, z0, z1, cc, pc, circ, m, cum, tgt)
+                                      : chunk_pick<T, DIM, 2, false>(lrec, z0, z1, cc, pc, circ, m, cum, tgt));
+        }
         if (active) ind_s[j * kS + tid] = pick;
       }
     }
