@@ -8,8 +8,11 @@
 // Circular coordinates are stored wrapped to [-pi, pi] (tree_build_kernel) and the chain mean comes out of atan2,
 // so |mu - M| <= 2 pi and the wrapped distance is min(|df|, 2 pi - |df|): no rounding instruction needed.
 // When every chain of a warp can prove from the message's coordinate range (tree_build_kernel) that no candidate is
-// more than pi away from its mean, the warp takes the all-Euclidean loop (`warp_nowrap`): identical values, 2
+// more than pi away from its mean, the warp takes the all-Euclidean loop (`flat`): identical values, 2
 // instructions per circular dimension fewer.  Beliefs that do not straddle the +-pi cut always qualify.
+// Shared-memory bandwidth is the other limiter (a warp-broadcast LDS.128 costs 2.4 clk of the SM-wide pipe,
+// bench/micro/lds_bcast.cu; doubling the record loads of the d = 6 kernel cost +56 %), so the FP32 d = 6 kernel runs
+// two chains per thread: every record register is used by both chains (kChains<T, DIM>).
 
 template <typename T, int N> struct alignas(16) VecRec { T v[N]; };
 
@@ -25,16 +28,17 @@ struct GibbsArgs {
   size_t stat_stride;
 };
 
-// what the kernel needs of each message, staged once per CTA in shared memory
-struct SMeta {
-  long long rec_off[kMaxLev + 1];
+// what the kernel needs of each message, staged once per CTA in shared memory (kept small: with two chains per thread the
+// CTA has 64 threads and seven CTAs share an SM, so the shared-memory footprint per CTA decides the occupancy)
+template <typename T> struct SMeta {
+  uint32_t rec_off32[kMaxLev + 1];  // level record offsets in units of 32 elements (validate_and_plan aligns them)
   long long perm_off;
-  float bw2[CB2_MAX_DIM];
-  double bw2d[CB2_MAX_DIM];
-  double cen[CB2_MAX_DIM];  // offset to add back to Euclidean output coordinates
+  T bw2[CB2_MAX_DIM];
   float cmin[CB2_MAX_DIM], cmax[CB2_MAX_DIM];  // range of the stored circular coordinates over all levels
   int N, depth, uniform;
+  __device__ __forceinline__ size_t rec_off(int l) const { return (size_t)rec_off32[l] * 32; }
 };
+typedef unsigned short ind_t;  // selected node of a chain on the current level (< 2^14)
 
 template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
 template <> __device__ __forceinline__ float tmin<float>(float a, float b) { return fminf(a, b); }
@@ -78,14 +82,73 @@ template <int N, bool SHARED> __device__ __forceinline__ void load_rec(const dou
   }
 }
 
+// chains per thread: a record fetched from shared memory is scored against this many chains
+#ifndef CB2_GIBBS_R
+#define CB2_GIBBS_R 1
+#endif
+#ifndef CB2_GIBBS_CTAS
+#define CB2_GIBBS_CTAS 4
+#endif
+template <typename T, int DIM> struct ChainsPerThread { static constexpr int value = CB2_GIBBS_R; };
+// bytes of one TMA stage: 8 KB of FP32 records (twice that in FP64), halved when the CTA has half the threads
+template <typename T, int DIM> __host__ __device__ constexpr int gibbs_tile_bytes() {
+  return kTileBytesF32 * (int)(sizeof(T) / 4) / ChainsPerThread<T, DIM>::value;
+}
+
+// ---- packed FP32 pairs (fma.rn.f32x2 -> SASS FFMA2 on sm_100a): one issue slot for two lanes of arithmetic; the
+// all-Euclidean scoring loops of six-dimensional products pair the coordinates (0,1) (2,3) (4,5) as LDS.128 delivers them.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+template <bool SHARED> __device__ __forceinline__ void load16p(const float* p, f32x2& lo, f32x2& hi) {
+  if (SHARED) asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(smem_u32(p)));
+  else asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p));
+}
+template <bool SHARED> __device__ __forceinline__ void load16p(const double*, f32x2&, f32x2&) {}
+
+// one candidate record in registers: N values of T, or (PACK) N/2 packed pairs
+template <typename T, int N, bool PACK> struct RecR {
+  T v[PACK ? 1 : N];
+  f32x2 q[PACK ? N / 2 : 1];
+};
+template <bool SHARED, typename T, int N, bool PACK> __device__ __forceinline__ void load_recr(const T* p, RecR<T, N, PACK>& r) {
+  if constexpr (PACK) {
+#pragma unroll
+    for (int k = 0; k < N / 4; ++k) load16p<SHARED>(p + 4 * k, r.q[2 * k], r.q[2 * k + 1]);
+  } else {
+    load_rec<N, SHARED>(p, r.v);
+  }
+}
+
+// per-chain constants of the packed loops (six dimensions as three pairs)
+struct PackedConst {
+  f32x2 a[3];  // leaf: sqrt(h)           coarse: -M
+  f32x2 b[3];  // leaf: -M sqrt(h)        coarse: C (1 for a single message)
+  f32x2 cmul;
+  float nqs;   // -qs
+};
+template <typename T, int DIM> __device__ __forceinline__ PackedConst make_packed(const ChainConst<T, DIM>& c, bool leaf) {
+  PackedConst p = {};
+  if constexpr (DIM == 6 && sizeof(T) == 4) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      p.a[k] = leaf ? pack2(c.a[2 * k], c.a[2 * k + 1]) : pack2(-c.a[2 * k], -c.a[2 * k + 1]);
+      p.b[k] = leaf ? pack2(-c.b[2 * k], -c.b[2 * k + 1]) : pack2(c.b[2 * k], c.b[2 * k + 1]);
+    }
+    p.cmul = pack2(c.cmul, c.cmul);
+    p.nqs = -c.qs;
+  }
+  return p;
+}
+
 // log2-score of a leaf relative to the running reference m (nm = -m):
 //   log2 w - m - sum_i wrapdiff_i^2 * h_i   (h_i = 0.5 log2e / (bw_i^2 + C_i); the log-variance term is the same
 //   for every leaf of the level and cancels in the normalisation; with uniform weights so does log2 w: UW)
-template <typename T, int DIM, bool SHARED, bool UW>
-__device__ __forceinline__ T score_leaf(const T* __restrict__ rec, const ChainConst<T, DIM>& c, uint32_t circ, T nm) {
-  constexpr int RECL = (DIM + 1 + 3) / 4 * 4;
-  T r[RECL];
-  load_rec<RECL, SHARED>(rec, r);
+template <typename T, int DIM, bool UW, int RECL>
+__device__ __forceinline__ T score_leaf(const T (&r)[RECL], const ChainConst<T, DIM>& c, uint32_t circ, T nm) {
   T e = UW ? nm : r[DIM] + nm;
 #pragma unroll
   for (int i = 0; i < DIM; ++i) {
@@ -100,11 +163,8 @@ __device__ __forceinline__ T score_leaf(const T* __restrict__ rec, const ChainCo
 }
 
 // log2-score of a coarse node relative to m: log2 w - m - qs sum_i d_i^2/(var_i + C_i) - 0.5 sum_i log2(var_i + C_i)
-template <typename T, int DIM, bool SHARED>
-__device__ __forceinline__ T score_node(const T* __restrict__ rec, const ChainConst<T, DIM>& c, uint32_t circ, T nm) {
-  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4;
-  T r[RECN];
-  load_rec<RECN, SHARED>(rec, r);
+template <typename T, int DIM, int RECN>
+__device__ __forceinline__ T score_node(const T (&r)[RECN], const ChainConst<T, DIM>& c, uint32_t circ, T nm) {
   T t[DIM], sv[DIM];
 #pragma unroll
   for (int i = 0; i < DIM; ++i) {
@@ -138,76 +198,32 @@ __device__ __forceinline__ T score_node(const T* __restrict__ rec, const ChainCo
   return e;
 }
 
-// ---- packed FP32 pairs (fma.rn.f32x2 -> SASS FFMA2 on sm_100a): one issue slot for two lanes of arithmetic.  The kernel
-// is bound by the issue rate (gibbs_kernel: 72 % of issue slots vs 51 % of the FMA pipe), so the all-Euclidean scoring
-// loops of six-dimensional products pair the coordinates (0,1) (2,3) (4,5) exactly as LDS.128 delivers them.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-template <bool SHARED> __device__ __forceinline__ void load16p(const float* p, f32x2& lo, f32x2& hi) {
-  if (SHARED) asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(smem_u32(p)));
-  else asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p));
-}
-
-// per-chain constants of the packed loops (six dimensions as three pairs)
-struct PackedConst {
-  f32x2 a[3];  // leaf: sqrt(h)           coarse: -M
-  f32x2 b[3];  // leaf: -M sqrt(h)        coarse: C (1 for a single message)
-  f32x2 cmul;
-  float nqs;   // -qs
-};
-template <typename T, int DIM> __device__ __forceinline__ PackedConst make_packed(const ChainConst<T, DIM>& c, bool leaf) {
-  PackedConst p = {};
-  if constexpr (DIM == 6 && sizeof(T) == 4) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      p.a[k] = leaf ? pack2(c.a[2 * k], c.a[2 * k + 1]) : pack2(-c.a[2 * k], -c.a[2 * k + 1]);
-      p.b[k] = leaf ? pack2(-c.b[2 * k], -c.b[2 * k + 1]) : pack2(c.b[2 * k], c.b[2 * k + 1]);
-    }
-    p.cmul = pack2(c.cmul, c.cmul);
-    p.nqs = -c.qs;
-  }
-  return p;
-}
-
 // packed leaf score: same quantity as score_leaf without wrap; the squares are summed as (d0^2+d2^2+d4^2) + (d1^2+d3^2+d5^2)
-template <bool SHARED, bool UW>
-__device__ __forceinline__ float score_leaf_p(const float* __restrict__ rec, const PackedConst& c, float nm) {
-  f32x2 q0, q1, q2, q3;
-  load16p<SHARED>(rec, q0, q1);
-  load16p<SHARED>(rec + 4, q2, q3);
-  const f32x2 d0 = fma2(q0, c.a[0], c.b[0]), d1 = fma2(q1, c.a[1], c.b[1]), d2 = fma2(q2, c.a[2], c.b[2]);
+template <bool UW>
+__device__ __forceinline__ float score_leaf_p(const f32x2 (&q)[4], const PackedConst& c, float nm) {
+  const f32x2 d0 = fma2(q[0], c.a[0], c.b[0]), d1 = fma2(q[1], c.a[1], c.b[1]), d2 = fma2(q[2], c.a[2], c.b[2]);
   f32x2 s = mul2(d0, d0);
   s = fma2(d1, d1, s);
   s = fma2(d2, d2, s);
   float sx, sy, lw, pad;
   unpack2(s, sx, sy);
-  unpack2(q3, lw, pad);
+  unpack2(q[3], lw, pad);
   const float e = UW ? nm : lw + nm;
   return (e - sx) - sy;
 }
 
 // packed coarse-node score: the two common-denominator groups are the even and the odd coordinates
-template <bool SHARED>
-__device__ __forceinline__ float score_node_p(const float* __restrict__ rec, const PackedConst& c, float nm) {
-  f32x2 m0, m1, m2, v0, v1, v2, w, pad;
-  load16p<SHARED>(rec, m0, m1);
-  load16p<SHARED>(rec + 4, m2, v0);
-  load16p<SHARED>(rec + 8, v1, v2);
-  load16p<SHARED>(rec + 12, w, pad);
-  const f32x2 d0 = add2(m0, c.a[0]), d1 = add2(m1, c.a[1]), d2 = add2(m2, c.a[2]);
+__device__ __forceinline__ float score_node_p(const f32x2 (&q)[8], const PackedConst& c, float nm) {
+  const f32x2 d0 = add2(q[0], c.a[0]), d1 = add2(q[1], c.a[1]), d2 = add2(q[2], c.a[2]);
   const f32x2 t0 = mul2(d0, d0), t1 = mul2(d1, d1), t2 = mul2(d2, d2);
-  const f32x2 s0 = fma2(v0, c.cmul, c.b[0]), s1 = fma2(v1, c.cmul, c.b[1]), s2 = fma2(v2, c.cmul, c.b[2]);
+  const f32x2 s0 = fma2(q[3], c.cmul, c.b[0]), s1 = fma2(q[4], c.cmul, c.b[1]), s2 = fma2(q[5], c.cmul, c.b[2]);
   const f32x2 s01 = mul2(s0, s1), s12 = mul2(s1, s2), s02 = mul2(s0, s2);
   const f32x2 num = fma2(t0, s12, fma2(t1, s02, mul2(t2, s01)));
   const f32x2 den = mul2(s01, s2);
   float nx, ny, dx, dy, lw, p1;
   unpack2(num, nx, ny);
   unpack2(den, dx, dy);
-  unpack2(w, lw, p1);
+  unpack2(q[6], lw, p1);
   float e = lw + nm;
   e = fma(c.nqs * nx, fast_rcp(dx), e);
   e = fma(-0.5f, fast_log2(dx), e);
@@ -216,71 +232,98 @@ __device__ __forceinline__ float score_node_p(const float* __restrict__ rec, con
   return e;
 }
 
-// one scoring pass over the candidates of a level held in shared-memory tiles: chunk partial sums of exp2(e - m).
 // MODE 0: coarse level, 1: leaf level with per-kernel weights, 2: leaf level with uniform weights
-template <typename T, int DIM, int MODE, bool PACK, bool SHARED>
-__device__ __forceinline__ T score_any(const T* rec, const ChainConst<T, DIM>& c, const PackedConst& pc, uint32_t circ, T nm) {
-  if constexpr (PACK && DIM == 6 && sizeof(T) == 4) {
-    return MODE == 0 ? score_node_p<SHARED>(rec, pc, nm)
-                     : (MODE == 1 ? score_leaf_p<SHARED, false>(rec, pc, nm) : score_leaf_p<SHARED, true>(rec, pc, nm));
+template <int DIM, int MODE> struct RecLen { static constexpr int value = MODE == 0 ? (2 * DIM + 1 + 3) / 4 * 4 : (DIM + 1 + 3) / 4 * 4; };
+
+template <typename T, int DIM, int MODE, bool PACK>
+__device__ __forceinline__ T score_regs(const RecR<T, RecLen<DIM, MODE>::value, PACK>& r, const ChainConst<T, DIM>& c,
+                                        const PackedConst& pc, uint32_t circ, T nm) {
+  if constexpr (PACK) {
+    if constexpr (MODE == 0) return score_node_p(r.q, pc, nm);
+    else return score_leaf_p<MODE == 2>(r.q, pc, nm);
   } else {
-    return MODE == 0 ? score_node<T, DIM, SHARED>(rec, c, circ, nm)
-                     : (MODE == 1 ? score_leaf<T, DIM, SHARED, false>(rec, c, circ, nm) : score_leaf<T, DIM, SHARED, true>(rec, c, circ, nm));
+    if constexpr (MODE == 0) return score_node<T, DIM>(r.v, c, circ, nm);
+    else return score_leaf<T, DIM, MODE == 2>(r.v, c, circ, nm);
   }
 }
 
-template <typename T, int DIM, int MODE, bool PACK>
-__device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int zbase, int CH, const ChainConst<T, DIM>& cc,
-                                          const PackedConst& pc, uint32_t circ, T* __restrict__ chunk, int tid, T& m, T& csum,
-                                          int& cidx) {
-  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
-  constexpr int REC = MODE == 0 ? RECN : RECL;
-  constexpr int G = kG;
-  const int ntg = nt & ~(G - 1);
-  T nm = -m;
+// one scoring pass over the candidates of a level held in a shared-memory tile: chunk partial sums of exp2(e - m) for
+// the R chains of this thread; every record is fetched once and scored against all R chains
+template <typename T, int DIM, int MODE, bool PACK, int R>
+__device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int zbase, int CH, const ChainConst<T, DIM> (&cc)[R],
+                                          const PackedConst (&pc)[R], uint32_t circ, T* __restrict__ chunk, int tid, T (&m)[R],
+                                          T (&csum)[R], int& cidx) {
+  constexpr int REC = RecLen<DIM, MODE>::value;
+  constexpr int NT = kS / R;   // threads per CTA; chain r of this thread is column r * NT + tid of the per-chain arrays
+  constexpr int G = kG / R;    // candidates scored together: G * R independent evaluations in flight
+  const int ntg = nt & ~(kG - 1);
+  T nm[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) nm[r] = -m[r];
   for (int z = 0; z < ntg; z += G) {
-    T e[G];
+    T e[R][G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) e[g] = score_any<T, DIM, MODE, PACK, true>(tb + (z + g) * REC, cc, pc, circ, nm);
-    T gm = e[0];
+    for (int g = 0; g < G; ++g) {
+      RecR<T, REC, PACK> rec;
+      load_recr<true>(tb + (z + g) * REC, rec);
 #pragma unroll
-    for (int g = 1; g < G; ++g) gm = fmax(gm, e[g]);
-    if (gm > T(60)) {  // rare: raise the reference by gm and rescale what has been summed so far
-      if (nm == INFINITY) {  // first group of the pass: scores were computed against m = -inf, nothing summed yet
-#pragma unroll
-        for (int g = 0; g < G; ++g) e[g] = score_any<T, DIM, MODE, PACK, true>(tb + (z + g) * REC, cc, pc, circ, T(0));
-        gm = e[0];
-#pragma unroll
-        for (int g = 1; g < G; ++g) gm = fmax(gm, e[g]);
-        m = gm;
-      } else {
-        T sc = fast_exp2(-gm);
-        csum *= sc;
-        for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
-        m += gm;
-      }
-#pragma unroll
-      for (int g = 0; g < G; ++g) e[g] -= gm;
-      nm = -m;
+      for (int r = 0; r < R; ++r) e[r][g] = score_regs<T, DIM, MODE, PACK>(rec, cc[r], pc[r], circ, nm[r]);
     }
 #pragma unroll
-    for (int g = 0; g < G; ++g) csum += fast_exp2(e[g]);
-    if (((zbase + z + G) & (CH - 1)) == 0) { chunk[cidx * kS + tid] = csum; csum = T(0); ++cidx; }
+    for (int r = 0; r < R; ++r) {
+      T gm = e[r][0];
+#pragma unroll
+      for (int g = 1; g < G; ++g) gm = fmax(gm, e[r][g]);
+      if (gm > T(60)) {  // rare: raise the reference by gm and rescale what has been summed so far
+        if (nm[r] == INFINITY) {  // first group of the pass: scores were computed against m = -inf, nothing summed yet
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            RecR<T, REC, PACK> rec;
+            load_recr<true>(tb + (z + g) * REC, rec);
+            e[r][g] = score_regs<T, DIM, MODE, PACK>(rec, cc[r], pc[r], circ, T(0));
+          }
+          gm = e[r][0];
+#pragma unroll
+          for (int g = 1; g < G; ++g) gm = fmax(gm, e[r][g]);
+          m[r] = gm;
+        } else {
+          T sc = fast_exp2(-gm);
+          csum[r] *= sc;
+          for (int c = 0; c < cidx; ++c) chunk[c * kS + r * NT + tid] *= sc;
+          m[r] += gm;
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) e[r][g] -= gm;
+        nm[r] = -m[r];
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) csum[r] += fast_exp2(e[r][g]);
+    }
+    if (((zbase + z + G) & (CH - 1)) == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) { chunk[cidx * kS + r * NT + tid] = csum[r]; csum[r] = T(0); }
+      ++cidx;
+    }
   }
-  for (int z = ntg; z < nt; ++z) {  // ragged tail of the level (count not a multiple of G)
-    T e = score_any<T, DIM, MODE, PACK, true>(tb + z * REC, cc, pc, circ, nm);
-    if (e > T(60)) {
-      if (nm == INFINITY) { e = score_any<T, DIM, MODE, PACK, true>(tb + z * REC, cc, pc, circ, T(0)); m = e; }
-      else {
-        T sc = fast_exp2(-e);
-        csum *= sc;
-        for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
-        m += e;
+  for (int z = ntg; z < nt; ++z) {  // ragged tail of the level (count not a multiple of kG)
+    RecR<T, REC, PACK> rec;
+    load_recr<true>(tb + z * REC, rec);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      T e = score_regs<T, DIM, MODE, PACK>(rec, cc[r], pc[r], circ, nm[r]);
+      if (e > T(60)) {
+        if (nm[r] == INFINITY) { e = score_regs<T, DIM, MODE, PACK>(rec, cc[r], pc[r], circ, T(0)); m[r] = e; }
+        else {
+          T sc = fast_exp2(-e);
+          csum[r] *= sc;
+          for (int c = 0; c < cidx; ++c) chunk[c * kS + r * NT + tid] *= sc;
+          m[r] += e;
+        }
+        e = T(0);
+        nm[r] = -m[r];
       }
-      e = T(0);
-      nm = -m;
+      csum[r] += fast_exp2(e);
     }
-    csum += fast_exp2(e);
   }
 }
 
@@ -288,8 +331,7 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
 template <typename T, int DIM, int MODE, bool PACK>
 __device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, int z1, const ChainConst<T, DIM>& cc,
                                           const PackedConst& pc, uint32_t circ, T m, T cum, T tgt) {
-  constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
-  constexpr int REC = MODE == 0 ? RECN : RECL;
+  constexpr int REC = RecLen<DIM, MODE>::value;
   int pick = -1, lastpos = z0;
   const T nm = -m;
   // four candidates per round: their (divergent, L2-resident) record loads are in flight together; the cumulative
@@ -299,7 +341,9 @@ __device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, in
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int zz = min(z + g, z1 - 1);
-      p[g] = fast_exp2(score_any<T, DIM, MODE, PACK, false>(lrec + (size_t)zz * REC, cc, pc, circ, nm));
+      RecR<T, REC, PACK> rec;
+      load_recr<false>(lrec + (size_t)zz * REC, rec);
+      p[g] = fast_exp2(score_regs<T, DIM, MODE, PACK>(rec, cc, pc, circ, nm));
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -315,8 +359,8 @@ __device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, in
 
 // Gaussian product of the currently selected nodes of all messages except `skip` (skip = -1: all)
 template <typename T, int DIM>
-__device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta* __restrict__ sm, int D,
-                                        const int* __restrict__ ind_s, int tid, int step, int skip, uint32_t circ,
+__device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta<T>* __restrict__ sm, int D,
+                                        const ind_t* __restrict__ ind_s, int tid, int step, int skip, uint32_t circ,
                                         T (&M)[DIM], T (&C)[DIM]) {
   constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
   T lam[DIM], s1[DIM], s2[DIM];
@@ -326,16 +370,16 @@ __device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta*
 #pragma unroll 4
   for (int kk = 0; kk < nk; ++kk) {  // branch-free skip so that the independent gathers of several messages overlap
     const int k = kk + ((skip >= 0 && kk >= skip) ? 1 : 0);
-    const SMeta& dm = sm[k];
+    const SMeta<T>& dm = sm[k];
     const int lev = min(step, dm.depth);
     const int node = ind_s[k * kS + tid];
     T mu[DIM], var[DIM];
     if (lev == dm.depth) {
-      const VecRec<T, RECL> r = *reinterpret_cast<const VecRec<T, RECL>*>(pool + dm.rec_off[lev] + (size_t)node * RECL);
+      const VecRec<T, RECL> r = *reinterpret_cast<const VecRec<T, RECL>*>(pool + dm.rec_off(lev) + (size_t)node * RECL);
 #pragma unroll
-      for (int i = 0; i < DIM; ++i) { mu[i] = r.v[i]; var[i] = sizeof(T) == 4 ? (T)dm.bw2[i] : (T)dm.bw2d[i]; }
+      for (int i = 0; i < DIM; ++i) { mu[i] = r.v[i]; var[i] = dm.bw2[i]; }
     } else {
-      const VecRec<T, RECN> r = *reinterpret_cast<const VecRec<T, RECN>*>(pool + dm.rec_off[lev] + (size_t)node * RECN);
+      const VecRec<T, RECN> r = *reinterpret_cast<const VecRec<T, RECN>*>(pool + dm.rec_off(lev) + (size_t)node * RECN);
 #pragma unroll
       for (int i = 0; i < DIM; ++i) { mu[i] = r.v[i]; var[i] = r.v[DIM + i]; }
     }
@@ -360,29 +404,37 @@ __device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta*
 }
 
 template <typename T, int DIM, uint32_t CIRC>
-__global__ void __launch_bounds__(kS, 4)
+__global__ void __launch_bounds__(kS / ChainsPerThread<T, DIM>::value, ChainsPerThread<T, DIM>::value == 2 ? 7 : (sizeof(T) == 4 ? CB2_GIBBS_CTAS : 4))
 gibbs_kernel(const GibbsArgs a) {
   constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
-  constexpr int TILE_BYTES = kTileBytesF32 * (int)(sizeof(T) / 4);
+  constexpr int TILE_BYTES = gibbs_tile_bytes<T, DIM>();
   constexpr int TN_NODE = TILE_BYTES / (RECN * (int)sizeof(T));
   constexpr int TN_LEAF = TILE_BYTES / (RECL * (int)sizeof(T));
-  constexpr int G = kG;  // candidates scored together (ILP, see tile_pass); tiles and chunks are multiples of G
+  constexpr int R = ChainsPerThread<T, DIM>::value;  // chains per thread
+  constexpr int NT = kS / R;                          // threads per CTA; the CTA always advances kS chains
+  constexpr bool kPack = DIM == 6 && sizeof(T) == 4;  // packed-pair scoring (see PackedConst)
   const uint32_t circ = CIRC == ~0u ? a.circ_mask : CIRC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* tile[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw + TILE_BYTES)};
   T* chunk = reinterpret_cast<T*>(smem_raw + 2 * TILE_BYTES);                // [kNCH][kS]
-  int* ind_s = reinterpret_cast<int*>(chunk + kNCH * kS);                      // [CB2_MAX_DENS][kS]
+  ind_t* ind_s = reinterpret_cast<ind_t*>(chunk + kNCH * kS);                  // [CB2_MAX_DENS][kS]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ind_s + CB2_MAX_DENS * kS);    // [2]
-  SMeta* sm = reinterpret_cast<SMeta*>(bars + 2);                              // [CB2_MAX_DENS]
+  SMeta<T>* sm = reinterpret_cast<SMeta<T>*>(bars + 2);                        // [CB2_MAX_DENS]
 
   const int tid = threadIdx.x;
   const Work wk = a.work[blockIdx.x];
   const ProdDev* __restrict__ prp = &a.prods[wk.prod];
   const int D = prp->D, L = prp->L, sweeps = prp->sweeps, Nout = prp->Nout;
   const uint32_t pstream = prp->stream;
-  const int s = wk.s0 + tid;
-  const bool active = s < Nout;
-  const uint32_t sid = (uint32_t)(prp->sample_offset + s);
+  int col[R];        // column of chain r in the per-chain shared arrays
+  bool active[R];
+  uint32_t sid[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    col[r] = r * NT + tid;
+    active[r] = wk.s0 + col[r] < Nout;
+    sid[r] = (uint32_t)(prp->sample_offset + wk.s0 + col[r]);
+  }
   const T* pool = reinterpret_cast<const T*>(a.node_pool);
   const T HL = (T)(0.5 * CB2_LOG2E);
   const bool single = D == 1;
@@ -394,13 +446,10 @@ gibbs_kernel(const GibbsArgs a) {
   }
   if (tid < D) {
     const DensMeta& dm = a.metas[prp->dens[tid]];
-    SMeta m;
-    for (int l = 0; l <= kMaxLev; ++l) m.rec_off[l] = dm.rec_off[l];
+    SMeta<T> m;
+    for (int l = 0; l <= kMaxLev; ++l) m.rec_off32[l] = (uint32_t)(dm.rec_off[l] >> 5);
     m.perm_off = dm.perm_off;
-    for (int i = 0; i < CB2_MAX_DIM; ++i) {
-      m.bw2d[i] = dm.bw[i] * dm.bw[i]; m.bw2[i] = (float)m.bw2d[i];
-      m.cen[i] = (i < DIM && !(circ >> i & 1)) ? dm.center[i] : 0.0;
-    }
+    for (int i = 0; i < CB2_MAX_DIM; ++i) m.bw2[i] = (T)(dm.bw[i] * dm.bw[i]);
     m.N = dm.N; m.depth = dm.depth; m.uniform = dm.w == nullptr;
     {
       const double* rg = a.stat + (size_t)prp->dens[tid] * a.stat_stride + (a.stat_stride - 16);
@@ -408,7 +457,9 @@ gibbs_kernel(const GibbsArgs a) {
     }
     sm[tid] = m;
   }
-  for (int k = 0; k < D; ++k) ind_s[k * kS + tid] = 0;
+  for (int k = 0; k < D; ++k)
+#pragma unroll
+    for (int r = 0; r < R; ++r) ind_s[k * kS + col[r]] = 0;
   __syncthreads();
   uint32_t use0 = 0, use1 = 0;  // completed uses of each tile buffer (phase parity)
 
@@ -417,56 +468,62 @@ gibbs_kernel(const GibbsArgs a) {
     for (int k = 0; k < D; ++k) {
       const int depth = sm[k].depth;
       if (step <= depth) {
-        int node = ind_s[k * kS + tid];
-        if (step == depth) { int lo, n; node_range(sm[k].N, step - 1, node, lo, n); node = lo; }
-        else node = 2 * node;
-        ind_s[k * kS + tid] = node;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          int node = ind_s[k * kS + col[r]];
+          if (step == depth) { int lo, n; node_range(sm[k].N, step - 1, node, lo, n); node = lo; }
+          else node = 2 * node;
+          ind_s[k * kS + col[r]] = (ind_t)node;
+        }
       }
     }
     for (int sweep = 0; sweep < sweeps; ++sweep) {
       for (int j = 0; j < D; ++j) {
-        const SMeta& dj = sm[j];
+        const SMeta<T>& dj = sm[j];
         const int lev = min(step, dj.depth);
         const bool leaf = lev == dj.depth;
         const int cnt = level_count(dj.N, dj.depth, lev);
-        const T* lrec = pool + dj.rec_off[lev];
+        const T* lrec = pool + dj.rec_off(lev);
         const int rec = leaf ? RECL : RECN;
         const int TN = leaf ? TN_LEAF : TN_NODE;
         const int ntiles = (cnt + TN - 1) / TN;
-        int CH = G;
+        int CH = kG;
         while (CH * kNCH < cnt) CH <<= 1;
 
-        ChainConst<T, DIM> cc;
+        ChainConst<T, DIM> cc[R];
+        PackedConst pc[R];
         bool nowrap = true;
-        {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
           T M[DIM], C[DIM];
-          if (!single) combine<T, DIM>(pool, sm, D, ind_s, tid, step, j, circ, M, C);
+          if (!single) combine<T, DIM>(pool, sm, D, ind_s, col[r], step, j, circ, M, C);
           // the wrap is a no-op for this chain if every stored coordinate of message j lies within pi of its mean
           if (circ != 0u && !single) {
 #pragma unroll
             for (int i = 0; i < DIM; ++i)
               if (circ >> i & 1) nowrap = nowrap && ((float)M[i] - 3.14159f <= dj.cmin[i]) && (dj.cmax[i] <= (float)M[i] + 3.14159f);
           }
-          cc.qs = single ? T(0) : HL;
-          cc.cmul = single ? T(0) : T(1);
+          cc[r].qs = single ? T(0) : HL;
+          cc[r].cmul = single ? T(0) : T(1);
 #pragma unroll
           for (int i = 0; i < DIM; ++i) {
             if (leaf) {
-              T h = single ? T(0) : HL / ((sizeof(T) == 4 ? (T)dj.bw2[i] : (T)dj.bw2d[i]) + C[i]);
+              T h = single ? T(0) : HL / (dj.bw2[i] + C[i]);
               T sh = tsqrt(h);
-              cc.a[i] = sh; cc.b[i] = single ? T(0) : M[i] * sh; cc.p[i] = T(CB2_TWO_PI) * sh;
+              cc[r].a[i] = sh; cc[r].b[i] = single ? T(0) : M[i] * sh; cc[r].p[i] = T(CB2_TWO_PI) * sh;
             } else {
-              cc.a[i] = single ? T(0) : M[i]; cc.b[i] = single ? T(1) : C[i]; cc.p[i] = T(0);
+              cc[r].a[i] = single ? T(0) : M[i]; cc[r].b[i] = single ? T(1) : C[i]; cc[r].p[i] = T(0);
             }
           }
+          pc[r] = make_packed<T, DIM>(cc[r], leaf);
         }
 
         // warp-uniform choice of the scoring loop (all chains of the warp must agree)
         const bool flat = circ == 0u || __all_sync(0xffffffffu, nowrap);
-        constexpr bool kPack = DIM == 6 && sizeof(T) == 4;  // packed-pair scoring (see PackedConst)
-        const PackedConst pc = make_packed<T, DIM>(cc, leaf);
         // ---- pass 1: chunk partial sums of exp2(e - m), m = running (lazily raised) reference maximum
-        T m = -INFINITY, csum = T(0);
+        T m[R], csum[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { m[r] = -INFINITY; csum[r] = T(0); }
         int cidx = 0;
         if (tid == 0) {
           uint32_t bytes = (uint32_t)(min(TN, cnt) * rec * (int)sizeof(T));
@@ -486,73 +543,86 @@ gibbs_kernel(const GibbsArgs a) {
           const int nt = min(TN, cnt - t * TN);
           const T* tb = reinterpret_cast<const T*>(smem_raw + b * TILE_BYTES);
           if (flat) {  // Euclidean arithmetic on every coordinate: same values as the wrapped form, fewer instructions
-            if (!leaf) tile_pass<T, DIM, 0, kPack>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
-            else if (!dj.uniform) tile_pass<T, DIM, 1, kPack>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
-            else tile_pass<T, DIM, 2, kPack>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
+            if (!leaf) tile_pass<T, DIM, 0, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
+            else if (!dj.uniform) tile_pass<T, DIM, 1, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
+            else tile_pass<T, DIM, 2, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
           } else {
-            if (!leaf) tile_pass<T, DIM, 0, false>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
-            else if (!dj.uniform) tile_pass<T, DIM, 1, false>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
-            else tile_pass<T, DIM, 2, false>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
+            if (!leaf) tile_pass<T, DIM, 0, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
+            else if (!dj.uniform) tile_pass<T, DIM, 1, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
+            else tile_pass<T, DIM, 2, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
           }
           __syncthreads();  // everyone is done with tile[b] before it is refilled
         }
-        if (cnt & (CH - 1)) { chunk[cidx * kS + tid] = csum; ++cidx; }
+        if (cnt & (CH - 1)) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) chunk[cidx * kS + col[r]] = csum[r];
+          ++cidx;
+        }
         const int nch = cidx;
 
         // ---- inverse CDF: pick the chunk, then re-score only that chunk
-        T tot = T(0);
-        for (int c = 0; c < nch; ++c) tot += chunk[c * kS + tid];
-        uint32_t rnd[4];
-        const uint32_t draw = (uint32_t)(((step - 1) * sweeps + sweep) * D + j);
-        philox4x32_10(sid, draw, pstream, 0u, a.k0, a.k1, rnd);
-        const T tgt = u01<T>(rnd[0], rnd[1]) * tot;
-        T cum = T(0);
-        int sel = nch - 1;
-        for (int c = 0; c < nch; ++c) {
-          T v = chunk[c * kS + tid];
-          if (cum + v >= tgt) { sel = c; break; }
-          cum += v;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          T tot = T(0);
+          for (int c = 0; c < nch; ++c) tot += chunk[c * kS + col[r]];
+          uint32_t rnd[4];
+          const uint32_t draw = (uint32_t)(((step - 1) * sweeps + sweep) * D + j);
+          philox4x32_10(sid[r], draw, pstream, 0u, a.k0, a.k1, rnd);
+          const T tgt = u01<T>(rnd[0], rnd[1]) * tot;
+          T cum = T(0);
+          int sel = nch - 1;
+          for (int c = 0; c < nch; ++c) {
+            T v = chunk[c * kS + col[r]];
+            if (cum + v >= tgt) { sel = c; break; }
+            cum += v;
+          }
+          const int z0 = sel * CH, z1 = min(cnt, z0 + CH);
+          // pass 2 must reproduce the scores of pass 1 bit for bit, so it takes the same (packed or wrapped) scorer
+          int pick;
+          if (flat) {
+            pick = !leaf ? chunk_pick<T, DIM, 0, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
+                         : (!dj.uniform ? chunk_pick<T, DIM, 1, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
+                                        : chunk_pick<T, DIM, 2, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt));
+          } else {
+            pick = !leaf ? chunk_pick<T, DIM, 0, false>(lrec, z0, z1, cc[r], pc[r], circ, m[r], cum, tgt)
+                         : (!dj.uniform ? chunk_pick<T, DIM, 1, false>(lrec, z0, z1, cc[r], pc[r], circ, m[r], cum, tgt)
+                                        : chunk_pick<T, DIM, 2, false>(lrec, z0, z1, cc[r], pc[r], circ, m[r], cum, tgt));
+          }
+          if (active[r]) ind_s[j * kS + col[r]] = (ind_t)pick;
         }
-        const int z0 = sel * CH, z1 = min(cnt, z0 + CH);
-        // pass 2 must reproduce the scores of pass 1 bit for bit, so it takes the same (packed or wrapped) scorer
-        int pick;
-        if (flat) {
-          pick = !leaf ? chunk_pick<T, DIM, 0, kPack>(lrec, z0, z1, cc, pc, 0u, m, cum, tgt)
-                       : (!dj.uniform ? chunk_pick<T, DIM, 1, kPack>(lrec, z0, z1, cc, pc, 0u, m, cum, tgt)
-                                      : chunk_pick<T, DIM, 2, kPack>(lrec, z0, z1, cc, pc, 0u, m, cum, tgt));
-        } else {
-          pick = !leaf ? chunk_pick<T, DIM, 0, false>(lrec, z0, z1, cc, pc, circ, m, cum, tgt)
-                       : (!dj.uniform ? chunk_pick<T, DIM, 1, false>(lrec, z0, z1, cc, pc, circ, m, cum, tgt)
-                                      : chunk_pick<T, DIM, 2, false>(lrec, z0, z1, cc, pc, circ, m, cum, tgt));
-        }
-        if (active) ind_s[j * kS + tid] = pick;
       }
     }
   }
 
-  if (!active) return;
-  // final point: product of all selected kernels plus one Gaussian draw
-  T M[DIM], C[DIM];
-  combine<T, DIM>(pool, sm, D, ind_s, tid, L, -1, circ, M, C);
-  uint32_t rnd[4];
-  double* out = prp->out;
+  // final point: product of all selected kernels plus one Gaussian draw; Euclidean coordinates were stored relative to
+  // the centre of the product's first message
+  const double* cen0 = a.metas[prp->dens[0]].center;
 #pragma unroll
-  for (int i = 0; i < DIM; ++i) {
-    if ((i & 1) == 0) philox4x32_10(sid, (uint32_t)(i >> 1), pstream, 1u, a.k0, a.k1, rnd);
-    double u1 = (double)u01<T>(rnd[0], rnd[1]), u2 = (double)u01<T>(rnd[2], rnd[3]);
-    double r = sqrt(-2.0 * log(u1)), sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
-    double v = (double)M[i] + sm[0].cen[i] + sqrt((double)C[i]) * ((i & 1) ? r * sn : r * cs);
-    if (circ >> i & 1) v = wrap_pi(v);
-    out[(size_t)s * DIM + i] = v;
-  }
-  int* labels = prp->labels;
-  if (labels) {
-    for (int k = 0; k < D; ++k) labels[(size_t)s * D + k] = a.int_pool[sm[k].perm_off + ind_s[k * kS + tid]];
+  for (int r = 0; r < R; ++r) {
+    if (!active[r]) continue;
+    const int s = wk.s0 + col[r];
+    T M[DIM], C[DIM];
+    combine<T, DIM>(pool, sm, D, ind_s, col[r], L, -1, circ, M, C);
+    uint32_t rnd[4];
+    double* out = prp->out;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      if ((i & 1) == 0) philox4x32_10(sid[r], (uint32_t)(i >> 1), pstream, 1u, a.k0, a.k1, rnd);
+      double u1 = (double)u01<T>(rnd[0], rnd[1]), u2 = (double)u01<T>(rnd[2], rnd[3]);
+      double rr = sqrt(-2.0 * log(u1)), sn, cs;
+      sincospi(2.0 * u2, &sn, &cs);
+      double v = (double)M[i] + ((circ >> i & 1) ? 0.0 : cen0[i]) + sqrt((double)C[i]) * ((i & 1) ? rr * sn : rr * cs);
+      if (circ >> i & 1) v = wrap_pi(v);
+      out[(size_t)s * DIM + i] = v;
+    }
+    int* labels = prp->labels;
+    if (labels) {
+      for (int k = 0; k < D; ++k) labels[(size_t)s * D + k] = a.int_pool[sm[k].perm_off + ind_s[k * kS + col[r]]];
+    }
   }
 }
 
-template <typename T> size_t gibbs_smem_bytes() {
-  return 2 * (size_t)kTileBytesF32 * (sizeof(T) / 4) + sizeof(T) * kNCH * kS + sizeof(int) * CB2_MAX_DENS * kS + 16 +
-         sizeof(SMeta) * CB2_MAX_DENS + 64;
+template <typename T, int DIM> size_t gibbs_smem_bytes() {
+  return 2 * (size_t)gibbs_tile_bytes<T, DIM>() + sizeof(T) * kNCH * kS + sizeof(ind_t) * CB2_MAX_DENS * kS + 16 +
+         sizeof(SMeta<T>) * CB2_MAX_DENS + 64;
 }

@@ -430,10 +430,12 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 
 template <typename T, int DIM, uint32_t CIRC>
 int launch_gibbs_inst(cb2_ctx* ctx, int nwork, const GibbsArgs& a) {
-  size_t smem = gibbs_smem_bytes<T>();
+  size_t smem = gibbs_smem_bytes<T, DIM>();
   cudaError_t e = cudaFuncSetAttribute(gibbs_kernel<T, DIM, CIRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gibbs_kernel<T, DIM, CIRC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "gibbs smem attribute: %s", cudaGetErrorString(e));
-  gibbs_kernel<T, DIM, CIRC><<<nwork, kS, smem, ctx->stream>>>(a);
+  gibbs_kernel<T, DIM, CIRC><<<nwork, kS / ChainsPerThread<T, DIM>::value, smem, ctx->stream>>>(a);
   CB2_CHECK_LAUNCH(ctx, "gibbs_kernel");
   return CB2_OK;
 }
