@@ -594,8 +594,8 @@ gibbs_kernel(const GibbsArgs a) {
     }
   }
 
-  // final point: product of all selected kernels plus one Gaussian draw; Euclidean coordinates were stored relative to
-  // the centre of the product's first message
+  // final point: product of all selected kernels plus one Gaussian draw; coordinates were stored relative to the centre of
+  // the product's first message (tree_build_kernel: Euclidean always, circular in FP32 mode)
   const double* cen0 = a.metas[prp->dens[0]].center;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -611,7 +611,7 @@ gibbs_kernel(const GibbsArgs a) {
       double u1 = (double)u01<T>(rnd[0], rnd[1]), u2 = (double)u01<T>(rnd[2], rnd[3]);
       double rr = sqrt(-2.0 * log(u1)), sn, cs;
       sincospi(2.0 * u2, &sn, &cs);
-      double v = (double)M[i] + ((circ >> i & 1) ? 0.0 : cen0[i]) + sqrt((double)C[i]) * ((i & 1) ? rr * sn : rr * cs);
+      double v = (double)M[i] + (((circ >> i & 1) && sizeof(T) == 8) ? 0.0 : cen0[i]) + sqrt((double)C[i]) * ((i & 1) ? rr * sn : rr * cs);
       if (circ >> i & 1) v = wrap_pi(v);
       out[(size_t)s * DIM + i] = v;
     }

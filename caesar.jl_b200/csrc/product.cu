@@ -281,7 +281,11 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
   for (int i = 0; i < CB2_MAX_DIM; ++i) { cmn[i] = 1e300; cmx[i] = -1e300; }
   double cen[CB2_MAX_DIM];
 #pragma unroll
-  for (int i = 0; i < CB2_MAX_DIM; ++i) cen[i] = (i < d && !(circ_mask >> i & 1)) ? m.center[i] : 0.0;
+  // Euclidean coordinates are stored relative to the product's centre (translation invariance).  In FP32 mode the circular
+  // coordinates are rotated the same way (rotation invariance on the circle): a belief narrower than pi then never straddles
+  // the +-pi cut of the stored values and the Gibbs kernel can take its wrap-free loops.  FP64 (validation) mode keeps the
+  // unrotated angles so that it follows the oracle operation for operation.
+  for (int i = 0; i < CB2_MAX_DIM; ++i) cen[i] = (i < d && (sizeof(T) == 4 || !(circ_mask >> i & 1))) ? m.center[i] : 0.0;
   {
     double* sl = sbase + (size_t)lvl_off(depth) * nd;
     T* rec = node_pool + m.rec_off[depth];
@@ -294,7 +298,7 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
         double v = m.pts[(size_t)idx * d + i];
         sl[(size_t)p * nd + i] = v;
         sl[(size_t)p * nd + d + i] = m.bw[i] * m.bw[i];
-        const double rv = (circ_mask >> i & 1) ? wrap_pi(v) : v - cen[i];
+        const double rv = (circ_mask >> i & 1) ? wrap_pi(v - cen[i]) : v - cen[i];
         rec[(size_t)p * RECL + i] = (T)rv;
         if (circ_mask >> i & 1) { cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv); }
       }
@@ -337,7 +341,7 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
         v /= ws;
         sl[(size_t)k * nd + i] = mm;
         sl[(size_t)k * nd + d + i] = v;
-        const double rv = (circ_mask >> i & 1) ? wrap_pi(mm) : mm - cen[i];
+        const double rv = (circ_mask >> i & 1) ? wrap_pi(mm - cen[i]) : mm - cen[i];
         rec[(size_t)k * RECN + i] = (T)rv;
         if (circ_mask >> i & 1) { cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv); }
         rec[(size_t)k * RECN + d + i] = (T)v;
