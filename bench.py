@@ -273,11 +273,11 @@ def main():
                         "evals_per_s": evals / (gibbs_ms * 1e-3) if gibbs_ms > 0 else None,
                         "sfu_frac": evals / (gibbs_ms * 1e-3) / sfu_peak if gibbs_ms > 0 else None},
         "launch_ms": gibbs_ms, "share_of_step": gibbs_ms * args.steps / ms_total if ms_total else None,
-        "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}, "traffic": 112.5e6 if args.vars_per_gpu == VARS_PER_GPU else None,
+        "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}, "traffic": 112.9e6 if args.vars_per_gpu == VARS_PER_GPU else None,
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one gibbs_kernel launch, ncu --set full (profiles/r01_ncu_full_summary.csv); "
                         "bytes: the kernel is compute-bound, its algorithmic HBM traffic is the 100 MB node pool read once",
-        "ncu": {"issue_active_pct": 72.1, "pipe_fma_pct": 50.8, "pipe_xu_pct": 42.3, "warp_instructions": 2.76e10,
-                "source": "profiles/r01_ncu_full_summary.csv (r01_gibbs_v5)"},
+        "ncu": {"issue_active_pct": 60.4, "pipe_fma_cycles_pct": 58.6, "pipe_xu_pct": 46.1, "lsu_wavefronts_pct": 51.0,
+                "warp_instructions": 2.12e10, "source": "profiles/r01_ncu_full_summary.csv (r01_gibbs_v6)"},
     }
 
     cpu = None
