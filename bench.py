@@ -13,7 +13,9 @@ leave-one-out bandwidth of every result (what upstream manifoldProduct -> manikd
           workload (the Julia reference cannot run here: no Julia, and the arithmetic lives in packages absent
           from /root/reference -- see DESIGN.md).
 
-Multi-GPU: variables are independent -> sharded across ranks, no data-path collective ("weak": 32 variables / GPU).
+N = 1 runs the configuration the metric is quoted on: all 256 variables of C5 on one GPU (it fits: 0.4 GB of messages,
+0.8 GB of level records).  Multi-GPU: variables are independent -> every rank runs its own 256 variables, no data-path
+collective ("weak": per-GPU work fixed; `--vars-per-gpu 32` gives BASELINE's literal "256 variables across 8 GPUs" split).
 """
 import argparse
 import json
@@ -30,7 +32,8 @@ sys.path.insert(0, ROOT)
 
 D_MSG, N_KER, DIM, N_OUT = 8, 4096, 6, 4096
 CIRC = (0, 0, 0, 1, 1, 1)
-VARS_PER_GPU = 32
+VARS_PER_GPU = 256
+TRAFFIC_NCU = {32: 112.9e6}  # dram bytes of one gibbs_kernel launch, ncu --set full, by variables per launch
 FP32_FLOPS_PER_EVAL = 4 * DIM + 3  # product kernel-eval ~ (4d+3) flops + 1 SFU
 
 
@@ -123,7 +126,8 @@ def main():
     config = {"workload": f"C5 SE(3) belief-product stress: {args.vars_per_gpu} variables/GPU x D={D_MSG} messages x N={N_KER} kernels, "
                           f"d={DIM} (3 Euclidean + 3 circular), N_out={N_OUT}, Niter=1, fresh LOO bandwidth per result",
               "vars_per_gpu": args.vars_per_gpu, "parallelism": f"variables sharded over {world} GPU(s), no collective",
-              "l2": "working set (inputs 50 MB + level records 100 MB per step) exceeds L2; 256 MiB flush write between timed steps"}
+              "l2": f"working set (inputs {args.vars_per_gpu * D_MSG * N_KER * DIM * 8 / 1e6:.0f} MB + level records "
+                    f"{args.vars_per_gpu * 3.15:.0f} MB per step) exceeds L2; 256 MiB flush write between timed steps"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -218,7 +222,8 @@ def main():
     pin_pts = [[torch.from_numpy(p).pin_memory() for p, _ in var] for var in variables]
     pin_out = [torch.empty((N_OUT, DIM), dtype=torch.float64).pin_memory() for _ in range(V)]
     pin_lab = [torch.empty((N_OUT, D_MSG), dtype=torch.int32).pin_memory() for _ in range(V)]
-    bw_out = [np.zeros(DIM) for _ in range(V)]
+    pin_bw = [torch.zeros(DIM, dtype=torch.float64).pin_memory() for _ in range(V)]
+    bw_out = [t.numpy() for t in pin_bw]
     hdescs = (cb.ProductDesc * V)()
     for v in range(V):
         arr = (cb.Density * D_MSG)(*[cb.Density(N_KER, pin_pts[v][j].data_ptr(), variables[v][j][1].ctypes.data, None) for j in range(D_MSG)])
@@ -273,7 +278,7 @@ def main():
                         "evals_per_s": evals / (gibbs_ms * 1e-3) if gibbs_ms > 0 else None,
                         "sfu_frac": evals / (gibbs_ms * 1e-3) / sfu_peak if gibbs_ms > 0 else None},
         "launch_ms": gibbs_ms, "share_of_step": gibbs_ms * args.steps / ms_total if ms_total else None,
-        "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}, "traffic": 112.9e6 if args.vars_per_gpu == VARS_PER_GPU else None,
+        "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}, "traffic": TRAFFIC_NCU.get(args.vars_per_gpu),
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one gibbs_kernel launch, ncu --set full (profiles/r01_ncu_full_summary.csv); "
                         "bytes: the kernel is compute-bound, its algorithmic HBM traffic is the 100 MB node pool read once",
         "ncu": {"issue_active_pct": 60.4, "pipe_fma_cycles_pct": 58.6, "pipe_xu_pct": 46.1, "lsu_wavefronts_pct": 51.0,

@@ -214,6 +214,46 @@ def test_product_batch_is_independent_of_batching_and_sharding(cb, ctx):
         assert np.array_equal(tail[1], solo[1][64:]) and np.array_equal(tail[0].pts, solo[0].pts[64:])
 
 
+def test_product_batch_from_pinned_host_arrays_uses_the_single_launch_copies(cb, ctx, monkeypatch):
+    """Batches of >= 64 arrays in pinned (mapped) host memory are gathered / scattered by one kernel per direction that reads and
+    writes the caller's arrays in place; results must equal the per-array copy path bit for bit.  Nout * D is odd for the labels
+    (4-byte tail of the 8-byte-word copy) and the bandwidth outputs are pageable (mixed batch)."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(12)
+    B, D, N, Nout, d = 24, 3, 4000, 33, 3  # 6.9 MB of inputs: above the packed-staging limit of small batches
+    L = cb._capi.lib()
+    msgs = [[_messages(rng, 1, N, d, 0.5)[0] for _ in range(D)] for _ in range(B)]
+    pin = [[torch.from_numpy(np.ascontiguousarray(m[0])).pin_memory() for m in g] for g in msgs]
+    circ = np.array([0, 0, 1], dtype=np.uint8)
+
+    def run():
+        out = [torch.zeros((Nout, d), dtype=torch.float64).pin_memory() for _ in range(B)]
+        lab = [torch.zeros((Nout, D), dtype=torch.int32).pin_memory() for _ in range(B)]
+        bw = [np.zeros(d) for _ in range(B)]
+        keep, descs = [], (cb.ProductDesc * B)()
+        for b in range(B):
+            arr = (cb.Density * D)(*[cb.Density(N, pin[b][j].data_ptr(), msgs[b][j][1].ctypes.data, None) for j in range(D)])
+            keep.append(arr)
+            descs[b].dens, descs[b].D, descs[b].Nout, descs[b].niter, descs[b].stream = arr, D, Nout, 1, b
+            descs[b].pts_out, descs[b].labels_out, descs[b].bw_out = out[b].data_ptr(), lab[b].data_ptr(), bw[b].ctypes.data
+        ctx.check(L.cb2_product_batch(ctx._h, descs, B, circ.ctypes.data_as(C.c_void_p), d, 77))
+        return [o.numpy().copy() for o in out], [l.numpy().copy() for l in lab], [x.copy() for x in bw]
+
+    launches0 = L.cb2_kernel_launches(ctx._h)
+    direct = run()
+    n_direct = L.cb2_kernel_launches(ctx._h) - launches0
+    monkeypatch.setenv("CB2_NO_DIRECT", "1")
+    launches0 = L.cb2_kernel_launches(ctx._h)
+    plain = run()
+    n_plain = L.cb2_kernel_launches(ctx._h) - launches0
+    assert n_direct == n_plain + 2  # one gather and one scatter launch
+    for a, b in zip(direct, plain):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert all((l >= 0).all() and (l < N + 14).all() for l in direct[1]) and all((x > 0).all() for x in direct[2])
+
+
 def test_manifold_product_api_behaviour(cb, ctx, tut3):
     a, b, c = (cb.MKD("Point2", *tut3[k]) for k in ("l3_2", "l3_3", "l3_4"))
     p = cb.manifoldProduct([a, b, c], seed=1, ctx=ctx)
