@@ -108,6 +108,23 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 __device__ __forceinline__ double fast_exp2(double x) { return exp2(x); }
+// exp2 of a non-positive argument on the FMA and ALU pipes instead of the XU pipe (16 MUFU per clock and SM is what bounds the
+// pair kernels: mixing one software evaluation into every four takes a quarter of the load off that pipe).  Round to nearest
+// integer with the 1.5 * 2^23 trick, degree-5 polynomial for 2^f on [-0.5, 0.5] (max relative error 2.4e-7, the same two ulp
+// as ex2.approx), exponent added in integer arithmetic.  Arguments below -125 return ~2e-38 instead of a flushed zero.
+__device__ __forceinline__ float soft_exp2(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = 0.0013390863f;
+  p = fmaf(p, f, 0.009676032f);
+  p = fmaf(p, f, 0.05550357f);
+  p = fmaf(p, f, 0.24022107f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0000001f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+__device__ __forceinline__ double soft_exp2(double x) { return exp2(x); }
 __device__ __forceinline__ float fast_log2(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

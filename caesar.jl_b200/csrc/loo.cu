@@ -15,6 +15,7 @@
 //                          the objective value and advances that problem's bracket.
 // The bracket and the update rule follow Ihler's `ksize(..., 'lcv')` / `golden` as restated in oracle/cb2_oracle.c.
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -150,80 +151,92 @@ loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict
   const double row_hi = xs[rend - 1];
   const double zero_r = ZeroRadius<T>::value / sc;
   T* colpart = colpart_all + pr.cp_off + (size_t)cm.y * pr.nstride;  // this row block's slice: [nstride]
-  for (int cs = rbase; cs < N; cs += kCT) {
-    const int cend = min(cs + kCT, N);
-    const bool diag = cs == rbase;
-    if (!circ && !diag && xs[cs] - row_hi > zero_r) {
-      // sorted data: a tile entirely beyond the flush-to-zero radius contributes exactly 0 (and so do all later ones)
-      for (int j = tid; j < cend - cs; j += kThreads) colpart[cs + j] = T(0);
-      continue;
-    }
-    __syncthreads();
-    for (int j = tid; j < kCT; j += kThreads) {
-      int col = cs + j;
-      if (col < N) { double v = xs[col]; sx[j] = (T)(((circ ? wrap_pi(v) : v) - x_mid) * sc); }
-      else sx[j] = T(1e18);
-    }
-    __syncthreads();
-    const int jn = cend - cs;
-    if (diag) {  // all ordered pairs inside the block, self term excluded
-      // a warp's rows are tid_base + lane + 256 r: its self terms sit in the 32-column groups with
-      // (j0 - tid_base) % 256 == 0 only; every other group runs without the per-pair predicate (warp-uniform branch)
-      const int tid_base = tid & ~31;
-      for (int j0 = 0; j0 < jn; j0 += 32) {
-        const int je = min(j0 + 32, jn);
-        if (((j0 - tid_base) & (kThreads - 1)) == 0) {
-          for (int j = j0; j < je; ++j) {
-            const T q = sx[j];
-#pragma unroll
-            for (int r = 0; r < kRI; ++r) {
-              T df = xi[r] - q;
-              if (circ) { T ad = fabs(df); df = fmin(ad, period - ad); }
-              T kv = fast_exp2(-(df * df));
-              acc[r] += (cs + j == rowi[r]) ? T(0) : kv;
-            }
-          }
-        } else {
-#pragma unroll 8
-          for (int j = j0; j < je; ++j) {
-            const T q = sx[j];
-#pragma unroll
-            for (int r = 0; r < kRI; ++r) {
-              T df = xi[r] - q;
-              if (circ) { T ad = fabs(df); df = fmin(ad, period - ad); }
-              acc[r] += fast_exp2(-(df * df));
-            }
-          }
-        }
-      }
-    } else {  // tile above the diagonal: the row block is complete (1024 valid rows); columns may be ragged
-      for (int j0 = 0; j0 < kCT; j0 += 32) {
-        T v[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const T q = sx[j0 + c];
-          T kv[kRI];
-#pragma unroll
-          for (int r = 0; r < kRI; ++r) {
-            T df = xi[r] - q;
-            if (circ) { T ad = fabs(df); df = fmin(ad, period - ad); }
-            kv[r] = fast_exp2(-(df * df));
-            if (circ && j0 + c >= jn) kv[r] = T(0);  // padding column (the wrap would fold the sentinel back)
-            acc[r] += kv[r];
-          }
-          v[c] = (kv[0] + kv[1]) + (kv[2] + kv[3]);
-        }
-        colacc[warp * kCT + j0 + lane] = lane_transpose_sum(v, lane);
+  // the pair loops are compiled once per topology: the wrap of circular coordinates costs four instructions per pair, which the
+  // Euclidean coordinates must not pay (the kernel sits at the issue limit next to the XU limit); uniform branch per CTA
+  auto sweep = [&](auto topo) {
+    constexpr bool CIRC = decltype(topo)::value;
+    for (int cs = rbase; cs < N; cs += kCT) {
+      const int cend = min(cs + kCT, N);
+      const bool diag = cs == rbase;
+      if (!CIRC && !diag && xs[cs] - row_hi > zero_r) {
+        // sorted data: a tile entirely beyond the flush-to-zero radius contributes exactly 0 (and so do all later ones)
+        for (int j = tid; j < cend - cs; j += kThreads) colpart[cs + j] = T(0);
+        continue;
       }
       __syncthreads();
-      for (int j = tid; j < jn; j += kThreads) {
-        T t = T(0);
+      for (int j = tid; j < kCT; j += kThreads) {
+        int col = cs + j;
+        if (col < N) { double v = xs[col]; sx[j] = (T)(((CIRC ? wrap_pi(v) : v) - x_mid) * sc); }
+        else sx[j] = T(1e18);
+      }
+      __syncthreads();
+      const int jn = cend - cs;
+      if (diag) {  // all ordered pairs inside the block, self term excluded
+        // a warp's rows are tid_base + lane + 256 r: its self terms sit in the 32-column groups with
+        // (j0 - tid_base) % 256 == 0 only; every other group runs without the per-pair predicate (warp-uniform branch)
+        const int tid_base = tid & ~31;
+        for (int j0 = 0; j0 < jn; j0 += 32) {
+          const int je = min(j0 + 32, jn);
+          if (((j0 - tid_base) & (kThreads - 1)) == 0) {
+            for (int j = j0; j < je; ++j) {
+              const T q = sx[j];
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) t += colacc[w * kCT + j];
-        colpart[cs + j] = t;
+              for (int r = 0; r < kRI; ++r) {
+                T df = xi[r] - q;
+                if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
+                T kv = fast_exp2(-(df * df));
+                acc[r] += (cs + j == rowi[r]) ? T(0) : kv;
+              }
+            }
+          } else {
+#pragma unroll 8
+            for (int j = j0; j < je; ++j) {
+              const T q = sx[j];
+#pragma unroll
+              for (int r = 0; r < kRI; ++r) {
+                T df = xi[r] - q;
+                if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
+                acc[r] += fast_exp2(-(df * df));
+              }
+            }
+          }
+        }
+      } else {  // tile above the diagonal: the row block is complete (1024 valid rows); columns may be ragged
+        // only the last 32-column group of a ragged tile needs the padding mask (circular case: the wrap would fold the
+        // sentinel back into range); every other group runs without it
+        auto colgroup = [&](int j0, auto ragged) {
+          constexpr bool RAGGED = decltype(ragged)::value;
+          T v[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const T q = sx[j0 + c];
+            T kv[kRI];
+#pragma unroll
+            for (int r = 0; r < kRI; ++r) {
+              T df = xi[r] - q;
+              if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
+              kv[r] = fast_exp2(-(df * df));
+              if (CIRC && RAGGED && j0 + c >= jn) kv[r] = T(0);
+              acc[r] += kv[r];
+            }
+            v[c] = (kv[0] + kv[1]) + (kv[2] + kv[3]);
+          }
+          colacc[warp * kCT + j0 + lane] = lane_transpose_sum(v, lane);
+        };
+        for (int j0 = 0; j0 < kCT; j0 += 32) {
+          if (CIRC && j0 + 32 > jn) colgroup(j0, std::true_type{}); else colgroup(j0, std::false_type{});
+        }
+        __syncthreads();
+        for (int j = tid; j < jn; j += kThreads) {
+          T t = T(0);
+#pragma unroll
+          for (int w = 0; w < kThreads / 32; ++w) t += colacc[w * kCT + j];
+          colpart[cs + j] = t;
+        }
       }
     }
-  }
+  };
+  if (circ) sweep(std::true_type{}); else sweep(std::false_type{});
   T* rowsum = rowsum_all + pr.xs_off;
 #pragma unroll
   for (int r = 0; r < kRI; ++r)
