@@ -14,6 +14,7 @@
 
 #define CB2_LOG2E 1.4426950408889634074
 #define CB2_TWO_PI 6.283185307179586476925286766559
+#define CB2_PI 3.14159265358979323846264338327950288
 
 struct cb2_arena {  // grow-only device scratch; reset at the start of each public call
   char* base = nullptr;
