@@ -21,6 +21,10 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kRI = 4;
+#ifndef CB2_LOO_SOFT_EVERY
+#define CB2_LOO_SOFT_EVERY 8
+#endif
+constexpr int kSoftEvery = CB2_LOO_SOFT_EVERY;  // multiple of kRI
 constexpr int kCT = 1024;
 constexpr int kSortThreads = 1024;
 constexpr double kTol = 1e-2;
@@ -225,7 +229,8 @@ loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict
               for (int r = 0; r < kRI; ++r) {
                 T df = xi[r] - q;
                 if (WRAP) { T ad = fabs(df); df = fmin(ad, period - ad); }
-                kv[r] = fast_exp2(-(df * df));
+                // XU relief: one evaluation in kSoftEvery runs on the FMA/ALU pipes (soft_exp2) where the issue rate leaves room
+                kv[r] = (!WRAP && r == kRI - 1 && (c % (kSoftEvery / kRI)) == 0) ? soft_exp2(-(df * df)) : fast_exp2(-(df * df));
                 if (WRAP && RAGGED && j0 + c >= jn) kv[r] = T(0);
                 acc[r] += kv[r];
               }
