@@ -147,7 +147,8 @@ __device__ __forceinline__ float rint_t(float x) { return rintf(x); }
 __device__ __forceinline__ double rint_t(double x) { return rint(x); }
 __device__ __forceinline__ float atan2_t(float y, float x) { return atan2f(y, x); }
 __device__ __forceinline__ double atan2_t(double y, double x) { return atan2(y, x); }
-__device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
+// FP32: MUFU.SIN / MUFU.COS (arguments are stored angles in [-pi, pi]: absolute error ~ 5e-7, no range-reduction slow path)
+__device__ __forceinline__ void sincos_t(float x, float* s, float* c) { __sincosf(x, s, c); }
 __device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
 
 template <typename T> __device__ __forceinline__ T warp_sum(T v) {

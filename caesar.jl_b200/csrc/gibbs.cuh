@@ -385,7 +385,7 @@ __device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta<
     }
 #pragma unroll
     for (int i = 0; i < DIM; ++i) {
-      T l = T(1) / var[i];
+      T l = fast_rcp(var[i]);
       lam[i] += l;
       if (circ >> i & 1) {
         T sn, cs;
@@ -398,10 +398,16 @@ __device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta<
   }
 #pragma unroll
   for (int i = 0; i < DIM; ++i) {
-    C[i] = T(1) / lam[i];
+    C[i] = fast_rcp(lam[i]);
     M[i] = (circ >> i & 1) ? atan2_t(s1[i], s2[i]) : s1[i] * C[i];
   }
 }
+
+#ifdef CB2_GIBBS_PROF
+#define GIBBS_T(slot) do { long long t_ = clock64(); gprof[slot] += t_ - glast; glast = t_; } while (0)
+#else
+#define GIBBS_T(slot) do { } while (0)
+#endif
 
 template <typename T, int DIM, uint32_t CIRC>
 __global__ void __launch_bounds__(kS / ChainsPerThread<T, DIM>::value, ChainsPerThread<T, DIM>::value == 2 ? 7 : (sizeof(T) == 4 ? CB2_GIBBS_CTAS : 4))
@@ -462,6 +468,9 @@ gibbs_kernel(const GibbsArgs a) {
     for (int r = 0; r < R; ++r) ind_s[k * kS + col[r]] = 0;
   __syncthreads();
   uint32_t use0 = 0, use1 = 0;  // completed uses of each tile buffer (phase parity)
+#ifdef CB2_GIBBS_PROF
+  long long gprof[6] = {0, 0, 0, 0, 0, 0}, glast = clock64();
+#endif
 
   for (int step = 1; step <= L; ++step) {
     // levelDown: a leaf stays itself, otherwise move to the first child
@@ -490,6 +499,7 @@ gibbs_kernel(const GibbsArgs a) {
         int CH = kG;
         while (CH * kNCH < cnt) CH <<= 1;
 
+        GIBBS_T(0);
         ChainConst<T, DIM> cc[R];
         PackedConst pc[R];
         bool nowrap = true;
@@ -518,6 +528,7 @@ gibbs_kernel(const GibbsArgs a) {
           pc[r] = make_packed<T, DIM>(cc[r], leaf);
         }
 
+        GIBBS_T(1);
         // warp-uniform choice of the scoring loop (all chains of the warp must agree)
         const bool flat = circ == 0u || __all_sync(0xffffffffu, nowrap);
         // ---- pass 1: chunk partial sums of exp2(e - m), m = running (lazily raised) reference maximum
@@ -559,6 +570,7 @@ gibbs_kernel(const GibbsArgs a) {
           ++cidx;
         }
         const int nch = cidx;
+        GIBBS_T(leaf ? 3 : 2);
 
         // ---- inverse CDF: pick the chunk, then re-score only that chunk
 #pragma unroll
@@ -577,6 +589,7 @@ gibbs_kernel(const GibbsArgs a) {
             cum += v;
           }
           const int z0 = sel * CH, z1 = min(cnt, z0 + CH);
+          GIBBS_T(4);
           // pass 2 must reproduce the scores of pass 1 bit for bit, so it takes the same (packed or wrapped) scorer
           int pick;
           if (flat) {
@@ -589,11 +602,16 @@ gibbs_kernel(const GibbsArgs a) {
                                         : chunk_pick<T, DIM, 2, false>(lrec, z0, z1, cc[r], pc[r], circ, m[r], cum, tgt));
           }
           if (active[r]) ind_s[j * kS + col[r]] = (ind_t)pick;
+          GIBBS_T(5);
         }
       }
     }
   }
 
+#ifdef CB2_GIBBS_PROF
+  if (blockIdx.x == 0 && (tid & 31) == 0)
+    printf("gibbs prof warp %d (clk): other %lld combine %lld pass1-coarse %lld pass1-leaf %lld cdf %lld pass2 %lld\n", tid >> 5, gprof[0], gprof[1], gprof[2], gprof[3], gprof[4], gprof[5]);
+#endif
   // final point: product of all selected kernels plus one Gaussian draw; coordinates were stored relative to the centre of
   // the product's first message (tree_build_kernel: Euclidean always, circular in FP32 mode)
   const double* cen0 = a.metas[prp->dens[0]].center;
