@@ -202,14 +202,14 @@ __device__ __forceinline__ T score_node(const T (&r)[RECN], const ChainConst<T, 
 template <bool UW>
 __device__ __forceinline__ float score_leaf_p(const f32x2 (&q)[4], const PackedConst& c, float nm) {
   const f32x2 d0 = fma2(q[0], c.a[0], c.b[0]), d1 = fma2(q[1], c.a[1], c.b[1]), d2 = fma2(q[2], c.a[2], c.b[2]);
-  f32x2 s = mul2(d0, d0);
+  // the reference -m rides in the first lane of the accumulator: s = (sum_even - nm, sum_odd), e = -s.x - s.y is one FADD
+  f32x2 s = fma2(d0, d0, pack2(-nm, 0.0f));
   s = fma2(d1, d1, s);
   s = fma2(d2, d2, s);
   float sx, sy, lw, pad;
   unpack2(s, sx, sy);
   unpack2(q[3], lw, pad);
-  const float e = UW ? nm : lw + nm;
-  return (e - sx) - sy;
+  return UW ? -sx - sy : (lw - sx) - sy;
 }
 
 // packed coarse-node score: the two common-denominator groups are the even and the odd coordinates
@@ -334,19 +334,21 @@ __device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, in
   constexpr int REC = RecLen<DIM, MODE>::value;
   int pick = -1, lastpos = z0;
   const T nm = -m;
-  // four candidates per round: their (divergent, L2-resident) record loads are in flight together; the cumulative
-  // sum is still taken strictly in candidate order, so the draw is the same as a one-by-one scan
-  for (int z = z0; z < z1 && pick < 0; z += 4) {
-    T p[4];
+  // PR candidates per round: their (divergent, L2-resident) record loads are in flight together (8 per round measured no
+  // faster: other warps cover the latency); the cumulative sum is still taken strictly in candidate order, so the draw is the same as a
+  // one-by-one scan
+  constexpr int PR = 4;
+  for (int z = z0; z < z1 && pick < 0; z += PR) {
+    T p[PR];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < PR; ++g) {
       const int zz = min(z + g, z1 - 1);
       RecR<T, REC, PACK> rec;
       load_recr<false>(lrec + (size_t)zz * REC, rec);
       p[g] = fast_exp2(score_regs<T, DIM, MODE, PACK>(rec, cc, pc, circ, nm));
     }
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < PR; ++g) {
       if (pick < 0 && z + g < z1) {
         cum += p[g];
         if (p[g] > T(0)) lastpos = z + g;
