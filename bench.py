@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 D_MSG, N_KER, DIM, N_OUT = 8, 4096, 6, 4096
 CIRC = (0, 0, 0, 1, 1, 1)
 VARS_PER_GPU = 256
-TRAFFIC_NCU = {32: 112.9e6}  # dram bytes of one gibbs_kernel launch, ncu --set full, by variables per launch
+TRAFFIC_NCU = {32: 112.9e6, 256: 950.1e6}  # dram bytes of one gibbs_kernel launch, ncu --set full, by variables per launch
 FP32_FLOPS_PER_EVAL = 4 * DIM + 3  # product kernel-eval ~ (4d+3) flops + 1 SFU
 
 
@@ -281,8 +281,8 @@ def main():
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}, "traffic": TRAFFIC_NCU.get(args.vars_per_gpu),
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one gibbs_kernel launch, ncu --set full (profiles/r01_ncu_full_summary.csv); "
                         "bytes: the kernel is compute-bound, its algorithmic HBM traffic is the 100 MB node pool read once",
-        "ncu": {"issue_active_pct": 60.4, "pipe_fma_cycles_pct": 58.6, "pipe_xu_pct": 46.1, "lsu_wavefronts_pct": 51.0,
-                "warp_instructions": 2.12e10, "source": "profiles/r01_ncu_full_summary.csv (r01_gibbs_v6)"},
+        "ncu": {"issue_active_pct": 63.6, "pipe_fma_cycles_pct": 60.3, "pipe_xu_pct": 50.5, "lsu_wavefronts_pct": 57.6,
+                "warp_instructions": 1.64e11, "source": "profiles/r01_ncu_full_summary.csv (r01_gibbs_v7, 256 variables)"},
     }
 
     cpu = None
