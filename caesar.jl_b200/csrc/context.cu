@@ -101,6 +101,46 @@ extern "C" int cb2_synchronize(cb2_ctx* ctx) {
   return CB2_OK;
 }
 
+// ---- device-resident beliefs: plain device buffers a caller keeps between calls; the *_dev entry points take
+// them as they are.  Copies are stream-ordered on the context stream; only the download waits.
+extern "C" int cb2_device_alloc(cb2_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx) return CB2_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CB2_REQUIRE(ctx, out && bytes > 0, "null out or zero bytes");
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); return cb2_fail(ctx, CB2_ERR_NOMEM, "device buffer of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
+  *out = p;
+  return CB2_OK;
+}
+extern "C" int cb2_device_free(cb2_ctx* ctx, void* ptr) {
+  if (!ctx) return CB2_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!ptr) return CB2_OK;
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  CB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // enqueued work may still use it
+  CB2_CUDA(ctx, cudaFree(ptr));
+  return CB2_OK;
+}
+extern "C" int cb2_upload(cb2_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  if (!ctx) return CB2_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CB2_REQUIRE(ctx, dst_dev && src_host, "null pointer");
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  CB2_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return CB2_OK;
+}
+extern "C" int cb2_download(cb2_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  if (!ctx) return CB2_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CB2_REQUIRE(ctx, dst_host && src_dev, "null pointer");
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  CB2_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return CB2_OK;
+}
+
 extern "C" uint64_t cb2_kernel_launches(const cb2_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int cb2_device_sm_count(const cb2_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 

@@ -140,3 +140,36 @@ extern "C" int cb2_approx_conv_batch(cb2_ctx* ctx, const cb2_conv_desc* descs, i
   for (int b = 0; b < B; ++b) memcpy(descs[b].out, stage + out_off[b], sizeof(double) * (size_t)descs[b].N * out_dim(descs[b]));
   return CB2_OK;
 }
+
+// Device-resident flavour: src / aux / out are device pointers (beliefs that stay on the GPU between the
+// convolution, the bandwidth search and the product); only the descriptor table travels, nothing is waited for.
+extern "C" int cb2_approx_conv_batch_dev(cb2_ctx* ctx, const cb2_conv_desc* descs, int B, uint64_t seed) {
+  if (!ctx) return CB2_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CB2_REQUIRE(ctx, descs && B > 0, "null descriptors or empty batch");
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<ConvDev> dd(B);
+  int maxN = 0;
+  for (int b = 0; b < B; ++b) {
+    const cb2_conv_desc& c = descs[b];
+    CB2_REQUIRE(ctx, c.kind >= 0 && c.kind <= 2, "convolution %d: unknown factor kind %d", b, c.kind);
+    CB2_REQUIRE(ctx, c.N > 0 && c.out, "convolution %d: N <= 0 or null out", b);
+    if (c.kind != CB2_FACTOR_PRIOR_POSE2) CB2_REQUIRE(ctx, c.src && c.n_src > 0, "convolution %d: missing source samples", b);
+    if (c.kind == CB2_FACTOR_POSE2POINT2_BEARINGRANGE && c.reverse)
+      CB2_REQUIRE(ctx, c.aux && c.n_aux > 0, "convolution %d: reverse bearing-range needs the pose's current samples", b);
+    ConvDev& d = dd[b];
+    d.kind = c.kind; d.reverse = c.reverse; d.N = c.N; d.n_src = c.n_src; d.n_aux = c.n_aux; d.stream = c.stream;
+    memcpy(d.mean, c.mean, sizeof(d.mean)); memcpy(d.chol, c.chol, sizeof(d.chol));
+    d.src = c.src; d.aux = c.aux; d.out = c.out;
+    if (c.N > maxN) maxN = c.N;
+  }
+  int rc = cb2_arena_reserve(ctx, sizeof(ConvDev) * B + 4096);
+  if (rc) return rc;
+  ConvDev* tab = (ConvDev*)cb2_arena_alloc(ctx, sizeof(ConvDev) * B);
+  if (!tab) return cb2_fail(ctx, CB2_ERR_NOMEM, "convolution table");
+  CB2_CUDA(ctx, cudaMemcpyAsync(tab, dd.data(), sizeof(ConvDev) * B, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 grid((maxN + 127) / 128, B);
+  approx_conv_kernel<<<grid, 128, 0, ctx->stream>>>(tab, (uint32_t)seed, (uint32_t)(seed >> 32));
+  CB2_CHECK_LAUNCH(ctx, "approx_conv_kernel");
+  return CB2_OK;
+}

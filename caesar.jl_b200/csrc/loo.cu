@@ -586,3 +586,23 @@ extern "C" int cb2_kde_bw_loo(cb2_ctx* ctx, const double* mu, int d, int N, cons
   int32_t Ns[1] = {N};
   return cb2_kde_bw_loo_batch(ctx, mus, Ns, 1, d, circular, sigma_out);
 }
+
+// Device-resident flavour: mu_dev[b] are device pointers (d x N[b]), sigma_out_dev is B x d on the device.
+// For N <= 1024 the whole search of a density runs inside one kernel and nothing is waited for.
+extern "C" int cb2_kde_bw_loo_batch_dev(cb2_ctx* ctx, const double* const* mu_dev, const int32_t* N, int B, int d,
+                                        const uint8_t* circular, double* sigma_out_dev) {
+  if (!ctx) return CB2_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CB2_REQUIRE(ctx, mu_dev && N && sigma_out_dev && B > 0, "null pointer or empty batch");
+  if (d < 1 || d > CB2_MAX_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d outside 1..%d", d, CB2_MAX_DIM);
+  for (int b = 0; b < B; ++b) CB2_REQUIRE(ctx, mu_dev[b] && N[b] >= 2, "density %d: need at least 2 points", b);
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t loo_need = 0;
+  int rc = cb2_bw_loo_dev_core(ctx, mu_dev, N, B, d, circular, nullptr, nullptr, 0, &loo_need);
+  if (rc) return rc;
+  rc = cb2_arena_reserve(ctx, loo_need + 4096);
+  if (rc) return rc;
+  void* scratch = cb2_arena_alloc(ctx, loo_need);
+  if (!scratch) return cb2_fail(ctx, CB2_ERR_NOMEM, "loo scratch exhausted");
+  return cb2_bw_loo_dev_core(ctx, mu_dev, N, B, d, circular, sigma_out_dev, scratch, loo_need, nullptr);
+}

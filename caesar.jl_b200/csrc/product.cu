@@ -379,11 +379,11 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
 #endif
 }
 
-// vals[i*d .. i*d+d) = *ptrs[i]  (device-resident bandwidth vectors of a batch, fetched with one copy)
-__global__ void gather_small_vectors_kernel(const double* const* __restrict__ ptrs, int n, int d, double* __restrict__ vals) {
+// metas[i].bw[0..d) = *ptrs[i]: bandwidths that live on the device go straight into the message table (no host round trip)
+__global__ void fill_meta_bw_kernel(DensMeta* __restrict__ metas, const double* const* __restrict__ ptrs, int n, int d) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  for (int k = 0; k < d; ++k) vals[(size_t)i * d + k] = ptrs[i][k];
+  for (int k = 0; k < d; ++k) metas[i].bw[k] = ptrs[i][k];
 }
 // *ptrs[i] = vals[i*d .. i*d+d)  (fresh bandwidths written back to the caller's device buffers)
 __global__ void scatter_small_vectors_kernel(double* const* __restrict__ ptrs, int n, int d, const double* __restrict__ vals) {
@@ -539,8 +539,8 @@ struct DevLayout {
 // Core: descriptors hold DEVICE pointers (pts, w, outputs); bw values are read from `bw_host[b][j]` (host copies).
 template <typename T>
 int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const std::vector<std::vector<const double*>>& bw_host,
-                       uint32_t mask, int d, uint64_t seed, BatchPlan& pl, char* base, size_t bytes, size_t* needed,
-                       DevLayout* lay_out) {
+                       const double* const* bw_ptrs_dev, uint32_t mask, int d, uint64_t seed, BatchPlan& pl, char* base, size_t bytes,
+                       size_t* needed, DevLayout* lay_out) {
   const int nd = 2 * d + 1;
   const size_t stat_stride = (size_t)pl.max_nodes * nd + 16;  // + circular coordinate ranges (min[8], max[8])
   size_t off = 0;
@@ -565,6 +565,7 @@ int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const
       pl.metas[mi].w = descs[b].dens[j].w;
       pl.metas[mi].center = descs[b].dens[0].pts;  // first kernel of the first message: products are translation invariant
       for (int k = 0; k < d; ++k) {
+        if (bw_ptrs_dev) { pl.metas[mi].bw[k] = 1.0; continue; }  // filled on the device below (fill_meta_bw_kernel)
         double s = bw_host[b][j][k];
         if (!(s > 0) || !isfinite(s)) return cb2_fail(ctx, CB2_ERR_INVALID, "product %d message %d: bandwidth[%d] must be positive", b, j, k);
         pl.metas[mi].bw[k] = s;
@@ -576,6 +577,10 @@ int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const
   CB2_CUDA(ctx, cudaMemcpyAsync(lay.metas, pl.metas.data(), sizeof(DensMeta) * pl.metas.size(), cudaMemcpyHostToDevice, ctx->stream));
   CB2_CUDA(ctx, cudaMemcpyAsync(lay.prods, pl.prods.data(), sizeof(ProdDev) * pl.prods.size(), cudaMemcpyHostToDevice, ctx->stream));
   CB2_CUDA(ctx, cudaMemcpyAsync(lay.work, pl.work.data(), sizeof(Work) * pl.work.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (bw_ptrs_dev) {
+    fill_meta_bw_kernel<<<(int)((pl.metas.size() + 127) / 128), 128, 0, ctx->stream>>>(lay.metas, bw_ptrs_dev, (int)pl.metas.size(), d);
+    CB2_CHECK_LAUNCH(ctx, "fill_meta_bw_kernel");
+  }
 
   CB2_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   size_t tree_smem = (size_t)pl.maxP2 * 13 + 64;
@@ -612,32 +617,14 @@ int product_batch_dev_locked(cb2_ctx* ctx, const cb2_product_desc* descs, int B,
   int rc = validate_and_plan(ctx, descs, B, circular, d, pl, &mask);
   if (rc) return rc;
   CB2_CUDA(ctx, cudaSetDevice(ctx->device));
-  // bandwidths are needed on the host for validation and the per-level record layout: fetch them if they live on the device
+  // bandwidths given on the host are validated there; bandwidths that live on the device are copied into the message table by
+  // a kernel (no host round trip, so a device-resident sequence of calls never waits)
   std::vector<std::vector<const double*>> bw_host;
-  std::vector<double> bw_store;
+  std::vector<const double*> bw_ptrs;
   if (bw_host_in) bw_host = *bw_host_in;
-  else {
-    size_t nd = pl.metas.size();
-    bw_store.resize(nd * d);
-    size_t mi = 0;
-    // one gather kernel + one copy instead of one tiny D2H copy per message
-    std::vector<const double*> ptrs(nd);
+  else
     for (int b = 0; b < B; ++b)
-      for (int j = 0; j < descs[b].D; ++j, ++mi) ptrs[mi] = descs[b].dens[j].bw;
-    char* io = (char*)cb2_io_block(ctx, cb2_align(sizeof(double*) * nd) + sizeof(double) * nd * d);
-    if (!io) return CB2_ERR_NOMEM;
-    const double** ptrs_dev = (const double**)io;
-    double* vals_dev = (double*)(io + cb2_align(sizeof(double*) * nd));
-    CB2_CUDA(ctx, cudaMemcpyAsync(ptrs_dev, ptrs.data(), sizeof(double*) * nd, cudaMemcpyHostToDevice, ctx->stream));
-    gather_small_vectors_kernel<<<(int)((nd + 127) / 128), 128, 0, ctx->stream>>>(ptrs_dev, (int)nd, d, vals_dev);
-    CB2_CHECK_LAUNCH(ctx, "gather_small_vectors_kernel");
-    CB2_CUDA(ctx, cudaMemcpyAsync(bw_store.data(), vals_dev, sizeof(double) * nd * d, cudaMemcpyDeviceToHost, ctx->stream));
-    CB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    bw_host.resize(B);
-    mi = 0;
-    for (int b = 0; b < B; ++b)
-      for (int j = 0; j < descs[b].D; ++j, ++mi) bw_host[b].push_back(&bw_store[mi * d]);
-  }
+      for (int j = 0; j < descs[b].D; ++j) bw_ptrs.push_back(descs[b].dens[j].bw);
   // optional LOO bandwidth of the outputs
   std::vector<const double*> bw_mu;
   std::vector<int32_t> bw_N;
@@ -649,20 +636,27 @@ int product_batch_dev_locked(cb2_ctx* ctx, const cb2_product_desc* descs, int B,
     }
   size_t need_prod = 0, need_loo = 0;
   const bool f64 = ctx->precision == CB2_FP64;
-  rc = f64 ? product_batch_core<double>(ctx, descs, B, bw_host, mask, d, seed, pl, nullptr, 0, &need_prod, nullptr)
-           : product_batch_core<float>(ctx, descs, B, bw_host, mask, d, seed, pl, nullptr, 0, &need_prod, nullptr);
+  rc = f64 ? product_batch_core<double>(ctx, descs, B, bw_host, nullptr, mask, d, seed, pl, nullptr, 0, &need_prod, nullptr)
+           : product_batch_core<float>(ctx, descs, B, bw_host, nullptr, mask, d, seed, pl, nullptr, 0, &need_prod, nullptr);
   if (rc) return rc;
   if (!bw_mu.empty()) {
     rc = cb2_bw_loo_dev_core(ctx, bw_mu.data(), bw_N.data(), (int)bw_mu.size(), d, circular, nullptr, nullptr, 0, &need_loo);
     if (rc) return rc;
   }
   size_t bw_out_bytes = cb2_align(sizeof(double) * d * (bw_mu.size() + 1)) + cb2_align(sizeof(double*) * (bw_mu.size() + 1));
-  rc = cb2_arena_reserve(ctx, need_prod + need_loo + bw_out_bytes + 8192);
+  const size_t ptr_bytes = cb2_align(sizeof(double*) * (bw_ptrs.size() + 1));
+  rc = cb2_arena_reserve(ctx, need_prod + need_loo + bw_out_bytes + ptr_bytes + 8192);
   if (rc) return rc;
+  const double** bw_ptrs_dev = nullptr;
+  if (!bw_ptrs.empty()) {
+    bw_ptrs_dev = (const double**)cb2_arena_alloc(ctx, ptr_bytes);
+    if (!bw_ptrs_dev) return cb2_fail(ctx, CB2_ERR_NOMEM, "product scratch exhausted");
+    CB2_CUDA(ctx, cudaMemcpyAsync(bw_ptrs_dev, bw_ptrs.data(), sizeof(double*) * bw_ptrs.size(), cudaMemcpyHostToDevice, ctx->stream));
+  }
   char* base = (char*)cb2_arena_alloc(ctx, need_prod);
   if (!base) return cb2_fail(ctx, CB2_ERR_NOMEM, "product scratch exhausted");
-  rc = f64 ? product_batch_core<double>(ctx, descs, B, bw_host, mask, d, seed, pl, base, need_prod, nullptr, lay_out)
-           : product_batch_core<float>(ctx, descs, B, bw_host, mask, d, seed, pl, base, need_prod, nullptr, lay_out);
+  rc = f64 ? product_batch_core<double>(ctx, descs, B, bw_host, bw_ptrs_dev, mask, d, seed, pl, base, need_prod, nullptr, lay_out)
+           : product_batch_core<float>(ctx, descs, B, bw_host, bw_ptrs_dev, mask, d, seed, pl, base, need_prod, nullptr, lay_out);
   if (rc) return rc;
   if (!bw_mu.empty()) {
     double* bw_dev = (double*)cb2_arena_alloc(ctx, bw_out_bytes);

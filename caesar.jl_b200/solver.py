@@ -219,12 +219,16 @@ def solveGraph(fg, backend, gibbs_iters=3, seed=0, stats=None):
                         stats["products"] += 1
                         key = f"D={len(g)},N={fg.N},d={r.d}"
                         stats["shapes"][key] = stats["shapes"].get(key, 0) + 1
+    if hasattr(backend, "finish"):  # device-resident beliefs: read everything back (the only point where the host waits)
+        backend.finish(fg)
     stats["seconds"] = time.perf_counter() - t0
     return stats
 
 
 def getPPE(belief):
     """Point estimate: Euclidean mean, circular mean on wrapped coordinates."""
+    if hasattr(belief, "to_host"):  # device-resident belief: this is where the host waits
+        belief = belief.to_host()
     out = []
     for i, c in enumerate(belief.circular):
         x = belief.pts[:, i]
@@ -247,3 +251,30 @@ class DeviceBackend:
 
     def approx_conv_batch(self, convs, seed):
         return self.cb.approxConvBatch(convs, seed=seed, ctx=self.ctx)
+
+
+class DeviceResidentBackend:
+    """beliefs stay on the device across the whole solve.  Proposals (approxConvBelief), bandwidths
+    (manikde!) and products are stream-ordered `*_dev` calls on device buffers carved from one slab; nothing waits for the
+    host until a belief is read back (`getPPE` / `to_host`).  Same Philox counters as DeviceBackend: in FP64 mode both
+    backends produce the same points."""
+
+    def __init__(self, cb, ctx=None, slab_bytes=64 << 20):
+        from . import resident
+        self.cb, self.ctx, self.r = cb, ctx or cb.context(), resident
+        self.slab = resident.DeviceSlab(self.ctx, slab_bytes)
+
+    def manikde_batch(self, vartype, arrays):
+        return self.r.manikde_dev(vartype, arrays, self.slab, self.ctx)
+
+    def products(self, vartype, groups, N, seed, streams):
+        return self.r.manifoldProducts_dev(groups, vartype, N, self.slab, Niter=1, seed=seed, streams=streams, ctx=self.ctx)
+
+    def approx_conv_batch(self, convs, seed):
+        return self.r.approxConvBatch_dev(convs, self.slab, seed=seed, ctx=self.ctx)
+
+    def finish(self, fg):
+        """Downloads every belief (the one synchronisation of the solve)."""
+        for v in fg.variables.values():
+            if hasattr(v.belief, "to_host"):
+                v.belief = v.belief.to_host()

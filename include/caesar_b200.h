@@ -191,6 +191,23 @@ typedef struct {
 
 int cb2_approx_conv_batch(cb2_ctx* ctx, const cb2_conv_desc* descs, int B, uint64_t seed);
 
+/* ---- device-resident beliefs ------------------------------------------------
+ * Across a Gibbs sweep IIF runs, per variable, approxConvBelief -> manikde! -> manifoldProduct -> manikde! and feeds the
+ * result to the next factor (R:docs/src/principles/approxConvDensities.md:25-34; IIF propagateBelief).  With the belief's
+ * points (d x N Float64) and bandwidths (d Float64) kept in device buffers, that whole chain is a sequence of stream-ordered
+ * calls that never wait for the host; only cb2_download (PackedManifoldKernelDensity / getPoints on the Julia side) does.
+ * cb2_product_batch_dev with device bandwidths, cb2_mmd_sums_dev and cb2_mmd_se_batch_dev complete the set.
+ * Device bandwidths are not validated on the host (a non-positive value yields NaN samples instead of an error code). */
+int cb2_device_alloc(cb2_ctx* ctx, size_t bytes, void** out);
+int cb2_device_free(cb2_ctx* ctx, void* ptr);
+int cb2_upload(cb2_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);    /* stream-ordered, does not wait */
+int cb2_download(cb2_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);  /* waits for the stream */
+/* cb2_approx_conv_batch with src / aux / out as device pointers */
+int cb2_approx_conv_batch_dev(cb2_ctx* ctx, const cb2_conv_desc* descs, int B, uint64_t seed);
+/* cb2_kde_bw_loo_batch with mu_dev[b] (host array of device pointers) and sigma_out_dev (B x d, device) */
+int cb2_kde_bw_loo_batch_dev(cb2_ctx* ctx, const double* const* mu_dev, const int32_t* N, int B, int d,
+                             const uint8_t* circular, double* sigma_out_dev);
+
 #ifdef __cplusplus
 }
 #endif

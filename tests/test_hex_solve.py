@@ -67,3 +67,29 @@ def test_hex_solve_on_device_matches_oracle_solve(precision):
             a, b = fg.variables[k].belief, fgo.variables[k].belief
             assert np.isclose(a.pts, b.pts, atol=1e-6).all(axis=1).mean() >= 0.97, k
             assert np.allclose(a.bw, b.bw, rtol=1e-3), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("N", [100, 1000, 1500])
+def test_hex_solve_with_device_resident_beliefs_equals_the_host_pointer_solve(precision, N):
+    """proposals, bandwidths and products as `*_dev` calls on beliefs that never leave the device must give the
+    beliefs of the host-pointer path bit for bit (same kernels, same Philox counters).  N = 1500 takes the multi-launch
+    bandwidth search (N > 1024) and N not a multiple of the chain block."""
+    from importlib import import_module
+    build()
+    cb = load_package()
+    solver = import_module("caesar_jl_b200.solver")
+    ctx = cb.Context(0, precision)
+    fa = solver.generateGraph_Hexagonal(N=N)
+    sa = solver.solveGraph(fa, solver.DeviceBackend(cb, ctx), gibbs_iters=2, seed=5)
+    fb = solver.generateGraph_Hexagonal(N=N)
+    L = cb._capi.lib()
+    launches0 = L.cb2_kernel_launches(ctx._h)
+    sb = solver.solveGraph(fb, solver.DeviceResidentBackend(cb, ctx), gibbs_iters=2, seed=5)
+    assert L.cb2_kernel_launches(ctx._h) > launches0
+    assert sa["products"] == sb["products"] and sa["shapes"] == sb["shapes"]
+    for k in HEX_TRUTH:
+        a, b = fa.variables[k].belief, fb.variables[k].belief
+        assert np.array_equal(a.pts, b.pts), k
+        assert np.array_equal(a.bw, b.bw), k
