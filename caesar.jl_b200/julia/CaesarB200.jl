@@ -251,4 +251,57 @@ function b200_scatter_align(cloud1::ManifoldKernelDensity, cloud2::ManifoldKerne
   return coords, score, iters
 end
 
+# ------------------------------------------------------------------------------------------------ device-resident beliefs
+# SURVEY sec. 8f N2: points (d x N) and bandwidths (d) of a belief kept in device buffers between approxConvBelief, manikde!
+# and manifoldProduct; every call below is stream-ordered, only b200_download! waits.
+struct DeviceBelief
+  pts::Ptr{Float64}   # device, d x N
+  bw::Ptr{Float64}    # device, d
+  N::Int
+  d::Int
+end
+
+function b200_device_alloc(nbytes::Integer; ctx::Context = context())
+  p = Ref{Ptr{Cvoid}}(C_NULL)
+  lock(ctx.lk) do
+    _check(ctx, ccall((:cb2_device_alloc, libcb2), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), ctx.h, nbytes, p))
+  end
+  return p[]
+end
+b200_device_free(p::Ptr; ctx::Context = context()) =
+  lock(() -> _check(ctx, ccall((:cb2_device_free, libcb2), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.h, p)), ctx.lk)
+b200_upload!(dst::Ptr, src::Array{Float64}; ctx::Context = context()) =
+  lock(() -> _check(ctx, ccall((:cb2_upload, libcb2), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Csize_t), ctx.h, dst, src, sizeof(src))), ctx.lk)
+b200_download!(dst::Array{Float64}, src::Ptr; ctx::Context = context()) =
+  lock(() -> _check(ctx, ccall((:cb2_download, libcb2), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}, Csize_t), ctx.h, dst, src, sizeof(dst))), ctx.lk)
+
+function DeviceBelief(mkd::ManifoldKernelDensity; ctx::Context = context())
+  pts = getPoints(mkd.belief); bw = vec(getBW(mkd.belief)[:, 1])
+  dp = convert(Ptr{Float64}, b200_device_alloc(sizeof(pts); ctx)); db = convert(Ptr{Float64}, b200_device_alloc(sizeof(bw); ctx))
+  b200_upload!(dp, pts; ctx); b200_upload!(db, bw; ctx)
+  return DeviceBelief(dp, db, size(pts, 2), size(pts, 1))
+end
+function Base.collect(b::DeviceBelief; ctx::Context = context())   # (points, bandwidths) back on the host
+  pts = zeros(b.d, b.N); bw = zeros(b.d)
+  b200_download!(pts, b.pts; ctx); b200_download!(bw, b.bw; ctx)
+  return pts, bw
+end
+
+# descriptors carry device pointers (src / aux / out of CB2ConvDesc, every pointer of CB2ProductDesc / CB2Density)
+b200_approx_conv_dev!(descs::Vector{CB2ConvDesc}; seed::UInt64 = rand(UInt64), ctx::Context = context()) =
+  lock(() -> _check(ctx, ccall((:cb2_approx_conv_batch_dev, libcb2), Cint, (Ptr{Cvoid}, Ptr{CB2ConvDesc}, Cint, UInt64),
+                               ctx.h, descs, length(descs), seed)), ctx.lk)
+function b200_bandwidth_dev!(sigma_dev::Ptr{Float64}, pts_dev::Vector{Ptr{Float64}}, Ns::Vector{Int32}, M; ctx::Context = context())
+  circ = _circular(M)
+  lock(ctx.lk) do
+    _check(ctx, ccall((:cb2_kde_bw_loo_batch_dev, libcb2), Cint,
+                      (Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Int32}, Cint, Cint, Ptr{UInt8}, Ptr{Float64}),
+                      ctx.h, pts_dev, Ns, length(Ns), length(circ), circ, sigma_dev))
+  end
+end
+b200_products_dev!(descs::Vector{CB2ProductDesc}, M; seed::UInt64 = rand(UInt64), ctx::Context = context()) =
+  lock(() -> (circ = _circular(M); _check(ctx, ccall((:cb2_product_batch_dev, libcb2), Cint,
+                               (Ptr{Cvoid}, Ptr{CB2ProductDesc}, Cint, Ptr{UInt8}, Cint, UInt64),
+                               ctx.h, descs, length(descs), circ, length(circ), seed))), ctx.lk)
+
 end # module
