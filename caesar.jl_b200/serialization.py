@@ -6,6 +6,8 @@ import numpy as np
 
 
 def packDistribution(mkd, varType=None):
+    if hasattr(mkd, "to_host"):  # device-resident belief (resident.DeviceBelief): packing is where it is read back
+        mkd = mkd.to_host()
     vt = varType or (mkd.manifold if isinstance(mkd.manifold, str) else "ContinuousEuclid")
     if "." not in vt:
         vt = "RoME." + vt

@@ -446,3 +446,28 @@ def test_pair_kernels_random_shapes(cb, ctx):
         x = np.c_[rng.normal(size=N) * 2.0, rng.uniform(-np.pi, np.pi, size=N)]
         got, want = cb.kde_bandwidth(x, (0, 1), ctx=ctx), oracle.kde_bw_loo(x, circular=[0, 1])
         assert np.allclose(got, want, rtol=1e-6 if ctx.precision == "fp64" else 3e-2), (N, got, want)
+
+
+def test_device_resident_belief_round_trip_and_packed_format(cb, ctx, tut3):
+    """a tut3 belief uploaded to the device packs back into exactly the PackedManifoldKernelDensity JSON of the
+    host object (the fixture format), and a product of resident beliefs equals the host-pointer product bit for bit."""
+    import json
+    from importlib import import_module
+    res = import_module("caesar_jl_b200.resident")
+    slab = res.DeviceSlab(ctx, 8 << 20)
+    host = [cb.MKD("Point2", *tut3[k]) for k in ("l3_2", "l3_3", "l3_4")]
+    dev = [res.upload_belief(m, slab, ctx) for m in host]
+    for m, dm in zip(host, dev):
+        assert json.dumps(cb.packDistribution(dm), sort_keys=True) == json.dumps(cb.packDistribution(m), sort_keys=True)
+    want = cb.manifoldProducts([host, host[:2]], "Point2", N=100, seed=11, streams=[3, 4], ctx=ctx)
+    got = res.manifoldProducts_dev([dev, dev[:2]], "Point2", 100, slab, seed=11, streams=[3, 4], ctx=ctx)
+    for w, g in zip(want, got):
+        h = g.to_host()
+        assert np.array_equal(h.pts, w.pts) and np.array_equal(h.bw, w.bw)
+    # fresh bandwidths of resident sample sets = the host call's
+    arrs = [d.pts for d in dev]
+    bel = res.manikde_dev("Point2", arrs, slab, ctx)
+    ref = cb.kde_bandwidth_batch([m.pts for m in host], "Point2", ctx=ctx)
+    for b, r in zip(bel, ref):
+        assert np.array_equal(b.to_host().bw, r)
+    slab.free()
