@@ -388,16 +388,39 @@ loo_small_kernel(const LooProblem* __restrict__ probs, const int* __restrict__ i
     T xi[kRI], acc[kRI];
 #pragma unroll
     for (int r = 0; r < kRI; ++r) { int row = tid + r * kThreads; xi[r] = sxs[row < N ? row : 0]; acc[r] = T(0); }
-    for (int j = 0; j < N; ++j) {
-      const T q = sxs[j];
+    // pair loops compiled per topology (the wrap costs four instructions per pair); the self term of row tid + 256 r sits
+    // in the 32-column group with (j0 - warp base) % 256 == 0, every other group runs without the per-pair predicate
+    auto sweep = [&](auto topo) {
+      constexpr bool CIRC = decltype(topo)::value;
+      const int tid_base = tid & ~31;
+      for (int j0 = 0; j0 < N; j0 += 32) {
+        const int je = min(j0 + 32, N);
+        if (((j0 - tid_base) & (kThreads - 1)) == 0) {
+          for (int j = j0; j < je; ++j) {
+            const T q = sxs[j];
 #pragma unroll
-      for (int r = 0; r < kRI; ++r) {
-        T df = xi[r] - q;
-        if (circ) { T ad = fabs(df); df = fmin(ad, period - ad); }
-        T kv = fast_exp2(-(df * df));
-        acc[r] += (j == tid + r * kThreads) ? T(0) : kv;
+            for (int r = 0; r < kRI; ++r) {
+              T df = xi[r] - q;
+              if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
+              T kv = fast_exp2(-(df * df));
+              acc[r] += (j == tid + r * kThreads) ? T(0) : kv;
+            }
+          }
+        } else {
+#pragma unroll 8
+          for (int j = j0; j < je; ++j) {
+            const T q = sxs[j];
+#pragma unroll
+            for (int r = 0; r < kRI; ++r) {
+              T df = xi[r] - q;
+              if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
+              acc[r] += fast_exp2(-(df * df));
+            }
+          }
+        }
       }
-    }
+    };
+    if (circ) sweep(std::true_type{}); else sweep(std::false_type{});
     double v = 0;
 #pragma unroll
     for (int r = 0; r < kRI; ++r)
