@@ -280,7 +280,13 @@ def main():
         "launch_ms": gibbs_ms, "share_of_step": gibbs_ms * args.steps / ms_total if ms_total else None,
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}, "traffic": TRAFFIC_NCU.get(args.vars_per_gpu),
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one gibbs_kernel launch, ncu --set full (profiles/r01_ncu_full_summary.csv); "
-                        "bytes: the kernel is compute-bound, its algorithmic HBM traffic is the 100 MB node pool read once",
+                        "bytes: the kernel is compute-bound, its algorithmic HBM traffic is the node pool (3.1 MB per variable) read once",
+        # the same launch against the HBM roofline the contract names, to show why it is not the bound: algorithmic bytes = the
+        # level records read once + inputs' permutations + outputs, per launch
+        "hbm_view": (lambda b, pk: {"algorithmic_bytes": b, "achieved_gbs": b / (gibbs_ms * 1e-3) / 1e9, "peak_gbs": pk,
+                                    "frac": b / (gibbs_ms * 1e-3) / 1e9 / pk, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks
+                                    else "B200_PROFILING.md fallback"})(
+            V * (3.146e6 + D_MSG * N_KER * 4 + N_OUT * (DIM * 8 + D_MSG * 4)), float(peaks.get("hbm_gbs", 6550.0))) if gibbs_ms > 0 else None,
         "ncu": {"issue_active_pct": 63.6, "pipe_fma_cycles_pct": 60.3, "pipe_xu_pct": 50.5, "lsu_wavefronts_pct": 57.6,
                 "warp_instructions": 1.64e11, "source": "profiles/r01_ncu_full_summary.csv (r01_gibbs_v7, 256 variables)"},
     }
@@ -463,10 +469,12 @@ def mmd_extras(cb, ctx, torch, tstream, rank=0, world=1, dist=None):
             g.append(cb.ManifoldKernelDensity("Pose2", pts, 0.53 * pts.std(0) * 1000 ** -0.2))
         return g
     groups = [c4_group(v) for v in range(256)]
-    cb.manifoldProducts(groups[:8], "Pose2", N=1000, seed=1, ctx=ctx)
-    t0 = time.perf_counter()
-    res = cb.manifoldProducts(groups, "Pose2", N=1000, seed=2, ctx=ctx)
-    c4_s = time.perf_counter() - t0
+    cb.manifoldProducts(groups, "Pose2", N=1000, seed=1, ctx=ctx)  # warm-up at full size (grow-only staging buffers)
+    c4_s = 1e9
+    for rep in range(3):
+        t0 = time.perf_counter()
+        res = cb.manifoldProducts(groups, "Pose2", N=1000, seed=2, ctx=ctx)
+        c4_s = min(c4_s, time.perf_counter() - t0)
     t0 = time.perf_counter()
     for g in groups[:4]:
         o, _ = oracle.product([(m.pts, m.bw) for m in g], 1000, seed=2, circular=[0, 0, 1], ubits=24)
