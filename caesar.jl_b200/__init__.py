@@ -454,6 +454,26 @@ def approxConvBatch(convs, seed=0, ctx=None):
     return outs
 
 
+def icp_align_batch(fix, mov, perturb=None, correspondences=500, neighbors=50, min_planarity=0.3, min_change=3.0,
+                    max_iterations=25, ctx=None):
+    """`_PCL.alignICP_Simple(X_fix, X_mov; ...)` (R:src/3rdParty/_PCL/services/ICP_Simple.jl:239) for K perturbed copies of
+    `X_mov` in one device batch.  Returns (H [K, 4, 4] fix_H_mov, stats [K, 4] = mean / std of the last residuals,
+    correspondences kept, iterations)."""
+    ctx = ctx or context()
+    fix, mov = f64(fix), f64(mov)
+    if fix.ndim != 2 or fix.shape[1] != 3:
+        raise ValueError('"X_fix" must have 3 columns')
+    if mov.ndim != 2 or mov.shape[1] != 3:
+        raise ValueError('"X_mov" must have 3 columns')
+    pert = None if perturb is None else f64(np.atleast_2d(perturb))
+    K = 1 if pert is None else pert.shape[0]
+    H, st = np.zeros((K, 4, 4)), np.zeros((K, 4))
+    ctx.check(_capi.lib().cb2_icp_align_batch(ctx._h, ptr(fix), fix.shape[0], ptr(mov), mov.shape[0], ptr(pert), K,
+                                              int(correspondences), int(neighbors), float(min_planarity), float(min_change),
+                                              int(max_iterations), ptr(H), ptr(st)))
+    return H, st
+
+
 def tree_levels(pts, bw, w=None, ctx=None):
     """Level hierarchy of one message as built on the device (parity tests)."""
     ctx = ctx or context()

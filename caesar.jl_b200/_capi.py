@@ -81,6 +81,7 @@ def lib():
             "cb2_download": (i32, [vp, vp, vp, C.c_size_t]),
             "cb2_approx_conv_batch_dev": (i32, [vp, C.POINTER(ConvDesc), i32, u64]),
             "cb2_kde_bw_loo_batch_dev": (i32, [vp, vp, vp, i32, i32, vp, vp]),
+            "cb2_icp_align_batch": (i32, [vp, vp, i32, vp, i32, vp, i32, i32, i32, f64, f64, i32, vp, vp]),
             "cb2_scatter_align": (i32, [vp, C.POINTER(Density), C.POINTER(Density), i32, i32, f64, vp, i32, u64, i32, f64,
                                         vp, vp, vp]),
         }
@@ -97,7 +98,7 @@ EXPORTS = ["cb2_create", "cb2_destroy", "cb2_last_error", "cb2_precision", "cb2_
            "cb2_kde_bw_loo_batch", "cb2_kde_sample", "cb2_product", "cb2_product_batch", "cb2_product_batch_dev",
            "cb2_product_batch_submit", "cb2_wait", "cb2_tree_debug", "cb2_scatter_align", "cb2_approx_conv_batch",
            "cb2_mmd_manifold", "cb2_device_alloc", "cb2_device_free", "cb2_upload", "cb2_download", "cb2_approx_conv_batch_dev",
-           "cb2_kde_bw_loo_batch_dev"]
+           "cb2_kde_bw_loo_batch_dev", "cb2_icp_align_batch"]
 
 
 def f64(x):

@@ -62,8 +62,7 @@ class CalcFactor:
 def preambleCache(dfg, vars, fnc):
     """Runs once at addFactor!.  Mirrors the named tuple (;M,e0,smps1,smps2,bw,score) of the reference; the
     sample buffers live on the device inside cb2_scatter_align, so only sizes are recorded here."""
-    if fnc.align.sample_count < 0:
-        raise NotImplementedError("ICP branch (sample_count < 0) is outside the hot path (SURVEY sec. 8f N3)")
+    # sample_count < 0 selects the ICP branch (SURVEY sec. 8f N3): no sample buffers, the clouds are aligned as they are
     M = "SpecialEuclidean(2)" if fnc.DIM == 2 else "SpecialEuclidean(3)"
     return dict(M=M, e0=np.zeros(fnc.ncoord), smps1=None, smps2=None, bw=np.array([fnc.align.bw]), score=[0.0])
 
@@ -78,6 +77,8 @@ def getSample(cf, K=1, seed=0, x0=None, max_iter=200, g_tol=1e-8, ctx=None, retu
     fnc = cf.factor
     al = fnc.align
     nc, dim = fnc.ncoord, fnc.DIM
+    if al.sample_count < 0:
+        return _getSampleICP(cf, K, seed, ctx, return_info)
     if x0 is None:
         rng = np.random.default_rng(seed)
         x0 = np.concatenate([5.0 * rng.standard_normal((K, dim)), 0.1 * rng.standard_normal((K, nc - dim))], axis=1)
@@ -91,6 +92,35 @@ def getSample(cf, K=1, seed=0, x0=None, max_iter=200, g_tol=1e-8, ctx=None, retu
     cf.cache.setdefault("score", [0.0])[0] = float(score[-1])
     if return_info:
         return coords, score, iters
+    return coords
+
+
+def _se3_log_coords(H):
+    """log(M, e0, ArrayPartition(t, R)) of SpecialEuclidean(3) as tangent coordinates [t; rotation vector] (:211-213)."""
+    R, t = H[:3, :3], H[:3, 3]
+    c = np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)
+    th = np.arccos(c)
+    w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / 2.0
+    w = w * (th / np.sin(th)) if th > 1e-9 else w
+    return np.r_[t, w]
+
+
+def _getSampleICP(cf, K, seed, ctx, return_info):
+    """sample_count < 0 (R:ext/Images/ScatterAlignPose2.jl:187-214): every particle perturbs cloud2 by dstb = 0.2 randn(6)
+    (backward) and aligns it to cloud1 with simpleICP (max_iterations = 25, correspondences = 500, neighbors = 50); the K
+    particles run as one device batch.  Returns the K x 6 tangent coordinates of fix_H_mov."""
+    from . import icp_align_batch
+    fnc = cf.factor
+    if fnc.DIM != 3:
+        raise NotImplementedError("ICP alignments are implemented for Pose3 (three-dimensional clouds), as upstream")
+    al = fnc.align
+    rng = np.random.default_rng(seed)
+    dstb = 0.2 * rng.standard_normal((K, 6))
+    H, st = icp_align_batch(al.cloud1.pts, al.cloud2.pts, dstb, correspondences=500, neighbors=50, max_iterations=25, ctx=ctx)
+    coords = np.array([_se3_log_coords(h) for h in H])
+    cf.cache.setdefault("score", [0.0])[0] = float(st[-1, 0])
+    if return_info:
+        return coords, st[:, 0], st[:, 3].astype(np.int32)
     return coords
 
 

@@ -208,6 +208,20 @@ int cb2_approx_conv_batch_dev(cb2_ctx* ctx, const cb2_conv_desc* descs, int B, u
 int cb2_kde_bw_loo_batch_dev(cb2_ctx* ctx, const double* const* mu_dev, const int32_t* N, int B, int d,
                              const uint8_t* circular, double* sigma_out_dev);
 
+/* ---- ICP branch of ScatterAlign ------------------------------------------------------
+ * getSample(cf::CalcFactor{<:ScatterAlignPose3}) with sample_count < 0 (R:ext/Images/ScatterAlignPose2.jl:187-214) perturbs
+ * cloud2 by `dstb = 0.2 randn(6)` (backward transform, :195-196) and runs `_PCL.alignICP_Simple(p_ptsM, phat_pts_mov;
+ * max_iterations = 25, correspondences = 500, neighbors = 50)` (R:src/3rdParty/_PCL/services/ICP_Simple.jl:239-332): point-to-plane
+ * ICP with PCA normals on `correspondences` evenly spaced points of the fixed cloud, median/MAD rejection and the planarity
+ * gate `min_planarity`, stopping when mean and std of the residuals change by less than `min_change` percent.
+ * K particles (one perturbation each; perturb = K x 6 tangent coordinates or NULL) run as one batch; the normals are computed
+ * once.  fix: nf x 3, mov: nm x 3 (host, row-major points).  H_out: K x 16, the 4 x 4 fix_H_mov of every particle (row-major);
+ * stats_out (nullable): K x 4 = [mean(residuals), std(residuals), correspondences kept, iterations (negative: the normal
+ * equations became singular in that iteration)].  Limits: correspondences <= 1024, neighbors <= 256. */
+int cb2_icp_align_batch(cb2_ctx* ctx, const double* fix, int nf, const double* mov, int nm, const double* perturb, int K,
+                        int correspondences, int neighbors, double min_planarity, double min_change, int max_iterations,
+                        double* H_out, double* stats_out);
+
 #ifdef __cplusplus
 }
 #endif

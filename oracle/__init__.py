@@ -228,3 +228,25 @@ def mmd_manifold(a, b, circular, bw, rot_weight=2.0):
                                  C.byref(out))
     assert rc == 0
     return out.value
+
+
+def icp_align(fix, mov, perturb=None, correspondences=500, neighbors=50, min_planarity=0.3, min_change=3.0, max_iterations=25):
+    """simpleICP (R:src/3rdParty/_PCL/services/ICP_Simple.jl:239-332) for K perturbed copies of `mov`; returns (H [K,4,4], stats [K,4])."""
+    fix, mov = _f64(fix), _f64(mov)
+    K = 1 if perturb is None else len(perturb)
+    pert = None if perturb is None else _f64(perturb)
+    H, st = np.zeros((K, 4, 4)), np.zeros((K, 4))
+    rc = lib().cb2o_icp_align(_p(fix), fix.shape[0], _p(mov), mov.shape[0], _p(pert), K, int(correspondences), int(neighbors),
+                              C.c_double(min_planarity), C.c_double(min_change), int(max_iterations), _p(H), _p(st))
+    if rc != 0:
+        raise ValueError("icp_align: invalid arguments")
+    return H, st
+
+
+def icp_normals(fix, correspondences=500, neighbors=50):
+    fix = _f64(fix)
+    n = min(correspondences, fix.shape[0])
+    sel, nrm, pl = np.zeros(n, dtype=np.int32), np.zeros((n, 3)), np.zeros(n)
+    ns = lib().cb2o_icp_normals(_p(fix), fix.shape[0], int(correspondences), int(neighbors), _p(sel), _p(nrm), _p(pl))
+    assert ns == n
+    return sel, nrm, pl

@@ -603,3 +603,209 @@ int cb2o_mmd_manifold(const double* a, int N, const double* b, int M, int d, con
   *out = s[0] / ((double)N * N) - 2.0 * s[1] / ((double)N * M) + s[2] / ((double)M * M);
   return 0;
 }
+
+/* ------------------------------------------------------------------ ICP branch of ScatterAlign
+ * Restatement of simpleICP as vendored in R:src/3rdParty/_PCL/services/ICP_Simple.jl (the algorithm's source IS in the
+ * reference tree).  Deliberate, documented deviations: exact nearest neighbours by exhaustive search instead of a kd-tree
+ * (same result up to distance ties, which break towards the lower index here); the normal's sign -- LAPACK's eigenvector
+ * sign upstream -- is fixed so that its largest-magnitude component is positive; `A \ l` (QR upstream) is solved through the
+ * normal equations with a Cholesky factorisation. */
+static void sym3_eigen(const double* Cin, double* eval, double* evec) { /* cyclic Jacobi; evec columns, ascending eigenvalues */
+  double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  memcpy(A, Cin, sizeof(A));
+  for (int sweep = 0; sweep < 32; ++sweep) {
+    double off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double apq = A[p * 3 + q];
+        if (fabs(apq) < 1e-300) continue;
+        double theta = (A[q * 3 + q] - A[p * 3 + p]) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        double c = 1.0 / sqrt(t * t + 1.0), s_ = t * c;
+        for (int k = 0; k < 3; ++k) { /* A <- A J */
+          double akp = A[k * 3 + p], akq = A[k * 3 + q];
+          A[k * 3 + p] = c * akp - s_ * akq; A[k * 3 + q] = s_ * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) { /* A <- J^T A */
+          double apk = A[p * 3 + k], aqk = A[q * 3 + k];
+          A[p * 3 + k] = c * apk - s_ * aqk; A[q * 3 + k] = s_ * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          double vkp = V[k * 3 + p], vkq = V[k * 3 + q];
+          V[k * 3 + p] = c * vkp - s_ * vkq; V[k * 3 + q] = s_ * vkp + c * vkq;
+        }
+      }
+  }
+  int idx[3] = {0, 1, 2};
+  double d[3] = {A[0], A[4], A[8]};
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2 - i; ++j)
+    if (d[idx[j]] > d[idx[j + 1]]) { int t = idx[j]; idx[j] = idx[j + 1]; idx[j + 1] = t; }
+  for (int k = 0; k < 3; ++k) { eval[k] = d[idx[k]]; for (int r = 0; r < 3; ++r) evec[r * 3 + k] = V[r * 3 + idx[k]]; }
+}
+
+static double median_of(const double* v, int n, double* tmp) { /* Statistics.median: mean of the two middle values for even n */
+  memcpy(tmp, v, sizeof(double) * n);
+  qsort(tmp, n, sizeof(double), cmp_double);
+  return (n & 1) ? tmp[n / 2] : 0.5 * (tmp[n / 2 - 1] + tmp[n / 2]);
+}
+
+static int icp_select(int nf, int n, int32_t* sel) { /* ICP_Simple.jl:78-84: round.(Int, range(1, nf, length = n)) */
+  if (nf <= n) { for (int i = 0; i < nf; ++i) sel[i] = i; return nf; }
+  for (int j = 0; j < n; ++j) sel[j] = (int32_t)nearbyint(1.0 + (double)j * (double)(nf - 1) / (double)(n - 1)) - 1;
+  return n;
+}
+
+int cb2o_icp_normals(const double* fix, int nf, int correspondences, int neighbors, int32_t* sel, double* normals, double* plan) {
+  if (nf < 3 || neighbors < 2 || correspondences < 10) return -1;
+  const int ns = icp_select(nf, correspondences, sel);
+  const int kn = neighbors < nf ? neighbors : nf;
+#pragma omp parallel
+  {
+    double* dist = (double*)malloc(sizeof(double) * (size_t)nf);
+    int* nn = (int*)malloc(sizeof(int) * (size_t)kn);
+#pragma omp for schedule(dynamic, 4)
+    for (int s = 0; s < ns; ++s) { /* ICP_Simple.jl:86-110 */
+      const double* q = fix + (size_t)sel[s] * 3;
+      for (int i = 0; i < nf; ++i) {
+        double dx = fix[(size_t)i * 3] - q[0], dy = fix[(size_t)i * 3 + 1] - q[1], dz = fix[(size_t)i * 3 + 2] - q[2];
+        dist[i] = dx * dx + dy * dy + dz * dz;
+      }
+      for (int k = 0; k < kn; ++k) { /* the kn nearest, ties towards the lower index */
+        int best = -1; double bd = 0;
+        for (int i = 0; i < nf; ++i) if (dist[i] >= 0 && (best < 0 || dist[i] < bd)) { best = i; bd = dist[i]; }
+        nn[k] = best; dist[best] = -1.0;
+      }
+      double mean[3] = {0, 0, 0}, C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int k = 0; k < kn; ++k) for (int a = 0; a < 3; ++a) mean[a] += fix[(size_t)nn[k] * 3 + a];
+      for (int a = 0; a < 3; ++a) mean[a] /= kn;
+      for (int k = 0; k < kn; ++k) {
+        double d[3];
+        for (int a = 0; a < 3; ++a) d[a] = fix[(size_t)nn[k] * 3 + a] - mean[a];
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) C[a * 3 + b] += d[a] * d[b];
+      }
+      for (int a = 0; a < 9; ++a) C[a] /= (kn - 1); /* Statistics.cov: corrected */
+      double ev[3], V[9];
+      sym3_eigen(C, ev, V);
+      double n[3] = {V[0], V[3], V[6]};
+      int big = fabs(n[1]) > fabs(n[0]) ? 1 : 0;
+      if (fabs(n[2]) > fabs(n[big])) big = 2;
+      double sg = n[big] < 0 ? -1.0 : 1.0;
+      for (int a = 0; a < 3; ++a) normals[(size_t)s * 3 + a] = sg * n[a];
+      plan[s] = (ev[1] - ev[0]) / ev[2];
+    }
+    free(dist); free(nn);
+  }
+  return ns;
+}
+
+static int chol6_solve(double* M, double* b) { /* M (6x6 SPD, row-major, overwritten) x = b (overwritten) */
+  for (int j = 0; j < 6; ++j) {
+    double s = M[j * 6 + j];
+    for (int k = 0; k < j; ++k) s -= M[j * 6 + k] * M[j * 6 + k];
+    if (!(s > 0)) return -1;
+    M[j * 6 + j] = sqrt(s);
+    for (int i = j + 1; i < 6; ++i) {
+      double t = M[i * 6 + j];
+      for (int k = 0; k < j; ++k) t -= M[i * 6 + k] * M[j * 6 + k];
+      M[i * 6 + j] = t / M[j * 6 + j];
+    }
+  }
+  for (int i = 0; i < 6; ++i) { double t = b[i]; for (int k = 0; k < i; ++k) t -= M[i * 6 + k] * b[k]; b[i] = t / M[i * 6 + i]; }
+  for (int i = 5; i >= 0; --i) { double t = b[i]; for (int k = i + 1; k < 6; ++k) t -= M[k * 6 + i] * b[k]; b[i] = t / M[i * 6 + i]; }
+  return 0;
+}
+
+int cb2o_icp_align(const double* fix, int nf, const double* mov0, int nm, const double* perturb, int K, int correspondences,
+                   int neighbors, double min_planarity, double min_change, int max_iterations, double* H_out, double* stats_out) {
+  if (nf < 3 || nm < 1 || K < 1 || correspondences < 10 || neighbors < 2 || !(min_planarity >= 0 && min_planarity < 1) ||
+      !(min_change > 0) || max_iterations < 1) return -1; /* argument checks of ICP_Simple.jl:252-258 */
+  int32_t* sel = (int32_t*)malloc(sizeof(int32_t) * (size_t)(correspondences < nf ? correspondences : nf));
+  double* normals = (double*)malloc(sizeof(double) * 3 * (size_t)correspondences);
+  double* plan = (double*)malloc(sizeof(double) * (size_t)correspondences);
+  const int ns = cb2o_icp_normals(fix, nf, correspondences, neighbors, sel, normals, plan);
+  if (ns < 0) { free(sel); free(normals); free(plan); return -1; }
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 0; k < K; ++k) {
+    double* mov = (double*)malloc(sizeof(double) * 3 * (size_t)nm);
+    if (perturb) cb2o_transform_points(3, perturb + (size_t)k * 6, 1, mov0, nm, mov);
+    else memcpy(mov, mov0, sizeof(double) * 3 * (size_t)nm);
+    int* match = (int*)malloc(sizeof(int) * ns);
+    double* dist = (double*)malloc(sizeof(double) * ns);
+    double* tmp = (double*)malloc(sizeof(double) * ns);
+    double* dev = (double*)malloc(sizeof(double) * ns);
+    double* res = (double*)malloc(sizeof(double) * ns);
+    double H[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    double mean_old = 0, std_old = 0, mean_new = 0, std_new = 0;
+    int iters = 0, nkeep = 0;
+    for (int it = 1; it <= max_iterations; ++it) {
+      iters = it;
+      for (int s = 0; s < ns; ++s) { /* matching!, ICP_Simple.jl:112-134 */
+        const double* f = fix + (size_t)sel[s] * 3;
+        int best = 0; double bd = 1e300;
+        for (int i = 0; i < nm; ++i) {
+          double dx = mov[(size_t)i * 3] - f[0], dy = mov[(size_t)i * 3 + 1] - f[1], dz = mov[(size_t)i * 3 + 2] - f[2];
+          double d2 = dx * dx + dy * dy + dz * dz;
+          if (d2 < bd) { bd = d2; best = i; }
+        }
+        match[s] = best;
+        const double* m = mov + (size_t)best * 3;
+        dist[s] = (m[0] - f[0]) * normals[s * 3] + (m[1] - f[1]) * normals[s * 3 + 1] + (m[2] - f[2]) * normals[s * 3 + 2];
+      }
+      /* reject!, ICP_Simple.jl:136-154 */
+      double med = median_of(dist, ns, tmp);
+      for (int s = 0; s < ns; ++s) dev[s] = fabs(dist[s] - med);
+      double sigmad = 1.4826022185056018 * median_of(dev, ns, tmp);
+      double AtA[36], Atl[6];
+      memset(AtA, 0, sizeof(AtA)); memset(Atl, 0, sizeof(Atl));
+      nkeep = 0;
+      for (int s = 0; s < ns; ++s) { /* estimate_rigid_body_transformation, :174-200 */
+        if (!(fabs(dist[s] - med) <= 3 * sigmad && plan[s] > min_planarity)) { match[s] = -1; continue; }
+        ++nkeep;
+        const double* f = fix + (size_t)sel[s] * 3; const double* m = mov + (size_t)match[s] * 3; const double* n = normals + s * 3;
+        double a[6] = {-m[2] * n[1] + m[1] * n[2], m[2] * n[0] - m[0] * n[2], -m[1] * n[0] + m[0] * n[1], n[0], n[1], n[2]};
+        double l = n[0] * (f[0] - m[0]) + n[1] * (f[1] - m[1]) + n[2] * (f[2] - m[2]);
+        for (int i = 0; i < 6; ++i) { Atl[i] += a[i] * l; for (int j = 0; j < 6; ++j) AtA[i * 6 + j] += a[i] * a[j]; }
+      }
+      double x[6];
+      memcpy(x, Atl, sizeof(x));
+      if (nkeep < 6 || chol6_solve(AtA, x) != 0) { iters = -it; break; } /* upstream would throw a singular-system error */
+      int nr = 0;
+      double sm = 0;
+      for (int s = 0; s < ns; ++s) {
+        if (match[s] < 0) continue;
+        const double* f = fix + (size_t)sel[s] * 3; const double* m = mov + (size_t)match[s] * 3; const double* n = normals + s * 3;
+        double a[6] = {-m[2] * n[1] + m[1] * n[2], m[2] * n[0] - m[0] * n[2], -m[1] * n[0] + m[0] * n[1], n[0], n[1], n[2]};
+        double l = n[0] * (f[0] - m[0]) + n[1] * (f[1] - m[1]) + n[2] * (f[2] - m[2]);
+        double r = -l;
+        for (int i = 0; i < 6; ++i) r += a[i] * x[i];
+        res[nr++] = r; sm += r;
+      }
+      mean_new = sm / nr;
+      double sv = 0;
+      for (int i = 0; i < nr; ++i) sv += (res[i] - mean_new) * (res[i] - mean_new);
+      std_new = sqrt(sv / (nr - 1));
+      double R[9];
+      so3_exp(x, R); /* euler_angles_to_linearized_rotation_matrix(..., rigid = true) = exp_lie, HomographyTransforms.jl:8-16 */
+      for (int i = 0; i < nm; ++i) { /* transform!(pcmov, dH) */
+        double* m = mov + (size_t)i * 3, o[3];
+        for (int a = 0; a < 3; ++a) o[a] = R[a * 3] * m[0] + R[a * 3 + 1] * m[1] + R[a * 3 + 2] * m[2] + x[3 + a];
+        m[0] = o[0]; m[1] = o[1]; m[2] = o[2];
+      }
+      double dH[16] = {R[0], R[1], R[2], x[3], R[3], R[4], R[5], x[4], R[6], R[7], R[8], x[5], 0, 0, 0, 1}, Hn[16];
+      for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) {
+        double t = 0; for (int c = 0; c < 4; ++c) t += dH[a * 4 + c] * H[c * 4 + b]; Hn[a * 4 + b] = t; }
+      memcpy(H, Hn, sizeof(H)); /* H .= dH * H */
+      if (it > 1) { /* check_convergence_criteria, :156-166 */
+        double cm = fabs((mean_new - mean_old) / mean_old * 100), cs = fabs((std_new - std_old) / std_old * 100);
+        if (cm < min_change && cs < min_change) break;
+      }
+      mean_old = mean_new; std_old = std_new;
+    }
+    memcpy(H_out + (size_t)k * 16, H, sizeof(H));
+    if (stats_out) { stats_out[k * 4] = mean_new; stats_out[k * 4 + 1] = std_new; stats_out[k * 4 + 2] = nkeep; stats_out[k * 4 + 3] = iters; }
+    free(mov); free(match); free(dist); free(tmp); free(dev); free(res);
+  }
+  free(sel); free(normals); free(plan);
+  return 0;
+}

@@ -90,6 +90,16 @@ const double* cb2o_tree_level_wt(const cb2o_tree* t, int level);   /* cnt */
 int cb2o_approx_conv(int kind, int reverse, int N, const double* src, int n_src, const double* aux, int n_aux,
                      uint32_t stream, const double* mean, const double* chol, uint64_t seed, double* out);
 
+/* ICP branch of ScatterAlign: simpleICP as vendored in R:src/3rdParty/_PCL/services/ICP_Simple.jl:239-332.
+ * fix: nf x 3, mov: nm x 3; perturb: K x 6 coordinates (or NULL) applied to mov with backward = 1 before the alignment
+ * (R:ext/Images/ScatterAlignPose2.jl:195-196).  H_out: K x 16 (row-major 4 x 4, fix_H_mov); stats_out: K x 4 =
+ * [mean(residuals), std(residuals), correspondences kept, iterations] of the last iteration. */
+int cb2o_icp_align(const double* fix, int nf, const double* mov, int nm, const double* perturb, int K, int correspondences,
+                   int neighbors, double min_planarity, double min_change, int max_iterations, double* H_out, double* stats_out);
+/* normals + planarity of the selected fixed points (ICP_Simple.jl:78-110): sel_out (n_sel), normals_out (n_sel x 3), plan_out */
+int cb2o_icp_normals(const double* fix, int nf, int correspondences, int neighbors, int32_t* sel_out, double* normals_out,
+                     double* plan_out);
+
 int cb2o_num_threads(void);
 void cb2o_set_num_threads(int n);
 

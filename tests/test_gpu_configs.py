@@ -20,6 +20,11 @@ def ctx(request, cb):
     return cb.Context(0, request.param)
 
 
+@pytest.fixture(scope="module")
+def ctx32(cb):
+    return cb.Context(0, "fp32")
+
+
 def test_c1_heatmap_scatter_align_pose2(cb, ctx):
     """R:test/testScatterAlignPose2.jl:19-69: 301x301 heatmaps of three Gaussians, true pCq = [5, 0, pi/8],
     N=1000, sample_count=100, bw=1.0; recovery within 1.5 m / 0.2 rad (:68-69)."""
@@ -212,3 +217,56 @@ def test_mmd_between_pose_beliefs_uses_manifold_distance(cb, ctx):
     A, B = cb.MKD("Pose2", pa, [0.1, 0.1, 0.05]), cb.MKD("Pose2", pb, [0.1, 0.1, 0.05])
     assert cb.mmd(A, B, bw=0.5, ctx=ctx) < 5e-3
     assert cb.mmd(pa, pb, bw=0.5, ctx=ctx) > 0.1
+
+
+def _room(n, rng):
+    k = n // 3
+    a = np.c_[rng.uniform(0, 4, k), rng.uniform(0, 4, k), 0.01 * rng.normal(size=k)]
+    b = np.c_[rng.uniform(0, 4, k), 0.01 * rng.normal(size=k), rng.uniform(0, 4, k)]
+    c = np.c_[0.01 * rng.normal(size=n - 2 * k), rng.uniform(0, 4, n - 2 * k), rng.uniform(0, 4, n - 2 * k)]
+    return np.r_[a, b, c]
+
+
+@pytest.mark.parametrize("shape", ["randn", "room", "small"])
+def test_icp_batch_matches_the_cpu_restatement(cb, ctx32, shape):
+    """`_PCL.alignICP_Simple` for K perturbed particles as one device batch == oracle/cb2_oracle.c (FP64 on both
+    sides; sums are taken in a different order, hence the 1e-9).  'randn' is the reference's own test input
+    (R:test/testScatterAlignPose3.jl:29-30: X_fix = randn(n, 3), X_mov = randn(n, 3); it only has to run), 'room' a structured
+    scene with a known answer, 'small' has fewer points than correspondences / an odd count for the median."""
+    rng = np.random.default_rng(31)
+    if shape == "randn":
+        fix, mov, kw = rng.normal(size=(3000, 3)), rng.normal(size=(3000, 3)), {}
+    elif shape == "room":
+        fix, kw = _room(6000, rng), {}
+        mov = oracle.transform_points(3, np.array([0.15, -0.1, 0.08, 0.03, -0.02, 0.05]), _room(5000, rng), True)
+    else:
+        fix, mov, kw = _room(333, rng), _room(400, rng) + 0.02, dict(correspondences=500, neighbors=12, max_iterations=7)
+    pert = np.r_[np.zeros((1, 6)), 0.2 * rng.normal(size=(4, 6)) * (0.25 if shape == "room" else 1.0)]
+    H, st = cb.icp_align_batch(fix, mov, pert, ctx=ctx32, **kw)
+    Ho, sto = oracle.icp_align(fix, mov, perturb=pert, **kw)
+    assert np.array_equal(st[:, 2:], sto[:, 2:]), (st, sto)            # same correspondences kept, same iteration count
+    assert np.allclose(H, Ho, rtol=0, atol=1e-9) and np.allclose(st[:, :2], sto[:, :2], rtol=1e-7, atol=1e-12)
+    assert np.allclose(H[:, 3], [0, 0, 0, 1]) and np.allclose(np.linalg.det(H[:, :3, :3]), 1.0, atol=1e-9)
+    if shape == "room":
+        assert np.abs(H[0, :3, 3] - [0.15, -0.1, 0.08]).max() < 6e-3
+
+
+def test_scatter_align_pose3_getsample_icp_branch(cb, ctx32):
+    """getSample(cf::CalcFactor{<:ScatterAlignPose3}) with sample_count = -1 (R:ext/Images/ScatterAlignPose2.jl:187-214,
+    R:test/testScatterAlignPose3.jl:50-62): K particles, each aligns its own perturbed copy of cloud2."""
+    rng = np.random.default_rng(5)
+    fix = _room(6000, rng)
+    truth = np.array([0.15, -0.1, 0.08, 0.03, -0.02, 0.05])
+    mov = oracle.transform_points(3, truth, _room(6000, rng), True)
+    sap = cb.ScatterAlignPose3(cloud1=cb.ManifoldKernelDensity("Point3", fix, [0.1, 0.1, 0.1]),
+                               cloud2=cb.ManifoldKernelDensity("Point3", mov, [0.1, 0.1, 0.1]), sample_count=-1)
+    cf = cb.CalcFactor(sap, cb.preambleCache(None, [], sap))
+    coords, score, iters = cb.getSample(cf, K=16, seed=3, ctx=ctx32, return_info=True)
+    assert coords.shape == (16, 6) and (iters > 0).all() and np.abs(score).max() < 1e-2
+    # every particle aligned its own bumped copy: undoing the bump (first order) gives the true transform
+    dstb = 0.2 * np.random.default_rng(3).standard_normal((16, 6))
+    assert np.abs(np.median(coords - dstb, axis=0) - truth).max() < 0.05
+    with pytest.raises(cb.CB2Error):
+        cb.icp_align_batch(fix, mov, correspondences=5, ctx=ctx32)
+    with pytest.raises(ValueError):
+        cb.icp_align_batch(fix[:, :2], mov, ctx=ctx32)

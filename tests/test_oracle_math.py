@@ -195,3 +195,43 @@ def test_product_single_density_and_offsets():
     full, lf = oracle.product(dens, 20, seed=3)
     part, lp = oracle.product(dens, 8, seed=3, sample_offset=12)
     assert np.array_equal(full[12:], part) and np.array_equal(lf[12:], lp)
+
+
+def _room(n, rng):
+    """Three orthogonal walls with 1 cm roughness: a cloud with well-defined normals."""
+    k = n // 3
+    a = np.c_[rng.uniform(0, 4, k), rng.uniform(0, 4, k), 0.01 * rng.normal(size=k)]
+    b = np.c_[rng.uniform(0, 4, k), 0.01 * rng.normal(size=k), rng.uniform(0, 4, k)]
+    c = np.c_[0.01 * rng.normal(size=n - 2 * k), rng.uniform(0, 4, n - 2 * k), rng.uniform(0, 4, n - 2 * k)]
+    return np.r_[a, b, c]
+
+
+def test_icp_restatement_recovers_a_known_rigid_transform():
+    """simpleICP (R:src/3rdParty/_PCL/services/ICP_Simple.jl:239-332) on a structured scene: the moving cloud is
+    an independent sampling of the same walls moved by T^-1, so fix_H_mov must come out as T."""
+    rng = np.random.default_rng(0)
+    fix, src = _room(6000, rng), _room(6000, rng)
+    truth = np.array([0.15, -0.1, 0.08, 0.03, -0.02, 0.05])
+    mov = oracle.transform_points(3, truth, src, True)
+    H, st = oracle.icp_align(fix, mov)
+    back = oracle.transform_points(3, truth, np.eye(3), False) - oracle.transform_points(3, truth, np.zeros((1, 3)), False)
+    assert np.abs(H[0, :3, :3] - back.T).max() < 2e-3          # rotation
+    assert np.abs(H[0, :3, 3] - truth[:3]).max() < 6e-3        # translation
+    assert H[0, 3].tolist() == [0, 0, 0, 1] and 2 <= st[0, 3] <= 25 and st[0, 2] > 300 and abs(st[0, 0]) < 1e-3
+    # normals of wall points are the wall normals (sign fixed: largest component positive); corners are rejected by planarity
+    sel, nrm, pl = oracle.icp_normals(fix, 500, 50)
+    flat = pl > 0.6
+    big = np.abs(nrm[flat]).argmax(axis=1)
+    v = nrm[flat][np.arange(flat.sum()), big]
+    assert flat.sum() > 300 and np.median(v) > 0.999 and (v > 0.8).all()   # tilted only next to the wall intersections
+    assert sel[0] == 0 and sel[-1] == 5999 and np.all(np.diff(sel) > 0)
+    # the perturbed particles of getSample (ScatterAlignPose2.jl:195-196) end at H_k = T o T(dstb_k)
+    pert = 0.05 * rng.normal(size=(3, 6))
+    Hk, stk = oracle.icp_align(fix, mov, perturb=pert)
+    for k in range(3):
+        Tp = np.eye(4)
+        Tp[:3, :3] = (oracle.transform_points(3, pert[k], np.eye(3), False) - oracle.transform_points(3, pert[k], np.zeros((1, 3)), False)).T
+        Tp[:3, 3] = pert[k, :3]
+        assert np.abs(Hk[k] - H[0] @ Tp).max() < 1.5e-2, k
+    with pytest.raises(ValueError):
+        oracle.icp_align(fix, mov, correspondences=5)
