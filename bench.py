@@ -430,6 +430,20 @@ def mmd_extras(cb, ctx, torch, tstream, rank=0, world=1, dist=None):
     sap_s = time.perf_counter() - t0
     out.update({"sap2_getsample_ms_per_particle": sap_s * 1e3 / 100, "sap2_particles": 100, "sap2_mean_bfgs_iters": float(iters.mean()),
                 "sap2_median_abs_err": [float(x) for x in np.median(np.abs(cs - np.array([2.0, 0, np.pi / 6])), axis=0)]})
+    # N3: ICP branch of ScatterAlignPose3 on the reference test's input shape (R:test/testScatterAlignPose3.jl:29-30: randn(10000, 3)
+    # clouds), K = 100 particles = 100 perturbed alignments (max_iterations 25, correspondences 500, neighbors 50) as one batch
+    xf, xm = rng.normal(size=(10000, 3)), rng.normal(size=(10000, 3))
+    pert = 0.2 * rng.normal(size=(100, 6))
+    cb.icp_align_batch(xf, xm, pert[:4], ctx=ctx)
+    t0 = time.perf_counter()
+    Hi, sti = cb.icp_align_batch(xf, xm, pert, ctx=ctx)
+    icp_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Ho, sto = oracle.icp_align(xf, xm, perturb=pert[:8])
+    icp_cpu = time.perf_counter() - t0
+    out["icp_align"] = {"particles": 100, "points_per_cloud": 10000, "ms_per_particle": icp_s * 1e3 / 100, "mean_iterations": float(np.abs(sti[:, 3]).mean()),
+                        "cpu_ms_per_particle": icp_cpu * 1e3 / 8, "cpu_sample": "8 of the 100 particles, oracle on all host cores",
+                        "max_abs_diff_vs_oracle": float(np.abs(Hi[:8] - Ho).max())}
     # C2: hexagonal Pose2 SLAM through the caller harness (caesar.jl_b200/solver.py), third headline of BASELINE.json
     solver = import_module("caesar_jl_b200.solver")
     from oracle.solver_backend import OracleBackend

@@ -304,4 +304,22 @@ b200_products_dev!(descs::Vector{CB2ProductDesc}, M; seed::UInt64 = rand(UInt64)
                                (Ptr{Cvoid}, Ptr{CB2ProductDesc}, Cint, Ptr{UInt8}, Cint, UInt64),
                                ctx.h, descs, length(descs), circ, length(circ), seed))), ctx.lk)
 
+# ------------------------------------------------------------------------------------------------ ICP branch (sample_count < 0)
+# K particles of getSample(cf::CalcFactor{<:ScatterAlignPose3}) (ext/Images/ScatterAlignPose2.jl:187-214) in one call:
+# dstb is 6 x K (0.2 * randn(6) per particle, :195); returns the 4 x 4 p_Hicp_phat of every particle and the ICP statistics.
+function b200_icp_align(p_pts::AbstractMatrix{Float64}, q_pts::AbstractMatrix{Float64}, dstb::AbstractMatrix{Float64};
+                        correspondences::Integer = 500, neighbors::Integer = 50, min_planarity::Real = 0.3, min_change::Real = 3,
+                        max_iterations::Integer = 25, ctx::Context = context())
+  K = size(dstb, 2)
+  Hrm = zeros(4, 4, K); st = zeros(4, K)          # row-major 4 x 4 per particle
+  lock(ctx.lk) do
+    _check(ctx, ccall((:cb2_icp_align_batch, libcb2), Cint,
+                      (Ptr{Cvoid}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Cint, Cint, Float64, Float64, Cint,
+                       Ptr{Float64}, Ptr{Float64}),
+                      ctx.h, p_pts, size(p_pts, 2), q_pts, size(q_pts, 2), dstb, K, correspondences, neighbors,
+                      Float64(min_planarity), Float64(min_change), max_iterations, Hrm, st))
+  end
+  return [permutedims(Hrm[:, :, k]) for k in 1:K], st
+end
+
 end # module
