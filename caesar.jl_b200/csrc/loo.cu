@@ -346,6 +346,7 @@ loo_small_kernel(const LooProblem* __restrict__ probs, const int* __restrict__ i
   const int N = pr.N, tid = threadIdx.x;
   __shared__ double sk[kSmallN];
   __shared__ T sxs[kSmallN];
+  __shared__ T colacc[(kThreads / 32) * kThreads];  // per-warp column sums of one block pair
   __shared__ double sred[kThreads / 32];
   __shared__ LooState ss;
   int P2 = 1;
@@ -377,50 +378,80 @@ loo_small_kernel(const LooProblem* __restrict__ probs, const int* __restrict__ i
   }
   const bool circ = pr.circular != 0;
   const double x_mid = circ ? 0.0 : sk[N >> 1];
+  // sorted: a circular problem whose points lie in [-pi, pi] within pi of each other never needs the wrap
+  const bool wraps = circ && !(sk[0] >= -CB2_PI && sk[N - 1] <= CB2_PI && sk[N - 1] - sk[0] <= CB2_PI);
   for (int it = 0; it < 96; ++it) {
     __syncthreads();
     if (ss.phase == 3) break;
     const double h = ss.h_eval;
     const double sc = sqrt(0.5 * CB2_LOG2E) / h;
     const T period = (T)(CB2_TWO_PI * sc);
-    for (int j = tid; j < N; j += kThreads) sxs[j] = (T)(((circ ? wrap_pi(sk[j]) : sk[j]) - x_mid) * sc);
+    for (int j = tid; j < kSmallN; j += kThreads) sxs[j] = j < N ? (T)(((circ ? wrap_pi(sk[j]) : sk[j]) - x_mid) * sc) : T(1e18);
     __syncthreads();
     T xi[kRI], acc[kRI];
 #pragma unroll
     for (int r = 0; r < kRI; ++r) { int row = tid + r * kThreads; xi[r] = sxs[row < N ? row : 0]; acc[r] = T(0); }
-    // pair loops compiled per topology (the wrap costs four instructions per pair); the self term of row tid + 256 r sits
-    // in the 32-column group with (j0 - warp base) % 256 == 0, every other group runs without the per-pair predicate
+    // The N points form up to four blocks of 256 (thread t owns row t of every block).  Pairs inside a block are evaluated in
+    // full with the self term excluded (it sits in the 32-column group at the warp's own base); pairs between blocks a < b are
+    // evaluated ONCE: k goes to the row of block a (register) and to the column of block b (lane transpose + per-warp
+    // shared-memory slots, summed in fixed order by the thread that owns that row).  0.62 of the exponentials at N = 1000.
+    // Compiled per topology: the wrap costs four instructions per pair; a sorted problem that spans less than pi never wraps.
     auto sweep = [&](auto topo) {
       constexpr bool CIRC = decltype(topo)::value;
-      const int tid_base = tid & ~31;
-      for (int j0 = 0; j0 < N; j0 += 32) {
-        const int je = min(j0 + 32, N);
-        if (((j0 - tid_base) & (kThreads - 1)) == 0) {
-          for (int j = j0; j < je; ++j) {
-            const T q = sxs[j];
+      const int tid_base = tid & ~31, lane = tid & 31, warp = tid >> 5;
+      const int nb = (N + kThreads - 1) / kThreads;
 #pragma unroll
-            for (int r = 0; r < kRI; ++r) {
-              T df = xi[r] - q;
+      for (int r = 0; r < kRI; ++r) {
+        if (r >= nb) break;
+        const int c0 = r * kThreads, c1 = min(N, c0 + kThreads);
+        for (int j0 = c0; j0 < c1; j0 += 32) {
+          const int je = min(j0 + 32, c1);
+          if (j0 - c0 == tid_base) {
+            for (int j = j0; j < je; ++j) {
+              T df = xi[r] - sxs[j];
               if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
               T kv = fast_exp2(-(df * df));
-              acc[r] += (j == tid + r * kThreads) ? T(0) : kv;
+              acc[r] += (j == tid + c0) ? T(0) : kv;
             }
-          }
-        } else {
+          } else {
 #pragma unroll 8
-          for (int j = j0; j < je; ++j) {
-            const T q = sxs[j];
-#pragma unroll
-            for (int r = 0; r < kRI; ++r) {
-              T df = xi[r] - q;
+            for (int j = j0; j < je; ++j) {
+              T df = xi[r] - sxs[j];
               if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
               acc[r] += fast_exp2(-(df * df));
             }
           }
         }
       }
+#pragma unroll
+      for (int bb = 1; bb < kRI; ++bb) {
+        if (bb >= nb) break;
+        const int c0 = bb * kThreads, ncol = min(N, c0 + kThreads) - c0;
+#pragma unroll
+        for (int aa = 0; aa < bb; ++aa) {
+          __syncthreads();  // colacc is free again
+          for (int j0 = 0; j0 < kThreads; j0 += 32) {
+            T v[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              T df = xi[aa] - sxs[c0 + j0 + c];  // columns past N hold the far sentinel: exp2 -> 0 without the wrap
+              if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
+              T kv = fast_exp2(-(df * df));
+              if (CIRC && j0 + c >= ncol) kv = T(0);
+              acc[aa] += kv;
+              v[c] = kv;
+            }
+            colacc[warp * kThreads + j0 + lane] = lane_transpose_sum(v, lane);
+          }
+          __syncthreads();
+          T t = T(0);
+#pragma unroll
+          for (int w = 0; w < kThreads / 32; ++w) t += colacc[w * kThreads + tid];
+          acc[bb] += t;
+        }
+      }
     };
-    if (circ) sweep(std::true_type{}); else sweep(std::false_type{});
+    if (wraps) sweep(std::true_type{}); else sweep(std::false_type{});
     double v = 0;
 #pragma unroll
     for (int r = 0; r < kRI; ++r)
