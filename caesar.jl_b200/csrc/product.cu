@@ -29,7 +29,10 @@ constexpr int kTreeThreads = 512;
 constexpr int kS = 128;            // chains (threads) per Gibbs CTA
 constexpr int kNCH = 32;           // chunk partial sums per chain
 constexpr int kTileBytesF32 = 8192;
-constexpr int kG = 8;              // candidates scored together by one chain (ILP); tiles and chunks are multiples of kG
+#ifndef CB2_KG
+#define CB2_KG 8
+#endif
+constexpr int kG = CB2_KG;              // candidates scored together by one chain (ILP); tiles and chunks are multiples of kG
 
 __host__ __device__ inline int recn_of(int d) { return (2 * d + 1 + 3) / 4 * 4; }  // [mu(d), var(d), log2 w]
 __host__ __device__ inline int recl_of(int d) { return (d + 1 + 3) / 4 * 4; }      // [mu(d), log2 w]
