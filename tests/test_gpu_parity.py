@@ -471,3 +471,31 @@ def test_device_resident_belief_round_trip_and_packed_format(cb, ctx, tut3):
     for b, r in zip(bel, ref):
         assert np.array_equal(b.to_host().bw, r)
     slab.free()
+
+
+@pytest.mark.parametrize("circ", [(0, 0, 0, 0, 0, 0), (0, 0, 0, 1, 1, 1), (1, 0, 1, 0, 1, 0)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_product_fp32_six_dimensional_packed_paths(cb, ctx32, circ, weighted):
+    """The FP32 d = 6 kernels score with packed f32x2 arithmetic whenever a warp needs no wrap (run-time mask kernel for the
+    non-Pose3 masks, uniform and per-kernel weights, ragged sizes, beliefs that do / do not straddle the +-pi cut): the chains
+    must still follow the oracle's (same uniforms; FP32 rounding flips a few draws)."""
+    rng = np.random.default_rng(77 + sum(circ) + 10 * weighted)
+    for straddle in (False, True):
+        dens = []
+        for j, N in enumerate((257, 300, 64, 129)):
+            pts = rng.normal(size=(N, 6)) * rng.uniform(0.2, 0.6, size=6) + rng.normal(size=6) * 0.2
+            for i, c in enumerate(circ):
+                if c:
+                    pts[:, i] = (pts[:, i] + (3.0 if straddle else 0.5) + np.pi) % (2 * np.pi) - np.pi
+            w = rng.uniform(0.1, 1.0, size=N) if weighted else None
+            dens.append((pts, rng.uniform(0.15, 0.4, size=6), w))
+        pts, lab = cb.product_points(dens, circ, 600, seed=21, niter=1, ctx=ctx32)
+        opts, olab = oracle.product(dens, 600, seed=21, circular=list(circ), niter=1, ubits=24)
+        assert np.isfinite(pts).all()
+        assert (lab == olab).all(axis=1).mean() > 0.9, (circ, weighted, straddle, (lab == olab).all(axis=1).mean())
+        same = (lab == olab).all(axis=1)
+        diff = pts[same] - opts[same]
+        for i, c in enumerate(circ):
+            if c:
+                diff[:, i] = (diff[:, i] + np.pi) % (2 * np.pi) - np.pi
+        assert np.abs(diff).max() < 5e-5   # same labels, same normal draws: FP32 arithmetic on the final mean only
