@@ -97,12 +97,6 @@ template <typename T, int DIM> __host__ __device__ constexpr int gibbs_tile_byte
 
 // ---- packed FP32 pairs (fma.rn.f32x2 -> SASS FFMA2 on sm_100a): one issue slot for two lanes of arithmetic; the
 // all-Euclidean scoring loops of six-dimensional products pair the coordinates (0,1) (2,3) (4,5) as LDS.128 delivers them.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 template <bool SHARED> __device__ __forceinline__ void load16p(const float* p, f32x2& lo, f32x2& hi) {
   if (SHARED) asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(smem_u32(p)));
   else asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p));

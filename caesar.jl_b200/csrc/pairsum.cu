@@ -73,7 +73,13 @@ pair_tiles_kernel(const PairSub<T>* __restrict__ subs, const Tile* __restrict__ 
   constexpr int REC = RecOf<DIM>::value;
   constexpr bool GRAD = MODE == 1;
   constexpr bool OFFS = MODE == 2;
-  __shared__ Rec<T, REC> sq[kCT];
+  // FP32 plain pair sums (mmd): rows are processed as two packed pairs per thread and every column is staged as negated,
+  // duplicated coordinates (-q_k, -q_k), so a pair of rows costs DIM FADD2 + FMUL2 + (DIM - 1) FFMA2 instead of twice
+  // DIM FADD + FMUL + (DIM - 1) FFMA: 5 instead of 8.5 issue slots per pair at DIM = 3, which leaves the XU pipe as the only limit
+  constexpr bool PACKED = (MODE == 0 || MODE == 2) && sizeof(T) == 4 && kRI == 4;
+  constexpr int REC2 = (DIM + 2) / 2 * 2;  // f32x2 per staged column (+1: the evaluate offset), padded to whole 16-byte loads
+  __shared__ Rec<T, REC> sq[PACKED ? 1 : kCT];
+  __shared__ __align__(16) f32x2 sq2[PACKED ? kCT * REC2 : 1];
   __shared__ double sred[kThreads / 32][8];
 
   const Tile tl = tiles[blockIdx.x];
@@ -138,9 +144,50 @@ pair_tiles_kernel(const PairSub<T>* __restrict__ subs, const Tile* __restrict__ 
         for (int k = 0; k < REC; ++k) q.v[k] = T(0);
         q.v[0] = T(1e18);  // padding column: exp2(-1e36) == 0
       }
-      sq[j] = q;
+      if constexpr (PACKED) {
+#pragma unroll
+        for (int k = 0; k < REC2; ++k)
+          sq2[j * REC2 + k] = k < DIM ? pack2(-(float)q.v[k], -(float)q.v[k]) : (k == DIM && OFFS ? pack2((float)q.v[REC - 1], 0.0f) : 0ull);
+      } else {
+        sq[j] = q;
+      }
     }
     __syncthreads();
+    if constexpr (PACKED) {
+      f32x2 pp[2][DIM];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) pp[h][k] = pack2((float)p[2 * h][k], (float)p[2 * h + 1][k]);
+#pragma unroll 4
+      for (int j = 0; j < kCT; ++j) {
+        f32x2 nq[REC2];
+#pragma unroll
+        for (int k = 0; k < REC2; k += 2)  // warp-broadcast LDS.128
+          asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(nq[k]), "=l"(nq[k + 1]) : "r"((uint32_t)__cvta_generic_to_shared(&sq2[j * REC2 + k])));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const f32x2 d0 = add2(pp[h][0], nq[0]);
+          f32x2 r2 = mul2(d0, d0);
+#pragma unroll
+          for (int k = 1; k < DIM; ++k) {
+            const f32x2 dk = add2(pp[h][k], nq[k]);
+            r2 = fma2(dk, dk, r2);
+          }
+          float ra, rb;
+          unpack2(r2, ra, rb);
+          if (OFFS) {  // evaluate: log2 of the column's weight and normalisation rides in the spare slot
+            float off, unused;
+            unpack2(nq[DIM], off, unused);
+            acc[2 * h] += fast_exp2(off - ra);
+            acc[2 * h + 1] += fast_exp2(off - rb);
+          } else {
+            acc[2 * h] += fast_exp2(-ra);
+            acc[2 * h + 1] += fast_exp2(-rb);
+          }
+        }
+      }
+    } else {
 #pragma unroll 4
     for (int j = 0; j < kCT; ++j) {
       const Rec<T, REC> q = sq[j];  // warp-broadcast LDS.128
@@ -163,6 +210,7 @@ pair_tiles_kernel(const PairSub<T>* __restrict__ subs, const Tile* __restrict__ 
         }
       }
     }
+    }  // scalar path
   }
 
   if (MODE == 2) {
