@@ -220,19 +220,34 @@ loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict
           // sentinel back into range); every other group runs without it
           auto colgroup = [&](int j0, auto ragged) {
             constexpr bool RAGGED = decltype(ragged)::value;
+            (void)RAGGED;
             T v[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const T q = sx[j0 + c];
               T kv[kRI];
+              if constexpr (!WRAP && sizeof(T) == 4 && kRI == 4) {
+                // the four rows as two packed pairs: 2 FADD2 + 2 FMUL2 instead of 4 FADD + 4 FMUL per column
+                const f32x2 qq = pack2((float)q, (float)q);
+                const f32x2 d01 = add2(qq, pack2(-(float)xi[0], -(float)xi[1])), d23 = add2(qq, pack2(-(float)xi[2], -(float)xi[3]));
+                float s[4];
+                unpack2(mul2(d01, d01), s[0], s[1]);
+                unpack2(mul2(d23, d23), s[2], s[3]);
 #pragma unroll
-              for (int r = 0; r < kRI; ++r) {
-                T df = xi[r] - q;
-                if (WRAP) { T ad = fabs(df); df = fmin(ad, period - ad); }
-                // XU relief: one evaluation in kSoftEvery runs on the FMA/ALU pipes (soft_exp2) where the issue rate leaves room
-                kv[r] = (!WRAP && r == kRI - 1 && (c % (kSoftEvery / kRI)) == 0) ? soft_exp2(-(df * df)) : fast_exp2(-(df * df));
-                if (WRAP && RAGGED && j0 + c >= jn) kv[r] = T(0);
-                acc[r] += kv[r];
+                for (int r = 0; r < kRI; ++r) {
+                  // XU relief: one evaluation in kSoftEvery runs on the FMA/ALU pipes (soft_exp2) where the issue rate leaves room
+                  kv[r] = (T)((r == kRI - 1 && (c % (kSoftEvery / kRI)) == 0) ? soft_exp2(-s[r]) : fast_exp2(-s[r]));
+                  acc[r] += kv[r];
+                }
+              } else {
+#pragma unroll
+                for (int r = 0; r < kRI; ++r) {
+                  T df = xi[r] - q;
+                  if (WRAP) { T ad = fabs(df); df = fmin(ad, period - ad); }
+                  kv[r] = fast_exp2(-(df * df));
+                  if (WRAP && RAGGED && j0 + c >= jn) kv[r] = T(0);
+                  acc[r] += kv[r];
+                }
               }
               v[c] = (kv[0] + kv[1]) + (kv[2] + kv[3]);
             }
@@ -432,14 +447,31 @@ loo_small_kernel(const LooProblem* __restrict__ probs, const int* __restrict__ i
           __syncthreads();  // colacc is free again
           for (int j0 = 0; j0 < kThreads; j0 += 32) {
             T v[32];
+            if constexpr (!CIRC && sizeof(T) == 4) {
+              // two columns per packed operation: (q_c, q_c+1) comes out of shared memory as one 64-bit broadcast load
+              const f32x2 nx = pack2(-(float)xi[aa], -(float)xi[aa]);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              T df = xi[aa] - sxs[c0 + j0 + c];  // columns past N hold the far sentinel: exp2 -> 0 without the wrap
-              if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
-              T kv = fast_exp2(-(df * df));
-              if (CIRC && j0 + c >= ncol) kv = T(0);
-              acc[aa] += kv;
-              v[c] = kv;
+              for (int c = 0; c < 32; c += 2) {
+                f32x2 qq;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(qq) : "r"((uint32_t)__cvta_generic_to_shared(&sxs[c0 + j0 + c])));
+                const f32x2 d2 = add2(qq, nx);
+                float sa, sb;
+                unpack2(mul2(d2, d2), sa, sb);
+                v[c] = (T)fast_exp2(-sa);      // columns past N hold the far sentinel: exp2 -> 0
+                v[c + 1] = (T)fast_exp2(-sb);
+                acc[aa] += v[c];
+                acc[aa] += v[c + 1];
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                T df = xi[aa] - sxs[c0 + j0 + c];  // columns past N hold the far sentinel: exp2 -> 0 without the wrap
+                if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
+                T kv = fast_exp2(-(df * df));
+                if (CIRC && j0 + c >= ncol) kv = T(0);
+                acc[aa] += kv;
+                v[c] = kv;
+              }
             }
             colacc[warp * kThreads + j0 + lane] = lane_transpose_sum(v, lane);
           }
