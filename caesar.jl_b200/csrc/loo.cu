@@ -202,6 +202,18 @@ loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict
                   acc[r] += (cs + j == rowi[r]) ? T(0) : kv;
                 }
               }
+            } else if constexpr (!WRAP && sizeof(T) == 4 && kRI == 4) {
+              const f32x2 nx01 = pack2(-(float)xi[0], -(float)xi[1]), nx23 = pack2(-(float)xi[2], -(float)xi[3]);
+#pragma unroll 8
+              for (int j = j0; j < je; ++j) {  // the four rows as two packed pairs (as in the tiles above the diagonal)
+                const float q = (float)sx[j];
+                const f32x2 qq = pack2(q, q);
+                const f32x2 d01 = add2(qq, nx01), d23 = add2(qq, nx23);
+                float s0, s1, s2, s3;
+                unpack2(mul2(d01, d01), s0, s1);
+                unpack2(mul2(d23, d23), s2, s3);
+                acc[0] += (T)fast_exp2(-s0); acc[1] += (T)fast_exp2(-s1); acc[2] += (T)fast_exp2(-s2); acc[3] += (T)fast_exp2(-s3);
+              }
             } else {
 #pragma unroll 8
               for (int j = j0; j < je; ++j) {
