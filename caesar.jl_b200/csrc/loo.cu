@@ -115,6 +115,86 @@ template <typename T> __device__ __forceinline__ T lane_transpose_sum(T (&v)[32]
   return v[0];
 }
 
+// All pairs among up to 1024 sorted points held in shared memory (`sxs`, padded with a far sentinel up to a multiple of 256;
+// thread t owns rows t + 256 r, xi / acc in registers).  The points form up to four blocks of 256.  Pairs inside a block are
+// evaluated in full with the self term excluded (it sits in the 32-column group at the warp's own base); pairs between blocks
+// a < b are evaluated ONCE: k goes to the row of block a (register) and to the column of block b (lane transpose + per-warp
+// shared-memory slots `colacc` [warps][256], summed in fixed order by the thread that owns that row): 0.62 of the
+// exponentials at n = 1000.  WRAP = circular coordinate that may wrap (four more instructions per pair).
+template <typename T, bool WRAP>
+__device__ __forceinline__ void block_pairs_symmetric(const T* __restrict__ sxs, int n, const T (&xi)[kRI], T (&acc)[kRI], T period,
+                                                      T* __restrict__ colacc, int tid) {
+  const int tid_base = tid & ~31, lane = tid & 31, warp = tid >> 5;
+  const int nb = (n + kThreads - 1) / kThreads;
+#pragma unroll
+  for (int r = 0; r < kRI; ++r) {
+    if (r >= nb) break;
+    const int c0 = r * kThreads, c1 = min(n, c0 + kThreads);
+    for (int j0 = c0; j0 < c1; j0 += 32) {
+      const int je = min(j0 + 32, c1);
+      if (j0 - c0 == tid_base) {
+        for (int j = j0; j < je; ++j) {
+          T df = xi[r] - sxs[j];
+          if (WRAP) { T ad = fabs(df); df = fmin(ad, period - ad); }
+          T kv = fast_exp2(-(df * df));
+          acc[r] += (j == tid + c0) ? T(0) : kv;
+        }
+      } else {
+#pragma unroll 8
+        for (int j = j0; j < je; ++j) {
+          T df = xi[r] - sxs[j];
+          if (WRAP) { T ad = fabs(df); df = fmin(ad, period - ad); }
+          acc[r] += fast_exp2(-(df * df));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int bb = 1; bb < kRI; ++bb) {
+    if (bb >= nb) break;
+    const int c0 = bb * kThreads, ncol = min(n, c0 + kThreads) - c0;
+#pragma unroll
+    for (int aa = 0; aa < bb; ++aa) {
+      __syncthreads();  // colacc is free again
+      for (int j0 = 0; j0 < kThreads; j0 += 32) {
+        T v[32];
+        if constexpr (!WRAP && sizeof(T) == 4) {
+          // two columns per packed operation: (q_c, q_c+1) comes out of shared memory as one 64-bit broadcast load
+          const f32x2 nx = pack2(-(float)xi[aa], -(float)xi[aa]);
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            f32x2 qq;
+            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(qq) : "r"((uint32_t)__cvta_generic_to_shared(&sxs[c0 + j0 + c])));
+            const f32x2 d2 = add2(qq, nx);
+            float sa, sb;
+            unpack2(mul2(d2, d2), sa, sb);
+            v[c] = (T)fast_exp2(-sa);      // columns past n hold the far sentinel: exp2 -> 0
+            v[c + 1] = (T)fast_exp2(-sb);
+            acc[aa] += v[c];
+            acc[aa] += v[c + 1];
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            T df = xi[aa] - sxs[c0 + j0 + c];  // columns past n hold the far sentinel: exp2 -> 0 without the wrap
+            if (WRAP) { T ad = fabs(df); df = fmin(ad, period - ad); }
+            T kv = fast_exp2(-(df * df));
+            if (WRAP && j0 + c >= ncol) kv = T(0);
+            acc[aa] += kv;
+            v[c] = kv;
+          }
+        }
+        colacc[warp * kThreads + j0 + lane] = lane_transpose_sum(v, lane);
+      }
+      __syncthreads();
+      T t = T(0);
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) t += colacc[w * kThreads + tid];
+      acc[bb] += t;
+    }
+  }
+}
+
 // k(x_i, x_j) is symmetric: the CTA of row block I only visits column tiles J >= I.  The diagonal tile is evaluated in
 // full; for a tile above the diagonal every kernel value is added to its row (registers) AND to its column (lane
 // transpose + per-warp shared-memory slots, summed in fixed order), and the column sums are handed to the rows of
@@ -185,48 +265,8 @@ loo_rows_kernel(const LooProblem* __restrict__ probs, const LooState* __restrict
       }
       auto pairs = [&](auto wrap_c) {
         constexpr bool WRAP = decltype(wrap_c)::value;
-        if (diag) {  // all ordered pairs inside the block, self term excluded
-          // a warp's rows are tid_base + lane + 256 r: its self terms sit in the 32-column groups with
-          // (j0 - tid_base) % 256 == 0 only; every other group runs without the per-pair predicate (warp-uniform branch)
-          const int tid_base = tid & ~31;
-          for (int j0 = 0; j0 < jn; j0 += 32) {
-            const int je = min(j0 + 32, jn);
-            if (((j0 - tid_base) & (kThreads - 1)) == 0) {
-              for (int j = j0; j < je; ++j) {
-                const T q = sx[j];
-#pragma unroll
-                for (int r = 0; r < kRI; ++r) {
-                  T df = xi[r] - q;
-                  if (WRAP) { T ad = fabs(df); df = fmin(ad, period - ad); }
-                  T kv = fast_exp2(-(df * df));
-                  acc[r] += (cs + j == rowi[r]) ? T(0) : kv;
-                }
-              }
-            } else if constexpr (!WRAP && sizeof(T) == 4 && kRI == 4) {
-              const f32x2 nx01 = pack2(-(float)xi[0], -(float)xi[1]), nx23 = pack2(-(float)xi[2], -(float)xi[3]);
-#pragma unroll 8
-              for (int j = j0; j < je; ++j) {  // the four rows as two packed pairs (as in the tiles above the diagonal)
-                const float q = (float)sx[j];
-                const f32x2 qq = pack2(q, q);
-                const f32x2 d01 = add2(qq, nx01), d23 = add2(qq, nx23);
-                float s0, s1, s2, s3;
-                unpack2(mul2(d01, d01), s0, s1);
-                unpack2(mul2(d23, d23), s2, s3);
-                acc[0] += (T)fast_exp2(-s0); acc[1] += (T)fast_exp2(-s1); acc[2] += (T)fast_exp2(-s2); acc[3] += (T)fast_exp2(-s3);
-              }
-            } else {
-#pragma unroll 8
-              for (int j = j0; j < je; ++j) {
-                const T q = sx[j];
-#pragma unroll
-                for (int r = 0; r < kRI; ++r) {
-                  T df = xi[r] - q;
-                  if (WRAP) { T ad = fabs(df); df = fmin(ad, period - ad); }
-                  acc[r] += fast_exp2(-(df * df));
-                }
-              }
-            }
-          }
+        if (diag) {  // all pairs inside the block, self terms excluded, pairs between its 256-row sub-blocks evaluated once
+          block_pairs_symmetric<T, WRAP>(sx, jn, xi, acc, period, colacc, tid);
         } else {  // tile above the diagonal: the row block is complete (1024 valid rows); columns may be ragged
           // only the last 32-column group of a ragged tile needs the padding mask (circular case: the wrap would fold the
           // sentinel back into range); every other group runs without it
@@ -418,84 +458,8 @@ loo_small_kernel(const LooProblem* __restrict__ probs, const int* __restrict__ i
     T xi[kRI], acc[kRI];
 #pragma unroll
     for (int r = 0; r < kRI; ++r) { int row = tid + r * kThreads; xi[r] = sxs[row < N ? row : 0]; acc[r] = T(0); }
-    // The N points form up to four blocks of 256 (thread t owns row t of every block).  Pairs inside a block are evaluated in
-    // full with the self term excluded (it sits in the 32-column group at the warp's own base); pairs between blocks a < b are
-    // evaluated ONCE: k goes to the row of block a (register) and to the column of block b (lane transpose + per-warp
-    // shared-memory slots, summed in fixed order by the thread that owns that row).  0.62 of the exponentials at N = 1000.
-    // Compiled per topology: the wrap costs four instructions per pair; a sorted problem that spans less than pi never wraps.
-    auto sweep = [&](auto topo) {
-      constexpr bool CIRC = decltype(topo)::value;
-      const int tid_base = tid & ~31, lane = tid & 31, warp = tid >> 5;
-      const int nb = (N + kThreads - 1) / kThreads;
-#pragma unroll
-      for (int r = 0; r < kRI; ++r) {
-        if (r >= nb) break;
-        const int c0 = r * kThreads, c1 = min(N, c0 + kThreads);
-        for (int j0 = c0; j0 < c1; j0 += 32) {
-          const int je = min(j0 + 32, c1);
-          if (j0 - c0 == tid_base) {
-            for (int j = j0; j < je; ++j) {
-              T df = xi[r] - sxs[j];
-              if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
-              T kv = fast_exp2(-(df * df));
-              acc[r] += (j == tid + c0) ? T(0) : kv;
-            }
-          } else {
-#pragma unroll 8
-            for (int j = j0; j < je; ++j) {
-              T df = xi[r] - sxs[j];
-              if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
-              acc[r] += fast_exp2(-(df * df));
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int bb = 1; bb < kRI; ++bb) {
-        if (bb >= nb) break;
-        const int c0 = bb * kThreads, ncol = min(N, c0 + kThreads) - c0;
-#pragma unroll
-        for (int aa = 0; aa < bb; ++aa) {
-          __syncthreads();  // colacc is free again
-          for (int j0 = 0; j0 < kThreads; j0 += 32) {
-            T v[32];
-            if constexpr (!CIRC && sizeof(T) == 4) {
-              // two columns per packed operation: (q_c, q_c+1) comes out of shared memory as one 64-bit broadcast load
-              const f32x2 nx = pack2(-(float)xi[aa], -(float)xi[aa]);
-#pragma unroll
-              for (int c = 0; c < 32; c += 2) {
-                f32x2 qq;
-                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(qq) : "r"((uint32_t)__cvta_generic_to_shared(&sxs[c0 + j0 + c])));
-                const f32x2 d2 = add2(qq, nx);
-                float sa, sb;
-                unpack2(mul2(d2, d2), sa, sb);
-                v[c] = (T)fast_exp2(-sa);      // columns past N hold the far sentinel: exp2 -> 0
-                v[c + 1] = (T)fast_exp2(-sb);
-                acc[aa] += v[c];
-                acc[aa] += v[c + 1];
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                T df = xi[aa] - sxs[c0 + j0 + c];  // columns past N hold the far sentinel: exp2 -> 0 without the wrap
-                if (CIRC) { T ad = fabs(df); df = fmin(ad, period - ad); }
-                T kv = fast_exp2(-(df * df));
-                if (CIRC && j0 + c >= ncol) kv = T(0);
-                acc[aa] += kv;
-                v[c] = kv;
-              }
-            }
-            colacc[warp * kThreads + j0 + lane] = lane_transpose_sum(v, lane);
-          }
-          __syncthreads();
-          T t = T(0);
-#pragma unroll
-          for (int w = 0; w < kThreads / 32; ++w) t += colacc[w * kThreads + tid];
-          acc[bb] += t;
-        }
-      }
-    };
-    if (wraps) sweep(std::true_type{}); else sweep(std::false_type{});
+    if (wraps) block_pairs_symmetric<T, true>(sxs, N, xi, acc, period, colacc, tid);
+    else block_pairs_symmetric<T, false>(sxs, N, xi, acc, period, colacc, tid);
     double v = 0;
 #pragma unroll
     for (int r = 0; r < kRI; ++r)
