@@ -645,8 +645,9 @@ static void sym3_eigen(const double* Cin, double* eval, double* evec) { /* cycli
 }
 
 static double median_of(const double* v, int n, double* tmp) { /* Statistics.median: mean of the two middle values for even n */
-  memcpy(tmp, v, sizeof(double) * n);
-  qsort(tmp, n, sizeof(double), cmp_double);
+  if (n <= 0) return 0.0;
+  memcpy(tmp, v, sizeof(double) * (size_t)n);
+  qsort(tmp, (size_t)n, sizeof(double), cmp_double);
   return (n & 1) ? tmp[n / 2] : 0.5 * (tmp[n / 2 - 1] + tmp[n / 2]);
 }
 
