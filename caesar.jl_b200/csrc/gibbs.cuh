@@ -32,6 +32,7 @@ struct GibbsArgs {
 // CTA has 64 threads and seven CTAs share an SM, so the shared-memory footprint per CTA decides the occupancy)
 template <typename T> struct SMeta {
   uint32_t rec_off32[kMaxLev + 1];  // level record offsets in units of 32 elements (validate_and_plan aligns them)
+  uint32_t feat_off32;              // leaf feature tiles of the tensor-core path (units of 32 elements) or 0xffffffff
   long long perm_off;
   T bw2[CB2_MAX_DIM];
   float cmin[CB2_MAX_DIM], cmax[CB2_MAX_DIM];  // range of the stored circular coordinates over all levels
@@ -399,6 +400,155 @@ __device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta<
   }
 }
 
+// ---- leaf level on the tensor cores (FP32, d = 6, CTA-wide wrap-free passes; compiled in with -DCB2_GIBBS_TC=1) ----------------
+// The leaf score is bilinear in per-chain coefficients and per-leaf features:
+//   log2 w - sum_i (a_i x_i - b_i)^2 = [x_i^2 (6), x_i (6), 1, log2 w, 0, 0] . [-a_i^2 (6), 2 a_i b_i (6), -sum b_i^2, 1, 0, 0],
+// a 128-chain x 64-leaf x 16 product per feature tile.  Both operands are split into TF32 hi + lo parts and three products
+// (hi.hi + hi.lo + lo.hi) are accumulated in FP32 in tensor memory: tcgen05.mma kind::tf32, M = 128, N = 64, K = 8, six
+// instructions per tile issued by one thread; operands K-major without swizzle (8 x 16-byte core matrices, LBO = 128 B between
+// the K halves, SBO = 512 B between 8-row groups).  The feature tiles come from the tree build (product.cu, kTcTile) by the same
+// 1-D bulk copies as the records; every thread writes its chain's coefficient row into shared memory once per pass.  Each
+// chain then reads ITS row of the accumulator (TMEM lane = thread) with tcgen05.ld and continues with the usual running-max /
+// chunk-sum bookkeeping: no per-thread record loads and one FADD instead of twelve FMA-pipe instructions per evaluation.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+               "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct TcState {
+  float* sA;          // [2][128 x 16] coefficient rows, hi then lo (canonical operand layout)
+  uint64_t* mbars;    // [2] MMA-complete barriers
+  uint32_t tmem;      // base of this CTA's 128 accumulator columns (two 64-column buffers)
+  uint32_t mu0, mu1;  // completed uses of the two MMA barriers (phase parity)
+};
+
+template <typename T, int DIM>
+__device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int cnt, int CH, const ChainConst<T, DIM>& cc, bool uniform,
+                                             unsigned char* smem_tiles, int tile_bytes, uint64_t* bars, uint32_t& use0, uint32_t& use1,
+                                             TcState& tc, float* __restrict__ chunk, int tid, float& m, float& csum, int& cidx) {
+  // ---- this chain's coefficient row, split hi / lo, into the A operand
+  {
+    float u[16];
+    float sb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float a = (float)cc.a[i], b = (float)cc.b[i];
+      u[i] = -a * a; u[6 + i] = 2.f * a * b; sb = fmaf(b, b, sb);
+    }
+    // with uniform weights log2 w is the same for every leaf and is dropped, exactly as score_leaf<UW> does (pass 2 must see
+    // the same reference); the padding leaves of the last tile are masked below instead of relying on their log2 w = -1e30
+    u[12] = -sb; u[13] = uniform ? 0.f : 1.f; u[14] = 0.f; u[15] = 0.f;
+    float* rowp = tc.sA + (tid >> 3) * 128 + (tid & 7) * 4;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float hi = tf32_round(u[k]);
+      rowp[(k >> 2) * 32 + (k & 3)] = hi;
+      rowp[2048 + (k >> 2) * 32 + (k & 3)] = tf32_round(u[k] - hi);
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const int ntl = (cnt + kTcTile - 1) / kTcTile;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcTile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t sA_hi = smem_u32(tc.sA), sA_lo = sA_hi + 8192;
+  auto load_tile = [&](int t) {  // thread 0: one bulk copy of 8 KB (hi + lo parts of 64 leaves)
+    const int b = t & 1;
+    mbar_expect_tx(&bars[b], (uint32_t)(kTcTileFloats * 4));
+    tma_load_1d(smem_tiles + b * tile_bytes, feat + (size_t)t * kTcTileFloats, (uint32_t)(kTcTileFloats * 4), &bars[b]);
+  };
+  auto issue_mma = [&](int t) {  // thread 0: wait for the tile, six MMAs into accumulator buffer t & 1, commit
+    const int b = t & 1;
+    mbar_wait(&bars[b], ((b ? use1 : use0) + (uint32_t)(t >> 1)) & 1);  // tile t is the (t >> 1)-th use of buffer b in this pass
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t sB_hi = smem_u32(smem_tiles + b * tile_bytes), sB_lo = sB_hi + 4096;
+    const uint32_t d = tc.tmem + (uint32_t)(b * kTcTile);
+    umma_tf32(d, umma_desc(sA_hi, 128, 512), umma_desc(sB_hi, 128, 512), idesc, 0u);
+    umma_tf32(d, umma_desc(sA_hi + 256, 128, 512), umma_desc(sB_hi + 256, 128, 512), idesc, 1u);
+    umma_tf32(d, umma_desc(sA_hi, 128, 512), umma_desc(sB_lo, 128, 512), idesc, 1u);
+    umma_tf32(d, umma_desc(sA_hi + 256, 128, 512), umma_desc(sB_lo + 256, 128, 512), idesc, 1u);
+    umma_tf32(d, umma_desc(sA_lo, 128, 512), umma_desc(sB_hi, 128, 512), idesc, 1u);
+    umma_tf32(d, umma_desc(sA_lo + 256, 128, 512), umma_desc(sB_hi + 256, 128, 512), idesc, 1u);
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&tc.mbars[b])) : "memory");
+  };
+  if (tid == 0) {
+    load_tile(0);
+    if (ntl > 1) load_tile(1);
+    issue_mma(0);
+  }
+  float nm = -m;
+  const uint32_t lane_base = (uint32_t)((tid >> 5) * 32) << 16;
+  for (int t = 0; t < ntl; ++t) {
+    const int b = t & 1;
+    if (tid == 0 && t + 1 < ntl) issue_mma(t + 1);  // the tensor core works on the next tile while this one is summed
+    mbar_wait(&tc.mbars[b], (b ? tc.mu1 : tc.mu0) & 1);
+    if (b) ++tc.mu1; else ++tc.mu0;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0 && t + 2 < ntl) load_tile(t + 2);   // MMA(t) is complete: its shared-memory tile may be refilled
+#pragma unroll
+    for (int c0 = 0; c0 < kTcTile; c0 += 32) {
+      if (t * kTcTile + c0 >= cnt) break;  // only padding leaves left
+      uint32_t r[32];
+      const uint32_t taddr = tc.tmem + lane_base + (uint32_t)(b * kTcTile + c0);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int g0 = 0; g0 < 32; g0 += kG) {
+        const int z = t * kTcTile + c0 + g0;
+        if (z >= cnt) break;
+        float e[kG];
+#pragma unroll
+        for (int g = 0; g < kG; ++g) e[g] = (z + g < cnt) ? __uint_as_float(r[g0 + g]) + nm : -INFINITY;
+        float gm = e[0];
+#pragma unroll
+        for (int g = 1; g < kG; ++g) gm = fmaxf(gm, e[g]);
+        if (gm > 60.f) {  // rare: raise the reference (same rule as tile_pass)
+          if (nm == INFINITY) {
+#pragma unroll
+            for (int g = 0; g < kG; ++g) e[g] = (z + g < cnt) ? __uint_as_float(r[g0 + g]) : -INFINITY;
+            gm = e[0];
+#pragma unroll
+            for (int g = 1; g < kG; ++g) gm = fmaxf(gm, e[g]);
+            m = gm;
+          } else {
+            const float sc = fast_exp2(-gm);
+            csum *= sc;
+            for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
+            m += gm;
+          }
+#pragma unroll
+          for (int g = 0; g < kG; ++g) e[g] -= gm;
+          nm = -m;
+        }
+#pragma unroll
+        for (int g = 0; g < kG; ++g) csum += fast_exp2(e[g]);
+        if (((z + kG) & (CH - 1)) == 0 && z + kG <= cnt) { chunk[cidx * kS + tid] = csum; csum = 0.f; ++cidx; }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // accumulator buffer b is free for MMA(t + 2)
+  }
+  // every thread keeps the phase counters of the bulk-copy barriers in step (only thread 0 waited on them here)
+  use0 += (uint32_t)((ntl + 1) >> 1);
+  use1 += (uint32_t)(ntl >> 1);
+}
+
 #ifdef CB2_GIBBS_PROF
 #define GIBBS_T(slot) do { long long t_ = clock64(); gprof[slot] += t_ - glast; glast = t_; } while (0)
 #else
@@ -422,6 +572,17 @@ gibbs_kernel(const GibbsArgs a) {
   ind_t* ind_s = reinterpret_cast<ind_t*>(chunk + kNCH * kS);                  // [CB2_MAX_DENS][kS]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ind_s + CB2_MAX_DENS * kS);    // [2]
   SMeta<T>* sm = reinterpret_cast<SMeta<T>*>(bars + 2);                        // [CB2_MAX_DENS]
+  constexpr bool kTC = CB2_GIBBS_TC && DIM == 6 && sizeof(T) == 4 && R == 1;   // tensor-core leaf passes (leaf_pass_tc)
+  TcState tc;
+  uint32_t* tmem_slot = nullptr;
+  if constexpr (kTC) {
+    unsigned char* after = reinterpret_cast<unsigned char*>(sm + CB2_MAX_DENS);
+    after = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(after) + 127) & ~(uintptr_t)127);
+    tc.sA = reinterpret_cast<float*>(after);
+    tc.mbars = reinterpret_cast<uint64_t*>(after + 16384);
+    tmem_slot = reinterpret_cast<uint32_t*>(after + 16384 + 16);
+    tc.mu0 = tc.mu1 = 0;
+  }
 
   const int tid = threadIdx.x;
   const Work wk = a.work[blockIdx.x];
@@ -444,12 +605,21 @@ gibbs_kernel(const GibbsArgs a) {
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    if constexpr (kTC) { mbar_init(&tc.mbars[0], 1); mbar_init(&tc.mbars[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if constexpr (kTC) {
+    if (tid < 32) {  // 128 accumulator columns (two 64-leaf buffers); four CTAs share the SM's 512
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   if (tid < D) {
     const DensMeta& dm = a.metas[prp->dens[tid]];
     SMeta<T> m;
     for (int l = 0; l <= kMaxLev; ++l) m.rec_off32[l] = (uint32_t)(dm.rec_off[l] >> 5);
+    m.feat_off32 = dm.feat_off >= 0 ? (uint32_t)(dm.feat_off >> 5) : 0xffffffffu;
     m.perm_off = dm.perm_off;
     for (int i = 0; i < CB2_MAX_DIM; ++i) m.bw2[i] = (T)(dm.bw[i] * dm.bw[i]);
     m.N = dm.N; m.depth = dm.depth; m.uniform = dm.w == nullptr;
@@ -463,6 +633,10 @@ gibbs_kernel(const GibbsArgs a) {
 #pragma unroll
     for (int r = 0; r < R; ++r) ind_s[k * kS + col[r]] = 0;
   __syncthreads();
+  if constexpr (kTC) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc.tmem = *tmem_slot;
+  }
   uint32_t use0 = 0, use1 = 0;  // completed uses of each tile buffer (phase parity)
 #ifdef CB2_GIBBS_PROF
   long long gprof[6] = {0, 0, 0, 0, 0, 0}, glast = clock64();
@@ -532,12 +706,23 @@ gibbs_kernel(const GibbsArgs a) {
 #pragma unroll
         for (int r = 0; r < R; ++r) { m[r] = -INFINITY; csum[r] = T(0); }
         int cidx = 0;
-        if (tid == 0) {
+        bool done_tc = false;
+        if constexpr (kTC) {
+          if (leaf && dj.feat_off32 != 0xffffffffu) {  // CTA-uniform conditions: every thread reaches the vote
+            const bool cta_flat = circ == 0u || __syncthreads_and(nowrap ? 1 : 0) != 0;
+            if (cta_flat) {
+              leaf_pass_tc<T, DIM>(reinterpret_cast<const float*>(pool) + (size_t)dj.feat_off32 * 32, cnt, CH, cc[0], dj.uniform != 0, smem_raw, TILE_BYTES,
+                                   bars, use0, use1, tc, reinterpret_cast<float*>(chunk), tid, m[0], csum[0], cidx);
+              done_tc = true;
+            }
+          }
+        }
+        if (!done_tc && tid == 0) {
           uint32_t bytes = (uint32_t)(min(TN, cnt) * rec * (int)sizeof(T));
           mbar_expect_tx(&bars[0], bytes);
           tma_load_1d(tile[0], lrec, bytes, &bars[0]);
         }
-        for (int t = 0; t < ntiles; ++t) {
+        for (int t = 0; t < (done_tc ? 0 : ntiles); ++t) {
           const int b = t & 1;
           if (tid == 0 && t + 1 < ntiles) {
             int n1 = min(TN, cnt - (t + 1) * TN);
@@ -634,9 +819,15 @@ gibbs_kernel(const GibbsArgs a) {
       for (int k = 0; k < D; ++k) labels[(size_t)s * D + k] = a.int_pool[sm[k].perm_off + ind_s[k * kS + col[r]]];
     }
   }
+  if constexpr (kTC) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tc.tmem), "r"(128u));
+  }
 }
 
 template <typename T, int DIM> size_t gibbs_smem_bytes() {
   return 2 * (size_t)gibbs_tile_bytes<T, DIM>() + sizeof(T) * kNCH * kS + sizeof(ind_t) * CB2_MAX_DENS * kS + 16 +
-         sizeof(SMeta<T>) * CB2_MAX_DENS + 64;
+         sizeof(SMeta<T>) * CB2_MAX_DENS + 64 +
+         ((CB2_GIBBS_TC && DIM == 6 && sizeof(T) == 4) ? (size_t)(16384 + 128 + 64) : 0);  // coefficient rows, MMA barriers, TMEM slot
 }

@@ -56,6 +56,16 @@ __host__ __device__ inline int node_of(int N, int l, int p) {
   return k;
 }
 
+// ---- tensor-core leaf scoring (FP32, d = 6; gibbs.cuh `leaf_pass_tc`): per message a block of leaf FEATURE tiles in the node
+// pool.  A tile = 64 leaves x 16 features [x_i^2 (6), x_i (6), 1, log2 w, 0, 0], split into TF32 hi and lo parts, each laid out
+// as the K-major no-swizzle operand of tcgen05.mma (8 x 16-byte core matrices: [leaf/8][k/4][leaf%8][k%4]).
+#ifndef CB2_GIBBS_TC
+#define CB2_GIBBS_TC 1
+#endif
+constexpr int kTcTile = 64;                     // leaves per feature tile (= N of one MMA)
+constexpr int kTcTileFloats = 2 * kTcTile * 16; // hi + lo
+__host__ __device__ inline bool tc_enabled(int d, bool f32) { return CB2_GIBBS_TC && f32 && d == 6; }
+
 struct DensMeta {
   const double* pts;  // d x N device Float64
   const double* w;    // N or null
@@ -63,6 +73,7 @@ struct DensMeta {
   int N, depth;
   long long rec_off[kMaxLev + 1];  // element offset of each level's records in the node pool
   long long perm_off;              // offset in the int pool
+  long long feat_off;              // element offset of the leaf feature tiles in the node pool (tensor-core path) or -1
   const double* center;            // d values (device): Euclidean coordinates are stored relative to this point
 };
 
@@ -78,6 +89,12 @@ struct ProdDev {
 struct Work { int prod, s0; };
 
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 __device__ __forceinline__ unsigned long long ordered_bits(double v) {
   unsigned long long b = (unsigned long long)__double_as_longlong(v);
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
@@ -309,6 +326,32 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
       for (int i = d; i < RECL; ++i) rec[(size_t)p * RECL + i] = T(0);
       rec[(size_t)p * RECL + d] = (T)(wt > 0 ? log2(wt) : -1e30);
     }
+    if (m.feat_off >= 0 && d == 6) {  // tensor-core leaf path: feature tiles (see kTcTile), built from the stored FP32 values
+      float* feat = reinterpret_cast<float*>(node_pool + m.feat_off);
+      const int npad = (N + kTcTile - 1) / kTcTile * kTcTile;
+      for (int p = tid; p < npad; p += nthr) {
+        double f[16];
+        if (p < N) {
+          for (int i = 0; i < 6; ++i) {
+            const double xf = (double)(float)rec[(size_t)p * RECL + i];
+            f[i] = xf * xf; f[6 + i] = xf;
+          }
+          f[12] = 1.0; f[13] = (double)(float)rec[(size_t)p * RECL + d]; f[14] = 0.0; f[15] = 0.0;
+        } else {  // padding leaf of the last tile: weight 2^-1e30 = 0
+          for (int k = 0; k < 16; ++k) f[k] = 0.0;
+          f[13] = -1e30;
+        }
+        float* tile = feat + (size_t)(p / kTcTile) * kTcTileFloats;
+        const int r = p % kTcTile;
+        for (int k = 0; k < 16; ++k) {
+          const float hi = tf32_rna((float)f[k]);
+          const float lo = tf32_rna((float)(f[k] - (double)hi));
+          const int off = (r >> 3) * 128 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3);
+          tile[off] = hi;
+          tile[kTcTile * 16 + off] = lo;
+        }
+      }
+    }
   }
   __syncthreads();
   TREE_T(4);
@@ -517,6 +560,11 @@ int validate_and_plan(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const 
         m.rec_off[l] = (long long)pl.node_elems;
         pl.node_elems += (size_t)level_count(dn.N, m.depth, l) * (l < m.depth ? RECN : RECL);
         pl.node_elems = (pl.node_elems + 31) / 32 * 32;  // keep every level 128-byte aligned for the bulk copies
+      }
+      m.feat_off = -1;
+      if (tc_enabled(d, ctx->precision == CB2_FP32)) {
+        m.feat_off = (long long)pl.node_elems;
+        pl.node_elems += (size_t)((dn.N + kTcTile - 1) / kTcTile) * kTcTileFloats;
       }
       int nodes = (1 << m.depth) + dn.N;
       if (nodes > pl.max_nodes) pl.max_nodes = nodes;
