@@ -514,7 +514,11 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
         if (z >= cnt) break;
         float e[kG];
 #pragma unroll
-        for (int g = 0; g < kG; ++g) e[g] = (z + g < cnt) ? __uint_as_float(r[g0 + g]) + nm : -INFINITY;
+        for (int g = 0; g < kG; ++g) e[g] = __uint_as_float(r[g0 + g]) + nm;
+        if (z + kG > cnt) {  // the group that straddles the end of the level: padding leaves carry no mass
+#pragma unroll
+          for (int g = 0; g < kG; ++g) if (z + g >= cnt) e[g] = -INFINITY;
+        }
         float gm = e[0];
 #pragma unroll
         for (int g = 1; g < kG; ++g) gm = fmaxf(gm, e[g]);
