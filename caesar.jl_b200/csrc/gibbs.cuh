@@ -460,16 +460,17 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
   const int ntl = (cnt + kTcTile - 1) / kTcTile;
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcTile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint32_t sA_hi = smem_u32(tc.sA), sA_lo = sA_hi + 8192;
-  auto load_tile = [&](int t) {  // thread 0: one bulk copy of 8 KB (hi + lo parts of 64 leaves)
-    const int b = t & 1;
+  constexpr bool kSingle = kTcTile == 128;  // one 16 KB tile and one 128-column accumulator instead of two of each
+  auto load_tile = [&](int t) {  // thread 0: one bulk copy (hi + lo parts of kTcTile leaves)
+    const int b = kSingle ? 0 : (t & 1);
     mbar_expect_tx(&bars[b], (uint32_t)(kTcTileFloats * 4));
     tma_load_1d(smem_tiles + b * tile_bytes, feat + (size_t)t * kTcTileFloats, (uint32_t)(kTcTileFloats * 4), &bars[b]);
   };
   auto issue_mma = [&](int t) {  // thread 0: wait for the tile, six MMAs into accumulator buffer t & 1, commit
-    const int b = t & 1;
-    mbar_wait(&bars[b], ((b ? use1 : use0) + (uint32_t)(t >> 1)) & 1);  // tile t is the (t >> 1)-th use of buffer b in this pass
+    const int b = kSingle ? 0 : (t & 1);
+    mbar_wait(&bars[b], ((b ? use1 : use0) + (uint32_t)(kSingle ? t : (t >> 1))) & 1);  // use count of buffer b within this pass
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t sB_hi = smem_u32(smem_tiles + b * tile_bytes), sB_lo = sB_hi + 4096;
+    const uint32_t sB_hi = smem_u32(smem_tiles + b * tile_bytes), sB_lo = sB_hi + kTcTile * 64;
     const uint32_t d = tc.tmem + (uint32_t)(b * kTcTile);
     umma_tf32(d, umma_desc(sA_hi, 128, 512), umma_desc(sB_hi, 128, 512), idesc, 0u);
     umma_tf32(d, umma_desc(sA_hi + 256, 128, 512), umma_desc(sB_hi + 256, 128, 512), idesc, 1u);
@@ -481,18 +482,18 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
   };
   if (tid == 0) {
     load_tile(0);
-    if (ntl > 1) load_tile(1);
+    if (!kSingle && ntl > 1) load_tile(1);
     issue_mma(0);
   }
   float nm = -m;
   const uint32_t lane_base = (uint32_t)((tid >> 5) * 32) << 16;
   for (int t = 0; t < ntl; ++t) {
-    const int b = t & 1;
-    if (tid == 0 && t + 1 < ntl) issue_mma(t + 1);  // the tensor core works on the next tile while this one is summed
+    const int b = kSingle ? 0 : (t & 1);
+    if (!kSingle && tid == 0 && t + 1 < ntl) issue_mma(t + 1);  // the tensor core works on the next tile while this one is summed
     mbar_wait(&tc.mbars[b], (b ? tc.mu1 : tc.mu0) & 1);
     if (b) ++tc.mu1; else ++tc.mu0;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == 0 && t + 2 < ntl) load_tile(t + 2);   // MMA(t) is complete: its shared-memory tile may be refilled
+    if (tid == 0 && t + (kSingle ? 1 : 2) < ntl) load_tile(t + (kSingle ? 1 : 2));   // MMA(t) is complete: its tile may be refilled
 #pragma unroll
     for (int c0 = 0; c0 < kTcTile; c0 += 32) {
       if (t * kTcTile + c0 >= cnt) break;  // only padding leaves left
@@ -547,10 +548,11 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();  // accumulator buffer b is free for MMA(t + 2)
+    if (kSingle && tid == 0 && t + 1 < ntl) issue_mma(t + 1);
   }
   // every thread keeps the phase counters of the bulk-copy barriers in step (only thread 0 waited on them here)
-  use0 += (uint32_t)((ntl + 1) >> 1);
-  use1 += (uint32_t)(ntl >> 1);
+  use0 += (uint32_t)(kSingle ? ntl : ((ntl + 1) >> 1));
+  use1 += (uint32_t)(kSingle ? 0 : (ntl >> 1));
 }
 
 #ifdef CB2_GIBBS_PROF

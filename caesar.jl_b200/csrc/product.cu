@@ -62,7 +62,10 @@ __host__ __device__ inline int node_of(int N, int l, int p) {
 #ifndef CB2_GIBBS_TC
 #define CB2_GIBBS_TC 1
 #endif
-constexpr int kTcTile = 64;                     // leaves per feature tile (= N of one MMA)
+#ifndef CB2_TC_TILE
+#define CB2_TC_TILE 128
+#endif
+constexpr int kTcTile = CB2_TC_TILE;            // leaves per feature tile (= N of one MMA): 64 double-buffered, 128 single-buffered
 constexpr int kTcTileFloats = 2 * kTcTile * 16; // hi + lo
 __host__ __device__ inline bool tc_enabled(int d, bool f32) { return CB2_GIBBS_TC && f32 && d == 6; }
 
