@@ -494,7 +494,7 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
     if (b) ++tc.mu1; else ++tc.mu0;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (tid == 0 && t + (kSingle ? 1 : 2) < ntl) load_tile(t + (kSingle ? 1 : 2));   // MMA(t) is complete: its tile may be refilled
-#pragma unroll
+#pragma unroll 1  // one copy of the 32-leaf body: the kernel is large enough to miss in the instruction cache
     for (int c0 = 0; c0 < kTcTile; c0 += 32) {
       if (t * kTcTile + c0 >= cnt) break;  // only padding leaves left
       uint32_t r[32];
