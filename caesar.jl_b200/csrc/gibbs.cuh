@@ -740,10 +740,14 @@ gibbs_kernel(const GibbsArgs a) {
           if (b) ++use1; else ++use0;
           const int nt = min(TN, cnt - t * TN);
           const T* tb = reinterpret_cast<const T*>(smem_raw + b * TILE_BYTES);
-          if (flat) {  // Euclidean arithmetic on every coordinate: same values as the wrapped form, fewer instructions
+          // with the tensor-core leaf pass compiled in, the packed leaf loops would only serve warp-flat passes of CTAs that are
+          // not flat as a whole: they take the wrapped loops instead and the kernel stays smaller (instruction cache)
+          if (flat && !(kTC && leaf)) {  // Euclidean arithmetic on every coordinate: same values as the wrapped form, fewer instructions
             if (!leaf) tile_pass<T, DIM, 0, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
-            else if (!dj.uniform) tile_pass<T, DIM, 1, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
-            else tile_pass<T, DIM, 2, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
+            else if constexpr (!kTC) {
+              if (!dj.uniform) tile_pass<T, DIM, 1, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
+              else tile_pass<T, DIM, 2, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
+            }
           } else {
             if (!leaf) tile_pass<T, DIM, 0, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
             else if (!dj.uniform) tile_pass<T, DIM, 1, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
@@ -779,10 +783,12 @@ gibbs_kernel(const GibbsArgs a) {
           GIBBS_T(4);
           // pass 2 must reproduce the scores of pass 1 bit for bit, so it takes the same (packed or wrapped) scorer
           int pick;
-          if (flat) {
-            pick = !leaf ? chunk_pick<T, DIM, 0, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
-                         : (!dj.uniform ? chunk_pick<T, DIM, 1, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
-                                        : chunk_pick<T, DIM, 2, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt));
+          if (flat && !(kTC && leaf)) {
+            if (!leaf) pick = chunk_pick<T, DIM, 0, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
+            else if constexpr (!kTC) {
+              pick = !dj.uniform ? chunk_pick<T, DIM, 1, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
+                                 : chunk_pick<T, DIM, 2, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
+            } else pick = z0;
           } else {
             pick = !leaf ? chunk_pick<T, DIM, 0, false>(lrec, z0, z1, cc[r], pc[r], circ, m[r], cum, tgt)
                          : (!dj.uniform ? chunk_pick<T, DIM, 1, false>(lrec, z0, z1, cc[r], pc[r], circ, m[r], cum, tgt)
