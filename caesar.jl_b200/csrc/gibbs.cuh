@@ -252,6 +252,12 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
   constexpr int NT = kS / R;   // threads per CTA; chain r of this thread is column r * NT + tid of the per-chain arrays
   constexpr int G = kG / R;    // candidates scored together: G * R independent evaluations in flight
   const int ntg = nt & ~(kG - 1);
+  if (zbase == 0) {  // the reference starts at the score of the level's first candidate (any finite score works; it is raised lazily)
+    RecR<T, REC, PACK> rec0;
+    load_recr<true>(tb, rec0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) m[r] = score_regs<T, DIM, MODE, PACK>(rec0, cc[r], pc[r], circ, T(0));
+  }
   T nm[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) nm[r] = -m[r];
@@ -270,23 +276,10 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
 #pragma unroll
       for (int g = 1; g < G; ++g) gm = fmax(gm, e[r][g]);
       if (gm > T(60)) {  // rare: raise the reference by gm and rescale what has been summed so far
-        if (nm[r] == INFINITY) {  // first group of the pass: scores were computed against m = -inf, nothing summed yet
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            RecR<T, REC, PACK> rec;
-            load_recr<true>(tb + (z + g) * REC, rec);
-            e[r][g] = score_regs<T, DIM, MODE, PACK>(rec, cc[r], pc[r], circ, T(0));
-          }
-          gm = e[r][0];
-#pragma unroll
-          for (int g = 1; g < G; ++g) gm = fmax(gm, e[r][g]);
-          m[r] = gm;
-        } else {
-          T sc = fast_exp2(-gm);
-          csum[r] *= sc;
-          for (int c = 0; c < cidx; ++c) chunk[c * kS + r * NT + tid] *= sc;
-          m[r] += gm;
-        }
+        T sc = fast_exp2(-gm);
+        csum[r] *= sc;
+        for (int c = 0; c < cidx; ++c) chunk[c * kS + r * NT + tid] *= sc;
+        m[r] += gm;
 #pragma unroll
         for (int g = 0; g < G; ++g) e[r][g] -= gm;
         nm[r] = -m[r];
@@ -307,13 +300,10 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
     for (int r = 0; r < R; ++r) {
       T e = score_regs<T, DIM, MODE, PACK>(rec, cc[r], pc[r], circ, nm[r]);
       if (e > T(60)) {
-        if (nm[r] == INFINITY) { e = score_regs<T, DIM, MODE, PACK>(rec, cc[r], pc[r], circ, T(0)); m[r] = e; }
-        else {
-          T sc = fast_exp2(-e);
-          csum[r] *= sc;
-          for (int c = 0; c < cidx; ++c) chunk[c * kS + r * NT + tid] *= sc;
-          m[r] += e;
-        }
+        T sc = fast_exp2(-e);
+        csum[r] *= sc;
+        for (int c = 0; c < cidx; ++c) chunk[c * kS + r * NT + tid] *= sc;
+        m[r] += e;
         e = T(0);
         nm[r] = -m[r];
       }
@@ -509,6 +499,7 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
             "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (t == 0 && c0 == 0) { m = __uint_as_float(r[0]); nm = -m; }  // the reference starts at the level's first leaf
 #pragma unroll
       for (int g0 = 0; g0 < 32; g0 += kG) {
         const int z = t * kTcTile + c0 + g0;
@@ -524,19 +515,10 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
 #pragma unroll
         for (int g = 1; g < kG; ++g) gm = fmaxf(gm, e[g]);
         if (gm > 60.f) {  // rare: raise the reference (same rule as tile_pass)
-          if (nm == INFINITY) {
-#pragma unroll
-            for (int g = 0; g < kG; ++g) e[g] = (z + g < cnt) ? __uint_as_float(r[g0 + g]) : -INFINITY;
-            gm = e[0];
-#pragma unroll
-            for (int g = 1; g < kG; ++g) gm = fmaxf(gm, e[g]);
-            m = gm;
-          } else {
-            const float sc = fast_exp2(-gm);
-            csum *= sc;
-            for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
-            m += gm;
-          }
+          const float sc = fast_exp2(-gm);
+          csum *= sc;
+          for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
+          m += gm;
 #pragma unroll
           for (int g = 0; g < kG; ++g) e[g] -= gm;
           nm = -m;
@@ -710,7 +692,7 @@ gibbs_kernel(const GibbsArgs a) {
         // ---- pass 1: chunk partial sums of exp2(e - m), m = running (lazily raised) reference maximum
         T m[R], csum[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) { m[r] = -INFINITY; csum[r] = T(0); }
+        for (int r = 0; r < R; ++r) { m[r] = T(0); csum[r] = T(0); }  // m is set from the level's first candidate (tile_pass / leaf_pass_tc)
         int cidx = 0;
         bool done_tc = false;
         if constexpr (kTC) {
