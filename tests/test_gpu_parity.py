@@ -499,3 +499,22 @@ def test_product_fp32_six_dimensional_packed_paths(cb, ctx32, circ, weighted):
             if c:
                 diff[:, i] = (diff[:, i] + np.pi) % (2 * np.pi) - np.pi
         assert np.abs(diff).max() < 5e-5   # same labels, same normal draws: FP32 arithmetic on the final mean only
+
+
+@pytest.mark.parametrize("D,N", [(2, 64), (2, 100), (3, 1024), (2, 4096), (8, 513)])
+def test_product_fp32_tensor_core_leaf_pass_follows_the_oracle_chains(cb, ctx32, D, N):
+    """FP32 d = 6 wrap-free leaf passes run on the tensor cores (tcgen05.mma kind::tf32 with a 3 x TF32 split, accumulators in
+    TMEM; gibbs.cuh leaf_pass_tc): tile counts 1, partial, many; the chains must still select the oracle's labels (same uniforms,
+    scores equal to ~1e-6) -- including Pose3 beliefs away from the +-pi cut and per-kernel weights."""
+    rng = np.random.default_rng(100 + D + N)
+    for circ, weighted in (((0,) * 6, False), ((0, 0, 0, 1, 1, 1), True)):
+        dens = []
+        for j in range(D):
+            pts = rng.normal(size=(N, 6)) * 0.5 + rng.normal(size=6) * 0.2
+            w = rng.uniform(0.2, 1.0, size=N) if weighted else None
+            dens.append((pts, np.full(6, 0.3) if N < 1000 else np.full(6, 0.2), w))
+        pts, lab = cb.product_points(dens, circ, 384, seed=3, ctx=ctx32)
+        opts, olab = oracle.product(dens, 384, seed=3, circular=list(circ), ubits=24)
+        same = (lab == olab).all(axis=1)
+        assert same.mean() > 0.97, (D, N, circ, weighted, same.mean())
+        assert np.abs(pts[same] - opts[same]).max() < 5e-5
