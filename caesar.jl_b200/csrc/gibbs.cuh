@@ -425,6 +425,10 @@ template <typename T, int DIM>
 __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int cnt, int CH, const ChainConst<T, DIM>& cc, bool uniform,
                                              unsigned char* smem_tiles, int tile_bytes, uint64_t* bars, uint32_t& use0, uint32_t& use1,
                                              TcState& tc, float* __restrict__ chunk, int tid, float& m, float& csum, int& cidx) {
+  if (tid == 0) {  // the first feature tile travels while the coefficient rows are written
+    mbar_expect_tx(&bars[0], (uint32_t)(kTcTileFloats * 4));
+    tma_load_1d(smem_tiles, feat, (uint32_t)(kTcTileFloats * 4), &bars[0]);
+  }
   // ---- this chain's coefficient row, split hi / lo, into the A operand
   {
     float u[16];
@@ -471,7 +475,6 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&tc.mbars[b])) : "memory");
   };
   if (tid == 0) {
-    load_tile(0);
     if (!kSingle && ntl > 1) load_tile(1);
     issue_mma(0);
   }
