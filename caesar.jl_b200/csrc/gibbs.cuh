@@ -480,11 +480,20 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
   }
   float nm = -m;
   const uint32_t lane_base = (uint32_t)((tid >> 5) * 32) << 16;
+#ifdef CB2_TC_PROF
+  long long pw = 0, pl = 0, pc_ = 0, ps = 0, p0;
+#endif
   for (int t = 0; t < ntl; ++t) {
+#ifdef CB2_TC_PROF
+    p0 = clock64();
+#endif
     const int b = kSingle ? 0 : (t & 1);
     if (!kSingle && tid == 0 && t + 1 < ntl) issue_mma(t + 1);  // the tensor core works on the next tile while this one is summed
     mbar_wait(&tc.mbars[b], (b ? tc.mu1 : tc.mu0) & 1);
     if (b) ++tc.mu1; else ++tc.mu0;
+#ifdef CB2_TC_PROF
+    pw += clock64() - p0; p0 = clock64();
+#endif
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (tid == 0 && t + (kSingle ? 1 : 2) < ntl) load_tile(t + (kSingle ? 1 : 2));   // MMA(t) is complete: its tile may be refilled
 #pragma unroll 1  // one copy of the 32-leaf body: the kernel is large enough to miss in the instruction cache
@@ -502,6 +511,9 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
             "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#ifdef CB2_TC_PROF
+      pl += clock64() - p0; p0 = clock64();
+#endif
       if (t == 0 && c0 == 0) { m = __uint_as_float(r[0]); nm = -m; }  // the reference starts at the level's first leaf
 #pragma unroll
       for (int g0 = 0; g0 < 32; g0 += kG) {
@@ -530,11 +542,20 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
         for (int g = 0; g < kG; ++g) csum += fast_exp2(e[g]);
         if (((z + kG) & (CH - 1)) == 0 && z + kG <= cnt) { chunk[cidx * kS + tid] = csum; csum = 0.f; ++cidx; }
       }
+#ifdef CB2_TC_PROF
+      pc_ += clock64() - p0; p0 = clock64();
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();  // accumulator buffer b is free for MMA(t + 2)
     if (kSingle && tid == 0 && t + 1 < ntl) issue_mma(t + 1);
+#ifdef CB2_TC_PROF
+    ps += clock64() - p0;
+#endif
   }
+#ifdef CB2_TC_PROF
+  if (blockIdx.x == 0 && (tid == 32 || tid == 0) && ntl >= 32) printf("tc prof tid %d tiles %d (clk/tile): wait-mma %lld ld %lld compute %lld sync+issue %lld\n", tid, ntl, pw / ntl, pl / ntl, pc_ / ntl, ps / ntl);
+#endif
   // every thread keeps the phase counters of the bulk-copy barriers in step (only thread 0 waited on them here)
   use0 += (uint32_t)(kSingle ? ntl : ((ntl + 1) >> 1));
   use1 += (uint32_t)(kSingle ? 0 : (ntl >> 1));
