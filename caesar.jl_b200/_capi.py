@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libcaesar_b200.so")
+# CB2_LIB selects an experiment build of the same library (bench/micro/build_variant.py); the product is the in-tree default
+SO_PATH = os.environ.get("CB2_LIB") or os.path.join(_HERE, "libcaesar_b200.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "caesar_b200.h")
 
 CB2_FP32, CB2_FP64 = 0, 1

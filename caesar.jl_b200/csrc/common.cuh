@@ -39,12 +39,14 @@ struct cb2_ctx {
   double* small_dev = nullptr;  // 64 doubles of persistent device scratch (scalar results of nested calls)
   uint64_t launches = 0;
   std::string err;
-  std::mutex mu;
+  std::recursive_mutex mu;  // recursive: host-pointer entry points hold it across their nested _dev calls
   std::map<std::string, double> stage_ms;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::map<int64_t, cb2_pending> pending;
   int64_t next_ticket = 1;
 };
+
+typedef std::lock_guard<std::recursive_mutex> cb2_lock;
 
 int cb2_fail(cb2_ctx* ctx, int code, const char* fmt, ...);
 

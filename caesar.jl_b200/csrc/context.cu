@@ -55,12 +55,16 @@ extern "C" int cb2_create(int device, int precision, cb2_ctx** out) {
     return cb2_fail(nullptr, CB2_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
   ctx->stream = ctx->own_stream;
-  for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
-  e = cudaMalloc((void**)&ctx->small_dev, 64 * sizeof(double));
-  if (e != cudaSuccess) {
+  for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->small_dev, 64 * sizeof(double));
+  if (e != cudaSuccess) {  // unwind whatever was created
+    const int code = e == cudaErrorMemoryAllocation ? CB2_ERR_NOMEM : CB2_ERR_CUDA;
+    cudaGetLastError();
+    for (int i = 0; i < 8; ++i)
+      if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
-    return cb2_fail(nullptr, CB2_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+    return cb2_fail(nullptr, code, "cb2_create: events / scratch: %s", cudaGetErrorString(e));
   }
   *out = ctx;
   return CB2_OK;
@@ -88,6 +92,7 @@ extern "C" int cb2_precision(const cb2_ctx* ctx) { return ctx ? ctx->precision :
 
 extern "C" int cb2_set_stream(cb2_ctx* ctx, void* s) {
   if (!ctx) return CB2_ERR_INVALID;
+  cb2_lock g(ctx->mu);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
@@ -105,7 +110,7 @@ extern "C" int cb2_synchronize(cb2_ctx* ctx) {
 // them as they are.  Copies are stream-ordered on the context stream; only the download waits.
 extern "C" int cb2_device_alloc(cb2_ctx* ctx, size_t bytes, void** out) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   CB2_REQUIRE(ctx, out && bytes > 0, "null out or zero bytes");
   CB2_CUDA(ctx, cudaSetDevice(ctx->device));
   void* p = nullptr;
@@ -116,7 +121,7 @@ extern "C" int cb2_device_alloc(cb2_ctx* ctx, size_t bytes, void** out) {
 }
 extern "C" int cb2_device_free(cb2_ctx* ctx, void* ptr) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   if (!ptr) return CB2_OK;
   CB2_CUDA(ctx, cudaSetDevice(ctx->device));
   CB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // enqueued work may still use it
@@ -125,7 +130,7 @@ extern "C" int cb2_device_free(cb2_ctx* ctx, void* ptr) {
 }
 extern "C" int cb2_upload(cb2_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   CB2_REQUIRE(ctx, dst_dev && src_host, "null pointer");
   CB2_CUDA(ctx, cudaSetDevice(ctx->device));
   CB2_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -133,7 +138,7 @@ extern "C" int cb2_upload(cb2_ctx* ctx, void* dst_dev, const void* src_host, siz
 }
 extern "C" int cb2_download(cb2_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   CB2_REQUIRE(ctx, dst_host && src_dev, "null pointer");
   CB2_CUDA(ctx, cudaSetDevice(ctx->device));
   CB2_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -146,6 +151,7 @@ extern "C" int cb2_device_sm_count(const cb2_ctx* ctx) { return ctx ? ctx->sm_co
 
 extern "C" double cb2_last_stage_ms(const cb2_ctx* ctx, const char* stage) {
   if (!ctx || !stage) return -1.0;
+  cb2_lock g(const_cast<cb2_ctx*>(ctx)->mu);  // resolves pending events: mutates the stage table and waits for the stream
   cb2_resolve_product_stages(const_cast<cb2_ctx*>(ctx));
   auto it = ctx->stage_ms.find(stage);
   return it == ctx->stage_ms.end() ? -1.0 : it->second;

@@ -80,7 +80,7 @@ inline int src_dim(const cb2_conv_desc& c) { return (c.kind == CB2_FACTOR_POSE2P
 
 extern "C" int cb2_approx_conv_batch(cb2_ctx* ctx, const cb2_conv_desc* descs, int B, uint64_t seed) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   CB2_REQUIRE(ctx, descs && B > 0, "null descriptors or empty batch");
   CB2_CUDA(ctx, cudaSetDevice(ctx->device));
   size_t total = cb2_align(sizeof(ConvDev) * B);
@@ -145,7 +145,7 @@ extern "C" int cb2_approx_conv_batch(cb2_ctx* ctx, const cb2_conv_desc* descs, i
 // convolution, the bandwidth search and the product); only the descriptor table travels, nothing is waited for.
 extern "C" int cb2_approx_conv_batch_dev(cb2_ctx* ctx, const cb2_conv_desc* descs, int B, uint64_t seed) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   CB2_REQUIRE(ctx, descs && B > 0, "null descriptors or empty batch");
   CB2_CUDA(ctx, cudaSetDevice(ctx->device));
   std::vector<ConvDev> dd(B);

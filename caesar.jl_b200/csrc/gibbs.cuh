@@ -120,21 +120,27 @@ template <bool SHARED, typename T, int N, bool PACK> __device__ __forceinline__ 
 
 // per-chain constants of the packed loops (six dimensions as three pairs)
 struct PackedConst {
-  f32x2 a[3];  // leaf: sqrt(h)           coarse: -M
+  f32x2 a[3];  // leaf: sqrt(h)           coarse: -M (CB2_COARSE_RSQ: -M sqrt(qs))
   f32x2 b[3];  // leaf: -M sqrt(h)        coarse: C (1 for a single message)
   f32x2 cmul;
-  float nqs;   // -qs
+  float nqs;   // -qs                     (CB2_COARSE_RSQ: sqrt(qs), the scale of the coordinate differences)
 };
 template <typename T, int DIM> __device__ __forceinline__ PackedConst make_packed(const ChainConst<T, DIM>& c, bool leaf) {
   PackedConst p = {};
   if constexpr (DIM == 6 && sizeof(T) == 4) {
 #pragma unroll
+#if CB2_COARSE_RSQ
+    const float sq = leaf ? 1.0f : sqrtf((float)c.qs);
+    p.nqs = sq;
+#else
+    const float sq = 1.0f;
+    p.nqs = -c.qs;
+#endif
     for (int k = 0; k < 3; ++k) {
-      p.a[k] = leaf ? pack2(c.a[2 * k], c.a[2 * k + 1]) : pack2(-c.a[2 * k], -c.a[2 * k + 1]);
+      p.a[k] = leaf ? pack2(c.a[2 * k], c.a[2 * k + 1]) : pack2(-c.a[2 * k] * sq, -c.a[2 * k + 1] * sq);
       p.b[k] = leaf ? pack2(-c.b[2 * k], -c.b[2 * k + 1]) : pack2(c.b[2 * k], c.b[2 * k + 1]);
     }
     p.cmul = pack2(c.cmul, c.cmul);
-    p.nqs = -c.qs;
   }
   return p;
 }
@@ -227,14 +233,58 @@ __device__ __forceinline__ float score_node_p(const f32x2 (&q)[8], const PackedC
   return e;
 }
 
+// CB2_COARSE_RSQ: the same coarse-node probability with three MUFU instead of five.  With D_g = prod (var_i + C_i) over the
+// coordinates of group g (even / odd) and N_g = sum_i qs d_i^2 prod_{k != i} (var_k + C_k):
+//   p = w 2^{-m} prod_g D_g^{-1/2} exp2(-N_g / D_g) = (r_x r_y) exp2(lw - m - N_x r_x^2 - N_y r_y^2),   r_g = rsqrt(D_g):
+// one MUFU.RSQ per group (its square is the reciprocal) and one MUFU.EX2, against 2 RCP + 2 LG2 + 1 EX2 when the log-variance
+// term is carried inside the exponent.  Returns the exponent e' (relative to the reference m) and the multiplier r = r_x r_y;
+// the caller sums r exp2(e').  The reference m of a pass is the FULL log2-score of the level's first candidate (tile_pass),
+// so r exp2(e') = 2^{score - m} exactly as before and only the bookkeeping of the lazily raised maximum differs: it compares
+// e' with 60 - log2 r_0 (r_0 of the first candidate), which is the old test for candidates whose variances resemble the first
+// candidate's and keeps r exp2(e') <= 2^60 r / r_0 in every case.
+__device__ __forceinline__ float fast_rsq(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float score_node_rsq(const f32x2 (&q)[8], const PackedConst& c, float nm, float& mul) {
+  const f32x2 sq = pack2(c.nqs, c.nqs);
+  const f32x2 d0 = fma2(q[0], sq, c.a[0]), d1 = fma2(q[1], sq, c.a[1]), d2 = fma2(q[2], sq, c.a[2]);
+  const f32x2 t0 = mul2(d0, d0), t1 = mul2(d1, d1), t2 = mul2(d2, d2);
+  const f32x2 s0 = fma2(q[3], c.cmul, c.b[0]), s1 = fma2(q[4], c.cmul, c.b[1]), s2 = fma2(q[5], c.cmul, c.b[2]);
+  const f32x2 s01 = mul2(s0, s1);
+  const f32x2 num = fma2(s2, fma2(t1, s0, mul2(t0, s1)), mul2(s01, t2));
+  const f32x2 den = mul2(s01, s2);
+  float nx, ny, dx, dy, lw, p1;
+  unpack2(num, nx, ny);
+  unpack2(den, dx, dy);
+  unpack2(q[6], lw, p1);
+  const float rx = fast_rsq(dx), ry = fast_rsq(dy);
+  float e = lw + nm;
+  e = fma(-nx, rx * rx, e);
+  e = fma(-ny, ry * ry, e);
+  mul = rx * ry;
+  return e;
+}
+
 // MODE 0: coarse level, 1: leaf level with per-kernel weights, 2: leaf level with uniform weights
 template <int DIM, int MODE> struct RecLen { static constexpr int value = MODE == 0 ? (2 * DIM + 1 + 3) / 4 * 4 : (DIM + 1 + 3) / 4 * 4; };
 
+// whether a scoring path returns the probability as mul * exp2(e) (CB2_COARSE_RSQ) instead of exp2(e)
+template <int MODE, bool PACK> struct HasMul { static constexpr bool value = CB2_COARSE_RSQ && PACK && MODE == 0; };
+
 template <typename T, int DIM, int MODE, bool PACK>
 __device__ __forceinline__ T score_regs(const RecR<T, RecLen<DIM, MODE>::value, PACK>& r, const ChainConst<T, DIM>& c,
-                                        const PackedConst& pc, uint32_t circ, T nm) {
+                                        const PackedConst& pc, uint32_t circ, T nm, T& mul) {
+  mul = T(1);
   if constexpr (PACK) {
-    if constexpr (MODE == 0) return score_node_p(r.q, pc, nm);
+    if constexpr (MODE == 0) {
+#if CB2_COARSE_RSQ
+      return score_node_rsq(r.q, pc, nm, mul);
+#else
+      return score_node_p(r.q, pc, nm);
+#endif
+    }
     else return score_leaf_p<MODE == 2>(r.q, pc, nm);
   } else {
     if constexpr (MODE == 0) return score_node<T, DIM>(r.v, c, circ, nm);
@@ -247,7 +297,7 @@ __device__ __forceinline__ T score_regs(const RecR<T, RecLen<DIM, MODE>::value, 
 template <typename T, int DIM, int MODE, bool PACK, int R>
 __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int zbase, int CH, const ChainConst<T, DIM> (&cc)[R],
                                           const PackedConst (&pc)[R], uint32_t circ, T* __restrict__ chunk, int tid, T (&m)[R],
-                                          T (&csum)[R], int& cidx) {
+                                          T (&csum)[R], int& cidx, T (&thr)[R]) {
   constexpr int REC = RecLen<DIM, MODE>::value;
   constexpr int NT = kS / R;   // threads per CTA; chain r of this thread is column r * NT + tid of the per-chain arrays
   constexpr int G = kG / R;    // candidates scored together: G * R independent evaluations in flight
@@ -256,26 +306,37 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
     RecR<T, REC, PACK> rec0;
     load_recr<true>(tb, rec0);
 #pragma unroll
-    for (int r = 0; r < R; ++r) m[r] = score_regs<T, DIM, MODE, PACK>(rec0, cc[r], pc[r], circ, T(0));
+    for (int r = 0; r < R; ++r) {
+      T mul0;
+      m[r] = score_regs<T, DIM, MODE, PACK>(rec0, cc[r], pc[r], circ, T(0), mul0);
+      if constexpr (HasMul<MODE, PACK>::value) {  // m = full score of the first candidate; the raise test moves by log2 r_0
+        const T l0 = fast_log2(mul0);
+        m[r] += l0;
+        thr[r] = T(60) - l0;
+      } else {
+        thr[r] = T(60);
+      }
+    }
   }
   T nm[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) nm[r] = -m[r];
   for (int z = 0; z < ntg; z += G) {
-    T e[R][G];
+    T e[R][G], mu[R][G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       RecR<T, REC, PACK> rec;
       load_recr<true>(tb + (z + g) * REC, rec);
 #pragma unroll
-      for (int r = 0; r < R; ++r) e[r][g] = score_regs<T, DIM, MODE, PACK>(rec, cc[r], pc[r], circ, nm[r]);
+      for (int r = 0; r < R; ++r) e[r][g] = score_regs<T, DIM, MODE, PACK>(rec, cc[r], pc[r], circ, nm[r], mu[r][g]);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       T gm = e[r][0];
 #pragma unroll
       for (int g = 1; g < G; ++g) gm = fmax(gm, e[r][g]);
-      if (gm > T(60)) {  // rare: raise the reference by gm and rescale what has been summed so far
+      if (gm > thr[r]) {  // rare: raise the reference and rescale what has been summed so far
+        gm -= thr[r] - T(60);  // (HasMul: the exponents sit log2 r_0 below the scores)
         T sc = fast_exp2(-gm);
         csum[r] *= sc;
         for (int c = 0; c < cidx; ++c) chunk[c * kS + r * NT + tid] *= sc;
@@ -285,7 +346,10 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
         nm[r] = -m[r];
       }
 #pragma unroll
-      for (int g = 0; g < G; ++g) csum[r] += fast_exp2(e[r][g]);
+      for (int g = 0; g < G; ++g) {
+        if constexpr (HasMul<MODE, PACK>::value) csum[r] = fma(fast_exp2(e[r][g]), mu[r][g], csum[r]);
+        else csum[r] += fast_exp2(e[r][g]);
+      }
     }
     if (((zbase + z + G) & (CH - 1)) == 0) {
 #pragma unroll
@@ -298,16 +362,18 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
     load_recr<true>(tb + z * REC, rec);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      T e = score_regs<T, DIM, MODE, PACK>(rec, cc[r], pc[r], circ, nm[r]);
-      if (e > T(60)) {
-        T sc = fast_exp2(-e);
+      T mul;
+      T e = score_regs<T, DIM, MODE, PACK>(rec, cc[r], pc[r], circ, nm[r], mul);
+      if (e > thr[r]) {
+        const T up = e - (thr[r] - T(60));
+        T sc = fast_exp2(-up);
         csum[r] *= sc;
         for (int c = 0; c < cidx; ++c) chunk[c * kS + r * NT + tid] *= sc;
-        m[r] += e;
-        e = T(0);
+        m[r] += up;
+        e -= up;
         nm[r] = -m[r];
       }
-      csum[r] += fast_exp2(e);
+      csum[r] += fast_exp2(e) * mul;
     }
   }
 }
@@ -330,7 +396,9 @@ __device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, in
       const int zz = min(z + g, z1 - 1);
       RecR<T, REC, PACK> rec;
       load_recr<false>(lrec + (size_t)zz * REC, rec);
-      p[g] = fast_exp2(score_regs<T, DIM, MODE, PACK>(rec, cc, pc, circ, nm));
+      T mul;
+      const T e = score_regs<T, DIM, MODE, PACK>(rec, cc, pc, circ, nm, mul);
+      p[g] = fast_exp2(e) * mul;
     }
 #pragma unroll
     for (int g = 0; g < PR; ++g) {
@@ -572,8 +640,11 @@ __global__ void __launch_bounds__(kS / ChainsPerThread<T, DIM>::value, ChainsPer
 gibbs_kernel(const GibbsArgs a) {
   constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
   constexpr int TILE_BYTES = gibbs_tile_bytes<T, DIM>();
-  constexpr int TN_NODE = TILE_BYTES / (RECN * (int)sizeof(T));
-  constexpr int TN_LEAF = TILE_BYTES / (RECL * (int)sizeof(T));
+  // candidates per tile, rounded down to whole scoring groups: tile_pass closes chunks on multiples of kG and assumes every tile
+  // starts on one (d = 4, 5 have 48-byte coarse records: 170 per 8 KB tile would shift every later tile off the grid)
+  constexpr int TN_NODE = TILE_BYTES / (RECN * (int)sizeof(T)) / kG * kG;
+  constexpr int TN_LEAF = TILE_BYTES / (RECL * (int)sizeof(T)) / kG * kG;
+  static_assert(TN_NODE > 0 && TN_LEAF > 0 && TN_NODE % kG == 0 && TN_LEAF % kG == 0, "tile sizes must be whole scoring groups");
   constexpr int R = ChainsPerThread<T, DIM>::value;  // chains per thread
   constexpr int NT = kS / R;                          // threads per CTA; the CTA always advances kS chains
   constexpr bool kPack = DIM == 6 && sizeof(T) == 4;  // packed-pair scoring (see PackedConst)
@@ -714,9 +785,9 @@ gibbs_kernel(const GibbsArgs a) {
         // warp-uniform choice of the scoring loop (all chains of the warp must agree)
         const bool flat = circ == 0u || __all_sync(0xffffffffu, nowrap);
         // ---- pass 1: chunk partial sums of exp2(e - m), m = running (lazily raised) reference maximum
-        T m[R], csum[R];
+        T m[R], csum[R], thr[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) { m[r] = T(0); csum[r] = T(0); }  // m is set from the level's first candidate (tile_pass / leaf_pass_tc)
+        for (int r = 0; r < R; ++r) { m[r] = T(0); csum[r] = T(0); thr[r] = T(60); }  // m is set from the level's first candidate (tile_pass / leaf_pass_tc)
         int cidx = 0;
         bool done_tc = false;
         if constexpr (kTC) {
@@ -749,15 +820,15 @@ gibbs_kernel(const GibbsArgs a) {
           // with the tensor-core leaf pass compiled in, the packed leaf loops would only serve warp-flat passes of CTAs that are
           // not flat as a whole: they take the wrapped loops instead and the kernel stays smaller (instruction cache)
           if (flat && !(kTC && leaf)) {  // Euclidean arithmetic on every coordinate: same values as the wrapped form, fewer instructions
-            if (!leaf) tile_pass<T, DIM, 0, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
+            if (!leaf) tile_pass<T, DIM, 0, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
             else if constexpr (!kTC) {
-              if (!dj.uniform) tile_pass<T, DIM, 1, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
-              else tile_pass<T, DIM, 2, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx);
+              if (!dj.uniform) tile_pass<T, DIM, 1, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
+              else tile_pass<T, DIM, 2, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
             }
           } else {
-            if (!leaf) tile_pass<T, DIM, 0, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
-            else if (!dj.uniform) tile_pass<T, DIM, 1, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
-            else tile_pass<T, DIM, 2, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx);
+            if (!leaf) tile_pass<T, DIM, 0, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx, thr);
+            else if (!dj.uniform) tile_pass<T, DIM, 1, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx, thr);
+            else tile_pass<T, DIM, 2, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx, thr);
           }
           __syncthreads();  // everyone is done with tile[b] before it is refilled
         }

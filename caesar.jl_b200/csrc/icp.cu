@@ -369,7 +369,7 @@ extern "C" int cb2_icp_align_batch(cb2_ctx* ctx, const double* fix, int nf, cons
                                    int correspondences, int neighbors, double min_planarity, double min_change,
                                    int max_iterations, double* H_out, double* stats_out) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   CB2_REQUIRE(ctx, fix && mov && H_out && nf >= 3 && nm >= 1 && K >= 1, "null clouds / outputs or empty batch");
   // the argument checks of alignICP_Simple (ICP_Simple.jl:252-258)
   CB2_REQUIRE(ctx, correspondences >= 10, "\"correspondences\" must be >= 10");

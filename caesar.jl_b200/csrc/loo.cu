@@ -600,7 +600,7 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
 extern "C" int cb2_kde_bw_loo_batch(cb2_ctx* ctx, const double* const* mu, const int32_t* N, int B, int d,
                                     const uint8_t* circular, double* sigma_out) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   CB2_REQUIRE(ctx, mu && N && sigma_out && B > 0, "null pointer or empty batch");
   if (d < 1 || d > CB2_MAX_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d outside 1..%d", d, CB2_MAX_DIM);
   size_t total = 0;
@@ -654,7 +654,7 @@ extern "C" int cb2_kde_bw_loo(cb2_ctx* ctx, const double* mu, int d, int N, cons
 extern "C" int cb2_kde_bw_loo_batch_dev(cb2_ctx* ctx, const double* const* mu_dev, const int32_t* N, int B, int d,
                                         const uint8_t* circular, double* sigma_out_dev) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   CB2_REQUIRE(ctx, mu_dev && N && sigma_out_dev && B > 0, "null pointer or empty batch");
   if (d < 1 || d > CB2_MAX_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d outside 1..%d", d, CB2_MAX_DIM);
   for (int b = 0; b < B; ++b) CB2_REQUIRE(ctx, mu_dev[b] && N[b] >= 2, "density %d: need at least 2 points", b);

@@ -598,7 +598,7 @@ template int cb2_se_batch_core<double>(cb2_ctx*, const double*, int, const doubl
 extern "C" int cb2_mmd_sums_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev, int M, int d, double bw,
                                 int ra0, int ra1, int rb0, int rb1, double* sums3_dev) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   int rc = check_cloud_args(ctx, a_dev, N, b_dev, M, d);
   if (rc) return rc;
   CB2_REQUIRE(ctx, sums3_dev, "null output");
@@ -635,14 +635,11 @@ static int upload_block(cb2_ctx* ctx, const std::vector<const double*>& src, con
 extern "C" int cb2_mmd_sums(cb2_ctx* ctx, const double* a, int N, const double* b, int M, int d, double bw,
                             int ra0, int ra1, int rb0, int rb1, double* sums3) {
   if (!ctx) return CB2_ERR_INVALID;
-  int rc;
-  {
-    std::lock_guard<std::mutex> g(ctx->mu);
-    rc = check_cloud_args(ctx, a, N, b, M, d);
-    if (rc) return rc;
-    CB2_REQUIRE(ctx, sums3, "null output");
-    CB2_CUDA(ctx, cudaSetDevice(ctx->device));
-  }
+  cb2_lock g(ctx->mu);  // held across upload, the nested _dev call and the read-back: the I/O block is shared per context
+  int rc = check_cloud_args(ctx, a, N, b, M, d);
+  if (rc) return rc;
+  CB2_REQUIRE(ctx, sums3, "null output");
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
   std::vector<double*> dev;
   double* block = nullptr;
   rc = upload_block(ctx, {a, b, nullptr}, {(size_t)N * d, (size_t)M * d, 3}, dev, &block);
@@ -672,7 +669,7 @@ extern "C" int cb2_mmd(cb2_ctx* ctx, const double* a, int N, const double* b, in
 extern "C" int cb2_mmd_se_batch_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev, int M, int dim,
                                     double bw, const double* coords, int K, int backward, double* vals, double* grads) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   int rc = check_cloud_args(ctx, a_dev, N, b_dev, M, dim);
   if (rc) return rc;
   CB2_REQUIRE(ctx, dim == 2 || dim == 3, "rigid-transform batch needs dim 2 or 3 (got %d)", dim);
@@ -699,13 +696,10 @@ extern "C" int cb2_mmd_se_batch_dev(cb2_ctx* ctx, const double* a_dev, int N, co
 extern "C" int cb2_mmd_se_batch(cb2_ctx* ctx, const double* a, int N, const double* b, int M, int dim, double bw,
                                 const double* coords, int K, int backward, double* vals, double* grads) {
   if (!ctx) return CB2_ERR_INVALID;
-  int rc;
-  {
-    std::lock_guard<std::mutex> g(ctx->mu);
-    rc = check_cloud_args(ctx, a, N, b, M, dim);
-    if (rc) return rc;
-    CB2_CUDA(ctx, cudaSetDevice(ctx->device));
-  }
+  cb2_lock g(ctx->mu);  // whole call: see cb2_mmd_sums
+  int rc = check_cloud_args(ctx, a, N, b, M, dim);
+  if (rc) return rc;
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
   std::vector<double*> dev;
   double* block = nullptr;
   rc = upload_block(ctx, {a, b}, {(size_t)N * dim, (size_t)M * dim}, dev, &block);
@@ -761,7 +755,7 @@ static int kde_eval_impl(cb2_ctx* ctx, const double* mu_dev, const double* sigma
 extern "C" int cb2_kde_eval(cb2_ctx* ctx, const double* mu, const double* sigma, const double* w, int d, int N,
                             const double* q, int Q, int logp, double* out) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   int rc = check_cloud_args(ctx, mu, N, q, Q, d);
   if (rc) return rc;
   CB2_REQUIRE(ctx, sigma && out, "null sigma/out");
@@ -793,7 +787,7 @@ extern "C" int cb2_kde_eval(cb2_ctx* ctx, const double* mu, const double* sigma,
 extern "C" int cb2_kde_sample(cb2_ctx* ctx, const double* mu, const double* sigma, const double* w, int d, int N,
                               const uint8_t* circular, int n, uint64_t seed, uint32_t stream, double* out) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   CB2_REQUIRE(ctx, mu && sigma && out, "null pointer");
   CB2_REQUIRE(ctx, N > 0 && n >= 0, "bad sizes");
   if (d < 1 || d > CB2_MAX_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d outside 1..%d", d, CB2_MAX_DIM);
@@ -962,7 +956,7 @@ extern "C" int cb2_scatter_align(cb2_ctx* ctx, const cb2_density* cloud1, const 
                                  double bw, const double* x0, int K, uint64_t seed, int max_iter, double g_tol,
                                  double* coords_out, double* score_out, int32_t* iters_out) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   CB2_REQUIRE(ctx, cloud1 && cloud2 && cloud1->pts && cloud2->pts && cloud1->bw && cloud2->bw, "null cloud");
   CB2_REQUIRE(ctx, dim == 2 || dim == 3, "dim must be 2 or 3");
   CB2_REQUIRE(ctx, sample_count > 0 && K > 0 && x0 && coords_out, "bad sample_count / K / pointers");
@@ -1045,7 +1039,7 @@ static int mmd_manifold_impl(cb2_ctx* ctx, const double* a_dev, int N, const dou
 extern "C" int cb2_mmd_manifold(cb2_ctx* ctx, const double* a, int N, const double* b, int M, int d, const uint8_t* circular,
                                 double rot_weight, double bw, double* out) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   int rc = check_cloud_args(ctx, a, N, b, M, d);
   if (rc) return rc;
   CB2_REQUIRE(ctx, out, "null output");

@@ -62,6 +62,9 @@ __host__ __device__ inline int node_of(int N, int l, int p) {
 #ifndef CB2_GIBBS_TC
 #define CB2_GIBBS_TC 1
 #endif
+#ifndef CB2_COARSE_RSQ
+#define CB2_COARSE_RSQ 1   // coarse levels of the packed FP32 d = 6 loops: 2 MUFU.RSQ + 1 MUFU.EX2 per candidate (gibbs.cuh)
+#endif
 #ifndef CB2_TC_TILE
 #define CB2_TC_TILE 128
 #endif
@@ -509,6 +512,10 @@ int launch_gibbs_inst(cb2_ctx* ctx, int nwork, const GibbsArgs& a) {
 template <typename T>
 int launch_gibbs(cb2_ctx* ctx, int d, uint32_t mask, int nwork, const GibbsArgs& a) {
   // the common variable types get compile-time circular masks; anything else takes the run-time mask
+#ifdef CB2_FAST_BUILD  // experiment builds (bench/micro/build_variant.py): the headline instance only, seconds instead of minutes
+  if (d == 6 && mask == 0x38u && sizeof(T) == 4) return launch_gibbs_inst<float, 6, 0x38u>(ctx, nwork, a);
+  return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "CB2_FAST_BUILD carries the FP32 Pose3 product kernel only");
+#else
   if (d == 1 && mask == 0) return launch_gibbs_inst<T, 1, 0u>(ctx, nwork, a);
   if (d == 2 && mask == 0) return launch_gibbs_inst<T, 2, 0u>(ctx, nwork, a);            // Point2
   if (d == 3 && mask == 0) return launch_gibbs_inst<T, 3, 0u>(ctx, nwork, a);            // Point3
@@ -523,6 +530,7 @@ int launch_gibbs(cb2_ctx* ctx, int d, uint32_t mask, int nwork, const GibbsArgs&
     case 6: return launch_gibbs_inst<T, 6, ~0u>(ctx, nwork, a);
   }
   return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d", d);
+#endif
 }
 
 struct BatchPlan {
@@ -536,7 +544,7 @@ struct BatchPlan {
 int validate_and_plan(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d, BatchPlan& pl,
                       uint32_t* mask_out) {
   CB2_REQUIRE(ctx, descs && B > 0, "null descriptors or empty batch");
-  if (d < 1 || d > CB2_MAX_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d outside 1..%d", d, CB2_MAX_DIM);
+  if (d < 1 || d > CB2_MAX_PRODUCT_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "product dimension %d outside 1..%d", d, CB2_MAX_PRODUCT_DIM);
   uint32_t mask = 0;
   for (int k = 0; k < d; ++k) if (circular && circular[k]) mask |= 1u << k;
   *mask_out = mask;
@@ -747,7 +755,7 @@ void cb2_resolve_product_stages(cb2_ctx* ctx) {
 extern "C" int cb2_product_batch_dev(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d,
                                      uint64_t seed) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   return product_batch_dev_locked(ctx, descs, B, circular, d, seed, nullptr, nullptr);
 }
 
@@ -778,7 +786,7 @@ static int launch_copy_segments(cb2_ctx* ctx, const std::vector<CopySeg>& segs, 
 static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d, uint64_t seed,
                               cb2_pending* pend) {
   CB2_REQUIRE(ctx, descs && B > 0, "null descriptors or empty batch");
-  if (d < 1 || d > CB2_MAX_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d outside 1..%d", d, CB2_MAX_DIM);
+  if (d < 1 || d > CB2_MAX_PRODUCT_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "product dimension %d outside 1..%d", d, CB2_MAX_PRODUCT_DIM);
   CB2_CUDA(ctx, cudaSetDevice(ctx->device));
   size_t total = 0, n_arrays = 0;
   for (int b = 0; b < B; ++b) {
@@ -935,7 +943,7 @@ static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B
 
 extern "C" int cb2_product_batch(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d, uint64_t seed) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   return product_batch_host(ctx, descs, B, circular, d, seed, nullptr);
 }
 
@@ -951,7 +959,7 @@ extern "C" int cb2_product(cb2_ctx* ctx, const cb2_density* dens, int D, const u
 extern "C" int cb2_product_batch_submit(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d,
                                         uint64_t seed, cb2_ticket* ticket) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   CB2_REQUIRE(ctx, ticket, "null ticket");
   cb2_pending pend;
   int rc = product_batch_host(ctx, descs, B, circular, d, seed, &pend);
@@ -965,7 +973,7 @@ extern "C" int cb2_wait(cb2_ctx* ctx, cb2_ticket ticket) {
   if (!ctx) return CB2_ERR_INVALID;
   cb2_pending pend;
   {
-    std::lock_guard<std::mutex> g(ctx->mu);
+    cb2_lock g(ctx->mu);
     auto it = ctx->pending.find(ticket);
     if (it == ctx->pending.end()) return cb2_fail(ctx, CB2_ERR_INVALID, "unknown ticket %lld", (long long)ticket);
     pend = it->second;
@@ -974,14 +982,17 @@ extern "C" int cb2_wait(cb2_ctx* ctx, cb2_ticket ticket) {
   cudaError_t e = cudaEventSynchronize(pend.done);
   cudaEventDestroy(pend.done);
   if (pend.dev_block) cudaFree(pend.dev_block);
-  if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "async product batch failed: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) {
+    cb2_lock g(ctx->mu);
+    return cb2_fail(ctx, CB2_ERR_CUDA, "async product batch failed: %s", cudaGetErrorString(e));
+  }
   return CB2_OK;
 }
 
 extern "C" int cb2_tree_debug(cb2_ctx* ctx, const cb2_density* den, int d, int level, int32_t* depth_out, int32_t* count_out,
                               int32_t* perm, double* mean, double* var, double* wt) {
   if (!ctx) return CB2_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  cb2_lock g(ctx->mu);
   CB2_REQUIRE(ctx, den && den->pts && den->bw && den->N > 0, "null density");
   if (d < 1 || d > CB2_MAX_DIM) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "dimension %d", d);
   CB2_CUDA(ctx, cudaSetDevice(ctx->device));

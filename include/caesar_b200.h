@@ -46,12 +46,13 @@ typedef enum {
   CB2_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed; message has the CUDA error string */
   CB2_ERR_NO_DEVICE = -3,   /* no CUDA device / wrong architecture: there is no CPU fallback */
   CB2_ERR_NOMEM = -4,       /* device or pinned-host allocation failed */
-  CB2_ERR_UNSUPPORTED = -5  /* shape outside compiled limits (d > 8, N > 16384 for products, D > 16) */
+  CB2_ERR_UNSUPPORTED = -5  /* shape outside compiled limits (d > 8; products: d > 6, N > 16384, D > 16) */
 } cb2_status;
 
 enum { CB2_FP32 = 0, CB2_FP64 = 1 }; /* arithmetic of the pair / Gibbs kernels; I/O is always Float64 */
 
-#define CB2_MAX_DIM 8
+#define CB2_MAX_DIM 8          /* pair sums, evaluate, bandwidth, sample */
+#define CB2_MAX_PRODUCT_DIM 6  /* Gibbs products (Pose3 is the largest variable type upstream multiplies) */
 #define CB2_MAX_DENS 16
 #define CB2_MAX_PRODUCT_N 16384
 

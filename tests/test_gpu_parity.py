@@ -518,3 +518,68 @@ def test_product_fp32_tensor_core_leaf_pass_follows_the_oracle_chains(cb, ctx32,
         same = (lab == olab).all(axis=1)
         assert same.mean() > 0.97, (D, N, circ, weighted, same.mean())
         assert np.abs(pts[same] - opts[same]).max() < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ round-2 additions
+@pytest.mark.parametrize("d,circ", [(4, (0, 1, 0, 1)), (5, (0, 0, 0, 1, 1)), (4, (0, 0, 0, 0)), (5, (1, 0, 0, 0, 0))])
+@pytest.mark.parametrize("N", [512, 4096])
+def test_product_fp64_d4_d5_many_tiles_reproduce_oracle_chains(cb, ctx64, d, circ, N):
+    """d = 4, 5 have 48-byte (FP32) / 96-byte (FP64) coarse records, so a tile holds 170 of them: not a whole number of scoring
+    groups.  Levels with more than one tile (N >= 257) must still close their chunk sums on the group grid (gibbs.cuh TN_NODE)."""
+    rng = np.random.default_rng(40 + d + N)
+    dens = _messages(rng, 3, N, d, spread=0.5 if any(circ) else 1.0)
+    Nout = 320
+    pts, lab = cb.product_points(dens, circ, Nout, seed=17, stream=1, ctx=ctx64)
+    opts, olab = oracle.product(dens, Nout, seed=17, circular=list(circ), stream=1, ubits=53)
+    same = (lab == olab).all(axis=1)
+    assert same.mean() >= 0.99, same.mean()
+    assert np.allclose(pts[same], opts[same], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("d", [4, 5])
+def test_product_fp32_d4_d5_many_tiles_follow_oracle_chains(cb, ctx32, d):
+    rng = np.random.default_rng(50 + d)
+    circ = (0, 0, 0, 1, 1)[:d]
+    dens = _messages(rng, 3, 1500, d, spread=0.5)
+    pts, lab = cb.product_points(dens, circ, 512, seed=23, ctx=ctx32)
+    opts, olab = oracle.product(dens, 512, seed=23, circular=list(circ), ubits=24)
+    assert (lab == olab).all(axis=1).mean() > 0.9
+
+
+def _c5_variable(seed):
+    """One variable of the bench workload (bench.make_variable): D = 8 messages x N = 4096 kernels, Pose3."""
+    import bench
+    return bench.make_variable(seed)
+
+
+def test_headline_instance_fp32_c5_shape_follows_oracle_chains(cb, ctx32):
+    """The exact kernel instance bench.py times -- FP32, D = 8 x N = 4096 x N_out = 4096, d = 6 Pose3, packed coarse levels and the
+    tensor-core leaf pass over 32 tiles -- against the oracle on 256 of its chains (same Philox uniforms, ubits = 24)."""
+    circ = (0, 0, 0, 1, 1, 1)
+    dens = _c5_variable(3)
+    pts, lab = cb.product_points(dens, circ, 4096, seed=31, stream=3, ctx=ctx32)
+    assert np.isfinite(pts).all() and lab.min() >= 0 and lab.max() < 4096
+    for off in (0, 3840):  # first and last CTA of the product
+        opts, olab = oracle.product(dens, 128, seed=31, circular=list(circ), stream=3, ubits=24, sample_offset=off)
+        sl = slice(off, off + 128)
+        same = (lab[sl] == olab).all(axis=1)
+        assert same.mean() > 0.9, (off, same.mean())
+        assert (lab[sl] == olab).mean() > 0.97   # per (chain, message) label
+        diff = pts[sl][same] - opts[same]
+        diff[:, 3:] = (diff[:, 3:] + np.pi) % (2 * np.pi) - np.pi
+        assert np.abs(diff).max() < 5e-5
+    # in distribution against the FP64 device chains of the same seeds
+    ctx64 = cb.Context(0, "fp64")
+    p64, _ = cb.product_points(dens, circ, 4096, seed=31, stream=3, ctx=ctx64)
+    dm = p64.mean(0) - pts.mean(0)
+    dm[3:] = (dm[3:] + np.pi) % (2 * np.pi) - np.pi
+    assert np.abs(dm).max() < 0.02
+
+
+def test_product_dimension_above_six_is_rejected_before_any_work(cb, ctx):
+    rng = np.random.default_rng(0)
+    dens = [(rng.normal(size=(64, 7)), np.full(7, 0.3)) for _ in range(2)]
+    launches = ctx.kernel_launches
+    with pytest.raises(cb.CB2Error) as ei:
+        cb.product_points(dens, (0,) * 7, 16, seed=1, ctx=ctx)
+    assert ei.value.code == -5 and ctx.kernel_launches == launches
