@@ -418,7 +418,14 @@ def product_points(dens, circular, Nout, seed=0, niter=1, stream=0, sample_offse
     return outs[0], labels[0]
 
 
-FACTOR_PRIOR_POSE2, FACTOR_POSE2POSE2, FACTOR_POSE2POINT2_BEARINGRANGE = 0, 1, 2
+FACTOR_PRIOR_POSE2, FACTOR_POSE2POSE2, FACTOR_POSE2POINT2_BEARINGRANGE, FACTOR_PRIOR_POSE3, FACTOR_POSE3POSE3 = 0, 1, 2, 3, 4
+
+
+def _conv_dims(kind, rev):
+    """(coordinates of the noise / mean, coordinates of the target) of a closed-form convolution."""
+    if kind >= FACTOR_PRIOR_POSE3:
+        return 6, 6
+    return 3, (2 if (kind == FACTOR_POSE2POINT2_BEARINGRANGE and not rev) else 3)
 
 
 def approxConvBatch(convs, seed=0, ctx=None):
@@ -431,7 +438,7 @@ def approxConvBatch(convs, seed=0, ctx=None):
     keep, outs = [], []
     for b, c in enumerate(convs):
         kind, rev = int(c["kind"]), int(bool(c.get("reverse", False)))
-        dt = 2 if (kind == FACTOR_POSE2POINT2_BEARINGRANGE and not rev) else 3
+        nz, dt = _conv_dims(kind, rev)
         out = np.zeros((int(c["N"]), dt))
         src = None if c.get("src") is None else f64(c["src"])
         aux = None if c.get("aux") is None else f64(c["aux"])
@@ -443,15 +450,28 @@ def approxConvBatch(convs, seed=0, ctx=None):
         d.n_aux = 0 if aux is None else aux.shape[0]
         d.src = None if src is None else src.ctypes.data
         d.aux = None if aux is None else aux.ctypes.data
-        mean = np.resize(np.asarray(c["mean"], dtype=np.float64), 3)
-        chol = np.asarray(c["chol"], dtype=np.float64).reshape(9)
-        for i in range(3):
+        mean = np.resize(np.asarray(c["mean"], dtype=np.float64), nz)
+        chol = np.asarray(c["chol"], dtype=np.float64).reshape(nz * nz)
+        for i in range(nz):
             d.mean[i] = mean[i]
-        for i in range(9):
+        for i in range(nz * nz):
             d.chol[i] = chol[i]
         d.out = out.ctypes.data
     ctx.check(_capi.lib().cb2_approx_conv_batch(ctx._h, descs, B, int(seed)))
     return outs
+
+
+def se_residual_batch(dim, X, p, q, ctx=None):
+    """Residual of the relative-pose factors (ScatterAlignPose2/3, Pose2Pose2, Pose3Pose3) for K particles in one launch:
+    `Xc = vee(M, q, log(M, q, p o exp(M, e0, X)))` (R:ext/Images/ScatterAlignPose2.jl:216-231).  X, p, q: K x ncoord coordinates."""
+    ctx = ctx or context()
+    X, p, q = (f64(np.atleast_2d(v)) for v in (X, p, q))
+    nc = 3 if dim == 2 else 6
+    if X.shape != p.shape or X.shape != q.shape or X.shape[1] != nc:
+        raise ValueError(f"X, p, q must all be K x {nc}")
+    out = np.zeros_like(X)
+    ctx.check(_capi.lib().cb2_se_residual_batch(ctx._h, int(dim), ptr(X), ptr(p), ptr(q), X.shape[0], ptr(out)))
+    return out
 
 
 def icp_align_batch(fix, mov, perturb=None, correspondences=500, neighbors=50, min_planarity=0.3, min_change=3.0,
@@ -493,5 +513,6 @@ def tree_levels(pts, bw, w=None, ctx=None):
 
 
 from .factors import (ScatterAlign, ScatterAlignPose2, ScatterAlignPose3, CalcFactor, preambleCache, getSample,  # noqa: E402
-                      HeatmapGridDensity, ScatterAlignPose2_from_images)
+                      HeatmapGridDensity, ScatterAlignPose2_from_images, getManifold, parchDistribution, packScatterAlign,
+                      unpackScatterAlign, BlobStoreGraph)
 from .serialization import packDistribution, unpackDistribution  # noqa: E402

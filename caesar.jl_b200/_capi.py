@@ -33,8 +33,8 @@ class ProductDesc(C.Structure):
 
 class ConvDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("reverse", C.c_int32), ("N", C.c_int32), ("n_src", C.c_int32), ("src", C.c_void_p),
-                ("aux", C.c_void_p), ("n_aux", C.c_int32), ("stream", C.c_uint32), ("mean", C.c_double * 3),
-                ("chol", C.c_double * 9), ("out", C.c_void_p)]
+                ("aux", C.c_void_p), ("n_aux", C.c_int32), ("stream", C.c_uint32), ("mean", C.c_double * 6),
+                ("chol", C.c_double * 36), ("out", C.c_void_p)]
 
 
 _lib = None
@@ -76,6 +76,7 @@ def lib():
             "cb2_wait": (i32, [vp, C.c_int64]),
             "cb2_tree_debug": (i32, [vp, C.POINTER(Density), i32, i32, vp, vp, vp, vp, vp, vp]),
             "cb2_approx_conv_batch": (i32, [vp, C.POINTER(ConvDesc), i32, u64]),
+            "cb2_se_residual_batch": (i32, [vp, i32, vp, vp, vp, i32, vp]),
             "cb2_device_alloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
             "cb2_device_free": (i32, [vp, vp]),
             "cb2_upload": (i32, [vp, vp, vp, C.c_size_t]),
@@ -99,7 +100,7 @@ EXPORTS = ["cb2_create", "cb2_destroy", "cb2_last_error", "cb2_precision", "cb2_
            "cb2_kde_bw_loo_batch", "cb2_kde_sample", "cb2_product", "cb2_product_batch", "cb2_product_batch_dev",
            "cb2_product_batch_submit", "cb2_wait", "cb2_tree_debug", "cb2_scatter_align", "cb2_approx_conv_batch",
            "cb2_mmd_manifold", "cb2_device_alloc", "cb2_device_free", "cb2_upload", "cb2_download", "cb2_approx_conv_batch_dev",
-           "cb2_kde_bw_loo_batch_dev", "cb2_icp_align_batch"]
+           "cb2_kde_bw_loo_batch_dev", "cb2_icp_align_batch", "cb2_se_residual_batch"]
 
 
 def f64(x):

@@ -128,7 +128,6 @@ struct PackedConst {
 template <typename T, int DIM> __device__ __forceinline__ PackedConst make_packed(const ChainConst<T, DIM>& c, bool leaf) {
   PackedConst p = {};
   if constexpr (DIM == 6 && sizeof(T) == 4) {
-#pragma unroll
 #if CB2_COARSE_RSQ
     const float sq = leaf ? 1.0f : sqrtf((float)c.qs);
     p.nqs = sq;
@@ -136,6 +135,7 @@ template <typename T, int DIM> __device__ __forceinline__ PackedConst make_packe
     const float sq = 1.0f;
     p.nqs = -c.qs;
 #endif
+#pragma unroll
     for (int k = 0; k < 3; ++k) {
       p.a[k] = leaf ? pack2(c.a[2 * k], c.a[2 * k + 1]) : pack2(-c.a[2 * k] * sq, -c.a[2 * k + 1] * sq);
       p.b[k] = leaf ? pack2(-c.b[2 * k], -c.b[2 * k + 1]) : pack2(c.b[2 * k], c.b[2 * k + 1]);
@@ -294,6 +294,8 @@ __device__ __forceinline__ T score_regs(const RecR<T, RecLen<DIM, MODE>::value, 
 
 // one scoring pass over the candidates of a level held in a shared-memory tile: chunk partial sums of exp2(e - m) for
 // the R chains of this thread; every record is fetched once and scored against all R chains
+// (a branch-free variant -- sum the tile optimistically, test the largest exponent once per tile, repeat the tile after a raise --
+// was measured slower here: 213 vs 192 ms per 256 variables; the tensor-core leaf pass below does use that scheme per tile)
 template <typename T, int DIM, int MODE, bool PACK, int R>
 __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int zbase, int CH, const ChainConst<T, DIM> (&cc)[R],
                                           const PackedConst (&pc)[R], uint32_t circ, T* __restrict__ chunk, int tid, T (&m)[R],
@@ -472,9 +474,17 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
          ((uint64_t)1 << 46);
 }
+// Executed by a CONVERGED warp, one elected lane issues: the operands stay warp-uniform, so the descriptors live in uniform
+// registers.  Issued from a divergent `tid == 0` branch every MMA pays register-to-uniform moves and costs the issuing thread
+// ~150 clk instead of ~75 (bench/micro/tcgen05_issue_probe.cu: chain of six 906 vs 541 clk).
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-               "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
@@ -484,18 +494,51 @@ __device__ __forceinline__ float tf32_round(float x) {
 
 struct TcState {
   float* sA;          // [2][128 x 16] coefficient rows, hi then lo (canonical operand layout)
-  uint64_t* mbars;    // [2] MMA-complete barriers
-  uint32_t tmem;      // base of this CTA's 128 accumulator columns (two 64-column buffers)
-  uint32_t mu0, mu1;  // completed uses of the two MMA barriers (phase parity)
+  uint64_t* mbars;    // [0..1] accumulator-full barriers (MMA commit), [2..3] accumulator-free barriers (one arrival per warp)
+  uint32_t tmem;      // base of this CTA's 128 accumulator columns (kTcBufs buffers of kTcTile columns)
+  uint32_t mu0, mu1;  // completed phases of the two accumulator-full barriers
+  uint32_t fu0, fu1;  // completed phases of the two accumulator-free barriers
 };
+constexpr int kTcBufs = 128 / kTcTile;  // accumulator buffers (and feature stages) per CTA: 2 x 64 leaves or 1 x 128
+static_assert(kTcTile == 64 || kTcTile == 128, "feature tiles hold 64 or 128 leaves");
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+// Pipeline of one leaf pass (tiles t = 0 .. ntl-1 of kTcTile leaves, buffer b = t mod kTcBufs):
+//   thread 0   : bulk copy of tile t into stage b (as soon as MMA(t - kTcBufs) has completed), six MMAs of tile t into accumulator b
+//                as soon as every warp has released it (accumulator-free barrier, one arrival per warp), commit -> full barrier b
+//   every warp : waits for full barrier b, reads its 32 rows of accumulator b in blocks of 32 leaves (tcgen05.ld), sums
+//                exp2(score - m) into the chain's chunk sums, releases the accumulator.
+// With two buffers the tensor core works on tile t + 1 while tile t is summed and no CTA-wide barrier sits inside the pass; the
+// warps drift by at most one tile.  The sums are taken optimistically (see tile_pass): no branch inside a block of 32 leaves, the
+// largest exponent of the tile is checked once per tile, and a warp with a chain above the threshold restores, raises and
+// re-reads the tile (its accumulator has not been released yet).
 template <typename T, int DIM>
 __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int cnt, int CH, const ChainConst<T, DIM>& cc, bool uniform,
                                              unsigned char* smem_tiles, int tile_bytes, uint64_t* bars, uint32_t& use0, uint32_t& use1,
                                              TcState& tc, float* __restrict__ chunk, int tid, float& m, float& csum, int& cidx) {
-  if (tid == 0) {  // the first feature tile travels while the coefficient rows are written
-    mbar_expect_tx(&bars[0], (uint32_t)(kTcTileFloats * 4));
-    tma_load_1d(smem_tiles, feat, (uint32_t)(kTcTileFloats * 4), &bars[0]);
+  const int ntl = (cnt + kTcTile - 1) / kTcTile;
+  auto load_tile = [&](int t) {  // thread 0: one bulk copy (hi + lo parts of kTcTile leaves)
+    const int b = t % kTcBufs;
+    mbar_expect_tx(&bars[b], (uint32_t)(kTcTileFloats * 4));
+    tma_load_1d(smem_tiles + b * tile_bytes, feat + (size_t)t * kTcTileFloats, (uint32_t)(kTcTileFloats * 4), &bars[b]);
+  };
+  if (tid == 0) {  // the first feature tiles travel while the coefficient rows are written
+    load_tile(0);
+    if (kTcBufs > 1 && ntl > 1) load_tile(1);
   }
   // ---- this chain's coefficient row, split hi / lo, into the A operand
   {
@@ -519,18 +562,11 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  const int ntl = (cnt + kTcTile - 1) / kTcTile;
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcTile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint32_t sA_hi = smem_u32(tc.sA), sA_lo = sA_hi + 8192;
-  constexpr bool kSingle = kTcTile == 128;  // one 16 KB tile and one 128-column accumulator instead of two of each
-  auto load_tile = [&](int t) {  // thread 0: one bulk copy (hi + lo parts of kTcTile leaves)
-    const int b = kSingle ? 0 : (t & 1);
-    mbar_expect_tx(&bars[b], (uint32_t)(kTcTileFloats * 4));
-    tma_load_1d(smem_tiles + b * tile_bytes, feat + (size_t)t * kTcTileFloats, (uint32_t)(kTcTileFloats * 4), &bars[b]);
-  };
-  auto issue_mma = [&](int t) {  // thread 0: wait for the tile, six MMAs into accumulator buffer t & 1, commit
-    const int b = kSingle ? 0 : (t & 1);
-    mbar_wait(&bars[b], ((b ? use1 : use0) + (uint32_t)(kSingle ? t : (t >> 1))) & 1);  // use count of buffer b within this pass
+  auto issue_mma = [&](int t) {  // warp 0 (converged): wait for the tile's bytes, six MMAs into accumulator t mod kTcBufs, commit
+    const int b = t % kTcBufs;
+    mbar_wait(&bars[b], ((b ? use1 : use0) + (uint32_t)(t / kTcBufs)) & 1);  // use count of stage b within this pass
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t sB_hi = smem_u32(smem_tiles + b * tile_bytes), sB_lo = sB_hi + kTcTile * 64;
     const uint32_t d = tc.tmem + (uint32_t)(b * kTcTile);
@@ -540,93 +576,110 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
     umma_tf32(d, umma_desc(sA_hi + 256, 128, 512), umma_desc(sB_lo + 256, 128, 512), idesc, 1u);
     umma_tf32(d, umma_desc(sA_lo, 128, 512), umma_desc(sB_hi, 128, 512), idesc, 1u);
     umma_tf32(d, umma_desc(sA_lo + 256, 128, 512), umma_desc(sB_hi + 256, 128, 512), idesc, 1u);
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&tc.mbars[b])) : "memory");
+    umma_commit(&tc.mbars[b]);
   };
-  if (tid == 0) {
-    if (!kSingle && ntl > 1) load_tile(1);
+  if (tid < 32) {  // every accumulator is free at the start of a pass
     issue_mma(0);
+    if (kTcBufs > 1 && ntl > 1) issue_mma(1);
   }
-  float nm = -m;
   const uint32_t lane_base = (uint32_t)((tid >> 5) * 32) << 16;
 #ifdef CB2_TC_PROF
-  long long pw = 0, pl = 0, pc_ = 0, ps = 0, p0;
+  long long pw = 0, pc_ = 0, ps = 0, p0, pld = 0, pfree = 0, pissue = 0;
 #endif
   for (int t = 0; t < ntl; ++t) {
 #ifdef CB2_TC_PROF
     p0 = clock64();
 #endif
-    const int b = kSingle ? 0 : (t & 1);
-    if (!kSingle && tid == 0 && t + 1 < ntl) issue_mma(t + 1);  // the tensor core works on the next tile while this one is summed
+    const int b = t % kTcBufs;
     mbar_wait(&tc.mbars[b], (b ? tc.mu1 : tc.mu0) & 1);
     if (b) ++tc.mu1; else ++tc.mu0;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #ifdef CB2_TC_PROF
     pw += clock64() - p0; p0 = clock64();
 #endif
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == 0 && t + (kSingle ? 1 : 2) < ntl) load_tile(t + (kSingle ? 1 : 2));   // MMA(t) is complete: its tile may be refilled
+    if (tid == 0 && t + kTcBufs < ntl) load_tile(t + kTcBufs);   // MMA(t) is complete: its stage may be refilled
+    const float csum0 = csum;
+    const int cidx0 = cidx;
+    bool init = t == 0;  // the reference starts at the score of the level's first leaf
+    for (;;) {
+      float nm = -m;
+      float gmax = -INFINITY;
 #pragma unroll 1  // one copy of the 32-leaf body: the kernel is large enough to miss in the instruction cache
-    for (int c0 = 0; c0 < kTcTile; c0 += 32) {
-      if (t * kTcTile + c0 >= cnt) break;  // only padding leaves left
-      uint32_t r[32];
-      const uint32_t taddr = tc.tmem + lane_base + (uint32_t)(b * kTcTile + c0);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int c0 = 0; c0 < kTcTile; c0 += 32) {
+        const int z0 = t * kTcTile + c0;
+        if (z0 >= cnt) break;  // only padding leaves left
+        uint32_t r[32];
 #ifdef CB2_TC_PROF
-      pl += clock64() - p0; p0 = clock64();
+        long long q0 = clock64();
 #endif
-      if (t == 0 && c0 == 0) { m = __uint_as_float(r[0]); nm = -m; }  // the reference starts at the level's first leaf
+        tmem_ld32(tc.tmem + lane_base + (uint32_t)(b * kTcTile + c0), r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#ifdef CB2_TC_PROF
+        pld += clock64() - q0;
+#endif
+        if (init) { m = __uint_as_float(r[0]); nm = -m; init = false; }
+        if (z0 + 32 > cnt) {  // the block that straddles the end of the level: padding leaves carry no mass
 #pragma unroll
-      for (int g0 = 0; g0 < 32; g0 += kG) {
-        const int z = t * kTcTile + c0 + g0;
-        if (z >= cnt) break;
-        float e[kG];
-#pragma unroll
-        for (int g = 0; g < kG; ++g) e[g] = __uint_as_float(r[g0 + g]) + nm;
-        if (z + kG > cnt) {  // the group that straddles the end of the level: padding leaves carry no mass
-#pragma unroll
-          for (int g = 0; g < kG; ++g) if (z + g >= cnt) e[g] = -INFINITY;
+          for (int g = 0; g < 32; ++g)
+            if (z0 + g >= cnt) r[g] = 0xff800000u;  // -inf
         }
-        float gm = e[0];
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int g = 1; g < kG; ++g) gm = fmaxf(gm, e[g]);
-        if (gm > 60.f) {  // rare: raise the reference (same rule as tile_pass)
-          const float sc = fast_exp2(-gm);
-          csum *= sc;
-          for (int c = 0; c < cidx; ++c) chunk[c * kS + tid] *= sc;
-          m += gm;
-#pragma unroll
-          for (int g = 0; g < kG; ++g) e[g] -= gm;
-          nm = -m;
+        for (int g = 0; g < 32; ++g) {
+          const float e = __uint_as_float(r[g]) + nm;
+          gmax = fmaxf(gmax, e);
+          s[g & 3] += fast_exp2(e);
         }
-#pragma unroll
-        for (int g = 0; g < kG; ++g) csum += fast_exp2(e[g]);
-        if (((z + kG) & (CH - 1)) == 0 && z + kG <= cnt) { chunk[cidx * kS + tid] = csum; csum = 0.f; ++cidx; }
+        csum += (s[0] + s[1]) + (s[2] + s[3]);
+        if (((z0 + 32) & (CH - 1)) == 0 && z0 + 32 <= cnt) { chunk[cidx * kS + tid] = csum; csum = 0.f; ++cidx; }
       }
-#ifdef CB2_TC_PROF
-      pc_ += clock64() - p0; p0 = clock64();
-#endif
+      // the sync.aligned accumulator loads need the whole warp: a warp repeats the tile if any of its chains is above the threshold
+      if (!__any_sync(0xffffffffu, gmax > 60.f)) break;
+      if (gmax > 60.f) {
+        const float up = gmax, sc = fast_exp2(-up);
+        m += up;
+        csum = csum0 * sc;
+        for (int c = 0; c < cidx0; ++c) chunk[c * kS + tid] *= sc;
+      } else {
+        csum = csum0;
+      }
+      cidx = cidx0;
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();  // accumulator buffer b is free for MMA(t + 2)
-    if (kSingle && tid == 0 && t + 1 < ntl) issue_mma(t + 1);
+#ifdef CB2_TC_PROF
+    pc_ += clock64() - p0; p0 = clock64();
+#endif
+    if (t + kTcBufs < ntl) {  // release accumulator b; thread 0 refills it once every warp has
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&tc.mbars[2 + b]);
+      if (tid < 32) {
+#ifdef CB2_TC_PROF
+        long long q0 = clock64();
+#endif
+        mbar_wait(&tc.mbars[2 + b], ((b ? tc.fu1 : tc.fu0) + (uint32_t)(t / kTcBufs)) & 1);
+#ifdef CB2_TC_PROF
+        pfree += clock64() - q0; q0 = clock64();
+#endif
+        issue_mma(t + kTcBufs);
+#ifdef CB2_TC_PROF
+        pissue += clock64() - q0;
+#endif
+      }
+    }
 #ifdef CB2_TC_PROF
     ps += clock64() - p0;
 #endif
   }
 #ifdef CB2_TC_PROF
-  if (blockIdx.x == 0 && (tid == 32 || tid == 0) && ntl >= 32) printf("tc prof tid %d tiles %d (clk/tile): wait-mma %lld ld %lld compute %lld sync+issue %lld\n", tid, ntl, pw / ntl, pl / ntl, pc_ / ntl, ps / ntl);
+  if (blockIdx.x == 0 && (tid == 32 || tid == 0) && ntl >= 32) printf("tc prof tid %d tiles %d (clk/tile): wait-mma %lld ld+compute %lld (ld latency %lld) release+issue %lld (wait-free %lld tma-wait+issue %lld)\n", tid, ntl, pw / ntl, pc_ / ntl, pld / ntl, ps / ntl, pfree / ntl, pissue / ntl);
 #endif
-  // every thread keeps the phase counters of the bulk-copy barriers in step (only thread 0 waited on them here)
-  use0 += (uint32_t)(kSingle ? ntl : ((ntl + 1) >> 1));
-  use1 += (uint32_t)(kSingle ? 0 : (ntl >> 1));
+  // every thread keeps the phase counters in step (only thread 0 waited on the copy and the accumulator-free barriers)
+  const int nrel0 = ntl > kTcBufs ? (ntl - kTcBufs + (kTcBufs - 1)) / kTcBufs : 0;  // releases of buffer 0: tiles t = 0, kTcBufs, .. with t + kTcBufs < ntl
+  const int nrel1 = (kTcBufs > 1 && ntl > kTcBufs) ? (ntl - kTcBufs) / kTcBufs : 0;
+  tc.fu0 += (uint32_t)nrel0;
+  tc.fu1 += (uint32_t)nrel1;
+  use0 += (uint32_t)((ntl + kTcBufs - 1) / kTcBufs);
+  use1 += (uint32_t)(kTcBufs > 1 ? ntl / kTcBufs : 0);
 }
 
 #ifdef CB2_GIBBS_PROF
@@ -663,8 +716,8 @@ gibbs_kernel(const GibbsArgs a) {
     after = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(after) + 127) & ~(uintptr_t)127);
     tc.sA = reinterpret_cast<float*>(after);
     tc.mbars = reinterpret_cast<uint64_t*>(after + 16384);
-    tmem_slot = reinterpret_cast<uint32_t*>(after + 16384 + 16);
-    tc.mu0 = tc.mu1 = 0;
+    tmem_slot = reinterpret_cast<uint32_t*>(after + 16384 + 32);
+    tc.mu0 = tc.mu1 = tc.fu0 = tc.fu1 = 0;
   }
 
   const int tid = threadIdx.x;
@@ -688,7 +741,10 @@ gibbs_kernel(const GibbsArgs a) {
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
-    if constexpr (kTC) { mbar_init(&tc.mbars[0], 1); mbar_init(&tc.mbars[1], 1); }
+    if constexpr (kTC) {
+      mbar_init(&tc.mbars[0], 1); mbar_init(&tc.mbars[1], 1);
+      mbar_init(&tc.mbars[2], NT / 32); mbar_init(&tc.mbars[3], NT / 32);  // accumulator-free: one arrival per warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if constexpr (kTC) {
@@ -794,6 +850,7 @@ gibbs_kernel(const GibbsArgs a) {
           if (leaf && dj.feat_off32 != 0xffffffffu) {  // CTA-uniform conditions: every thread reaches the vote
             const bool cta_flat = circ == 0u || __syncthreads_and(nowrap ? 1 : 0) != 0;
             if (cta_flat) {
+              if (CH < 32) CH = 32;  // the tensor-core pass sums blocks of 32 leaves (pass 2 below scans the same chunks)
               leaf_pass_tc<T, DIM>(reinterpret_cast<const float*>(pool) + (size_t)dj.feat_off32 * 32, cnt, CH, cc[0], dj.uniform != 0, smem_raw, TILE_BYTES,
                                    bars, use0, use1, tc, reinterpret_cast<float*>(chunk), tid, m[0], csum[0], cidx);
               done_tc = true;
@@ -879,7 +936,7 @@ gibbs_kernel(const GibbsArgs a) {
   }
 
 #ifdef CB2_GIBBS_PROF
-  if (blockIdx.x == 0 && (tid & 31) == 0)
+  if (blockIdx.x == gridDim.x / 2 && (tid & 31) == 0)  // a CTA from the middle of the grid: the SM is fully loaded
     printf("gibbs prof warp %d (clk): other %lld combine %lld pass1-coarse %lld pass1-leaf %lld cdf %lld pass2 %lld\n", tid >> 5, gprof[0], gprof[1], gprof[2], gprof[3], gprof[4], gprof[5]);
 #endif
   // final point: product of all selected kernels plus one Gaussian draw; coordinates were stored relative to the centre of

@@ -53,18 +53,116 @@ class ScatterAlignPose3(_ScatterAlignPose):
 
 @dataclass
 class CalcFactor:
-    """The slice of IIF.CalcFactor the factor uses: .factor, .cache, ._allowThreads."""
+    """The slice of IIF.CalcFactor the factor uses: .factor, .cache, ._allowThreads.  Calling it evaluates the factor
+    residual `(cf::CalcFactor{<:ScatterAlignPose2/3})(X, p, q)` (R:ext/Images/ScatterAlignPose2.jl:216-231)."""
     factor: object
     cache: dict = field(default_factory=dict)
     _allowThreads: bool = True
 
+    def __call__(self, X, p, q, ctx=None):
+        """X: tangent coordinates of the measurement at the identity, p / q: pose coordinates ([x, y, theta] or
+        [t; rotation vector]); one particle (1-D arrays) or K particles (K x ncoord).  Returns
+        `vee(M, q, log(M, q, p o exp(M, e0, X)))` -- computed for all particles in one device launch (cb2_se_residual_batch)."""
+        from . import se_residual_batch
+        X = np.asarray(X, dtype=np.float64)
+        one = X.ndim == 1
+        out = se_residual_batch(self.factor.DIM, np.atleast_2d(X), np.atleast_2d(p), np.atleast_2d(q), ctx=ctx)
+        return out[0] if one else out
+
+
+def getManifold(fnc):
+    """getManifold(::ScatterAlignPose2) = getManifold(Pose2Pose2), Pose3 likewise (R:ext/Images/ScatterAlignPose2.jl:111-112)."""
+    return "SpecialEuclidean(2)" if fnc.DIM == 2 else "SpecialEuclidean(3)"
+
 
 def preambleCache(dfg, vars, fnc):
-    """Runs once at addFactor!.  Mirrors the named tuple (;M,e0,smps1,smps2,bw,score) of the reference; the
-    sample buffers live on the device inside cb2_scatter_align, so only sizes are recorded here."""
+    """Runs once at addFactor! (R:ext/Images/ScatterAlignPose2.jl:115-152).  With `useStashing` the two clouds are first
+    reconstituted from the blob store: `getData(dfg, label, UUID(dataEntry))` returns the JSON of a PackedManifoldKernelDensity,
+    which replaces the (parched) cloud the factor was unpacked with (:124-137).  Mirrors the named tuple
+    (;M,e0,smps1,smps2,bw,score) of the reference; the sample buffers live on the device inside cb2_scatter_align, so only
+    sizes are recorded here."""
+    al = fnc.align
+    if al.useStashing:
+        from .serialization import unpackDistribution
+        if dfg is None or not hasattr(dfg, "getData"):
+            raise ValueError("useStashing needs a graph with a blob store (getData)")
+        for va, de, which in zip(vars, (al.dataEntry_cloud1, al.dataEntry_cloud2), ("cloud1", "cloud2")):
+            if not de:
+                raise AssertionError(f"cannot reconstitute {type(fnc).__name__} without necessary data entry, only have {de!r}")
+            _, blob = dfg.getData(getattr(va, "label", va), de)
+            cld = unpackDistribution(blob.decode() if isinstance(blob, (bytes, bytearray)) else blob)
+            _update(getattr(al, which), cld)
     # sample_count < 0 selects the ICP branch (SURVEY sec. 8f N3): no sample buffers, the clouds are aligned as they are
-    M = "SpecialEuclidean(2)" if fnc.DIM == 2 else "SpecialEuclidean(3)"
-    return dict(M=M, e0=np.zeros(fnc.ncoord), smps1=None, smps2=None, bw=np.array([fnc.align.bw]), score=[0.0])
+    return dict(M=getManifold(fnc), e0=np.zeros(fnc.ncoord), smps1=None, smps2=None, bw=np.array([al.bw]), score=[0.0])
+
+
+def _update(dst, src):
+    """`_update!(cl, cld)`: the stored belief takes the points and bandwidth of the reconstituted one, in place."""
+    dst.pts, dst.bw = src.pts, src.bw
+    dst.N, dst.d = src.pts.shape
+    dst.weights = src.weights
+
+
+def parchDistribution(mkd):
+    """IIF.parchDistribution(::ManifoldKernelDensity): the belief reduced to its first point (same bandwidth, partial,
+    infoPerCoord) -- what a stashed factor carries instead of the full cloud (R:ext/Images/ScatterAlignPose2.jl:362-367)."""
+    from . import ManifoldKernelDensity
+    return ManifoldKernelDensity(mkd.manifold, mkd.pts[:1].copy(), mkd.bw.copy(), None, mkd.partial, mkd.infoPerCoord)
+
+
+_PACKED_TYPE = {2: "Caesar.PackedScatterAlignPose2", 3: "Caesar.PackedScatterAlignPose3"}
+
+
+def packScatterAlign(arp):
+    """`convert(PackedScatterAlignPose2/3, arp)` (R:ext/Images/ScatterAlignPose2.jl:354-385; fields
+    R:ext/factors/ScatterAlignPose.jl:100-132): both clouds as PackedManifoldKernelDensity dictionaries -- parched to a single
+    point when `useStashing`, in which case both data-entry identifiers must be present."""
+    from .serialization import packDistribution
+    al = arp.align
+    cld1, cld2 = al.cloud1, al.cloud2
+    if al.useStashing:
+        if not al.dataEntry_cloud1:
+            raise AssertionError("packing of ScatterAlignPose asked to be `useStashing=true` yet no `.dataEntry_cloud1` exists for later loading")
+        if not al.dataEntry_cloud2:
+            raise AssertionError("packing of ScatterAlignPose asked to be `useStashing=true` yet no `.dataEntry_cloud2` exists for later loading")
+        cld1, cld2 = parchDistribution(cld1), parchDistribution(cld2)
+    return {"_type": _PACKED_TYPE[arp.DIM], "cloud1": packDistribution(cld1), "cloud2": packDistribution(cld2),
+            "gridscale": al.gridscale, "sample_count": al.sample_count, "bw": al.bw, "useStashing": bool(al.useStashing),
+            "dataEntry_cloud1": al.dataEntry_cloud1, "dataEntry_cloud2": al.dataEntry_cloud2, "dataStoreHint": al.dataStoreHint}
+
+
+def unpackScatterAlign(parp):
+    """`convert(ScatterAlignPose2/3, parp)` (R:ext/Images/ScatterAlignPose2.jl:387-427).  Accepts the dictionary or its JSON."""
+    import json
+    from .serialization import unpackDistribution
+    if isinstance(parp, (str, bytes)):
+        parp = json.loads(parp)
+    kinds = {v: k for k, v in _PACKED_TYPE.items()}
+    if parp.get("_type") not in kinds:
+        raise ValueError(f"unsupported packed factor type {parp.get('_type')!r}")
+    cls = ScatterAlignPose2 if kinds[parp["_type"]] == 2 else ScatterAlignPose3
+    return cls(cloud1=unpackDistribution(parp["cloud1"]), cloud2=unpackDistribution(parp["cloud2"]),
+               sample_count=parp.get("sample_count", 50), bw=parp.get("bw", 0.01), rescale=parp.get("gridscale", 1.0),
+               useStashing=parp.get("useStashing", False), dataEntry_cloud1=parp.get("dataEntry_cloud1", ""),
+               dataEntry_cloud2=parp.get("dataEntry_cloud2", ""), dataStoreHint=parp.get("dataStoreHint", ""))
+
+
+class BlobStoreGraph:
+    """The two DFG calls the stashed factor needs (R:test/testScatterAlignParched.jl:62-80,:118-127): `addData!` stores a blob
+    under a variable label and returns its entry id, `getData` fetches it back.  In-memory stand-in for a FolderStore."""
+
+    def __init__(self):
+        self._blobs = {}
+
+    def addData(self, label, key, blob):
+        import uuid
+        eid = str(uuid.uuid5(uuid.NAMESPACE_OID, f"{label}/{key}/{len(self._blobs)}"))
+        self._blobs[(str(label), eid)] = (key, bytes(blob))
+        return eid
+
+    def getData(self, label, entry_id):
+        key, blob = self._blobs[(str(label), str(entry_id))]
+        return key, blob
 
 
 def getSample(cf, K=1, seed=0, x0=None, max_iter=200, g_tol=1e-8, ctx=None, return_info=False):

@@ -90,7 +90,7 @@ def approxConvBatch_dev(convs, slab, seed=0, ctx=None):
     outs = []
     for b, c in enumerate(convs):
         kind, rev = int(c["kind"]), int(bool(c.get("reverse", False)))
-        dt = 2 if (kind == 2 and not rev) else 3
+        nz, dt = (6, 6) if kind >= 3 else (3, 2 if (kind == 2 and not rev) else 3)
         N = int(c["N"])
         out = DeviceArray(slab.take(N * dt * 8), N, dt)
         outs.append(out)
@@ -101,11 +101,11 @@ def approxConvBatch_dev(convs, slab, seed=0, ctx=None):
         d.n_aux = 0 if aux is None else aux.N
         d.src = None if src is None else src.ptr
         d.aux = None if aux is None else aux.ptr
-        mean = np.resize(np.asarray(c["mean"], dtype=np.float64), 3)
-        chol = np.asarray(c["chol"], dtype=np.float64).reshape(9)
-        for i in range(3):
+        mean = np.resize(np.asarray(c["mean"], dtype=np.float64), nz)
+        chol = np.asarray(c["chol"], dtype=np.float64).reshape(nz * nz)
+        for i in range(nz):
             d.mean[i] = mean[i]
-        for i in range(9):
+        for i in range(nz * nz):
             d.chol[i] = chol[i]
         d.out = out.ptr
     ctx.check(_capi.lib().cb2_approx_conv_batch_dev(ctx._h, descs, B, int(seed)))

@@ -173,7 +173,9 @@ int cb2_scatter_align(cb2_ctx* ctx, const cb2_density* cloud1, const cb2_density
 typedef enum {
   CB2_FACTOR_PRIOR_POSE2 = 0,               /* target ~ N(mean, L L^T), no source */
   CB2_FACTOR_POSE2POSE2 = 1,                /* forward: x_j = x_i o exp(z);  reverse: x_i = x_j o exp(z)^-1 */
-  CB2_FACTOR_POSE2POINT2_BEARINGRANGE = 2   /* forward: landmark from pose;  reverse: pose position from landmark, heading from aux */
+  CB2_FACTOR_POSE2POINT2_BEARINGRANGE = 2,  /* forward: landmark from pose;  reverse: pose position from landmark, heading from aux */
+  CB2_FACTOR_PRIOR_POSE3 = 3,               /* Pose3 coordinates [t; rotation vector]: t = mean_t + n_t, R = Exp(mean_w) Exp(n_w) */
+  CB2_FACTOR_POSE3POSE3 = 4                 /* forward: x_j = x_i o exp(z) on SE(3);  reverse: x_i = x_j o exp(z)^-1 */
 } cb2_factor_kind;
 
 typedef struct {
@@ -185,12 +187,19 @@ typedef struct {
   const double* aux;   /* reverse bearing-range only: 3 x n_aux current samples of the target pose (heading is kept) */
   int32_t n_aux;
   uint32_t stream;     /* Philox stream id of this convolution */
-  double mean[3];      /* Pose2 prior / Pose2Pose2: [x, y, theta]; bearing-range: [bearing, range, 0] */
-  double chol[9];      /* lower Cholesky factor L of the 3x3 noise covariance, row-major; bearing-range: L = diag(sigma_b, sigma_r, 0) */
-  double* out;         /* d_tgt x N (Pose2: 3, Point2: 2) */
+  double mean[6];      /* Pose2 prior / Pose2Pose2: [x, y, theta]; bearing-range: [bearing, range, 0]; Pose3 kinds: [t; rotation vector] */
+  double chol[36];     /* lower Cholesky factor L of the noise covariance, row-major n x n in the first n*n entries (n = 3, Pose3
+                          kinds: n = 6); bearing-range: L = diag(sigma_b, sigma_r, 0) */
+  double* out;         /* d_tgt x N (Pose2: 3, Point2: 2, Pose3: 6) */
 } cb2_conv_desc;
 
 int cb2_approx_conv_batch(cb2_ctx* ctx, const cb2_conv_desc* descs, int B, uint64_t seed);
+
+/* ---- residual of the relative-pose factors, K particles per call ----------------------------------------------------
+ * (cf::CalcFactor{<:ScatterAlignPose2/3})(X, p, q) (R:ext/Images/ScatterAlignPose2.jl:216-231; the body is RoME's Pose2Pose2
+ * residual): q^ = p o exp_e0(X), out = vee(M, q, log(M, q, q^)) with the product exponential / logarithm of SpecialEuclidean(n).
+ * dim = 2: coordinates [x, y, theta]; dim = 3: [t; rotation vector].  X, p, q, out: K x ncoord host arrays. */
+int cb2_se_residual_batch(cb2_ctx* ctx, int dim, const double* X, const double* p, const double* q, int K, double* out);
 
 /* ---- device-resident beliefs ------------------------------------------------
  * Across a Gibbs sweep IIF runs, per variable, approxConvBelief -> manikde! -> manifoldProduct -> manikde! and feeds the

@@ -207,12 +207,23 @@ class Tree:
         L.cb2o_tree_free(h)
 
 
+def se_residual(dim, X, p, q):
+    """Residual of the relative-pose factors for K particles: vee(log(q, p o exp(X))), product exp / log (coordinates)."""
+    X, p, q = (_f64(np.atleast_2d(v)) for v in (X, p, q))
+    out = np.zeros_like(X)
+    rc = lib().cb2o_se_residual(int(dim), _p(X), _p(p), _p(q), X.shape[0], _p(out))
+    assert rc == 0
+    return out
+
+
 def approx_conv(kind, reverse, N, mean, chol, seed, stream=0, src=None, aux=None):
-    """Closed-form approxConv (kind 0 Pose2 prior, 1 Pose2Pose2, 2 Pose2Point2BearingRange); returns N x d_tgt."""
-    mean, chol = _f64(np.resize(np.asarray(mean, dtype=np.float64), 3)), _f64(np.asarray(chol, dtype=np.float64).reshape(9))
+    """Closed-form approxConv (kind 0 Pose2 prior, 1 Pose2Pose2, 2 Pose2Point2BearingRange, 3 Pose3 prior, 4 Pose3Pose3);
+    returns N x d_tgt."""
+    n = 6 if kind >= 3 else 3
+    mean, chol = _f64(np.resize(np.asarray(mean, dtype=np.float64), n)), _f64(np.asarray(chol, dtype=np.float64).reshape(n * n))
     src = None if src is None else _f64(src)
     aux = None if aux is None else _f64(aux)
-    dt = 2 if (kind == 2 and not reverse) else 3
+    dt = 6 if kind >= 3 else (2 if (kind == 2 and not reverse) else 3)
     out = np.zeros((N, dt))
     rc = lib().cb2o_approx_conv(kind, int(reverse), N, _p(src), 0 if src is None else src.shape[0], _p(aux),
                                 0 if aux is None else aux.shape[0], stream, _p(mean), _p(chol), C.c_uint64(seed), _p(out))

@@ -538,9 +538,99 @@ void cb2o_set_num_threads(int n) {
 /* ------------------------------------------------------------------ approxConv for closed-form factors
  * Restates the closed-form per-particle solves of R:docs/src/principles/approxConvDensities.md:25-34 for Pose2 priors,
  * Pose2Pose2 and Pose2Point2BearingRange; same Philox draws (tag 4) as caesar.jl_b200/csrc/conv.cu. */
+/* rotation vector of R through the unit quaternion (Shepperd's branch on the largest diagonal term), angle in [0, pi] */
+static void so3_log(const double* R, double* w) {
+  const double tr = R[0] + R[4] + R[8];
+  double q[4];
+  if (tr > 0.0) {
+    const double s = sqrt(tr + 1.0) * 2.0;
+    q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s;
+  } else if (R[0] > R[4] && R[0] > R[8]) {
+    const double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2.0;
+    q[0] = (R[7] - R[5]) / s; q[1] = 0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s;
+  } else if (R[4] > R[8]) {
+    const double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2.0;
+    q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) / s;
+  } else {
+    const double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2.0;
+    q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = 0.25 * s;
+  }
+  if (q[0] < 0.0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+  const double n = sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double f = n < 1e-12 ? 2.0 : 2.0 * atan2(n, q[0]) / n;
+  w[0] = f * q[1]; w[1] = f * q[2]; w[2] = f * q[3];
+}
+static void mat3_mul(const double* A, const double* B, double* C, int transA, int transB) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += (transA ? A[k * 3 + i] : A[i * 3 + k]) * (transB ? B[j * 3 + k] : B[k * 3 + j]);
+      C[i * 3 + j] = s;
+    }
+}
+
+/* kinds 3 (Pose3 prior) and 4 (Pose3Pose3): coordinates [t; rotation vector], noise X = L z in the tangent space, product
+ * exponential (translation = coordinates), R:docs/src/principles/approxConvDensities.md:25-34 with a Pose3Pose3 factor */
+static void approx_conv_pose3(int kind, int reverse, int N, const double* src, int n_src, uint32_t stream, const double* mean,
+                              const double* chol, uint64_t seed, double* out) {
+  for (int i = 0; i < N; ++i) {
+    double z[6], X[6], R1[9], R2[9], R3[9];
+    for (int k = 0; k < 6; ++k) z[k] = cb2o_normal(seed, (uint32_t)i, (uint32_t)k, stream, 4, 53);
+    for (int r = 0; r < 6; ++r) {
+      double v = 0;
+      for (int k = 0; k < 6; ++k) v += chol[r * 6 + k] * z[k];
+      X[r] = v;
+    }
+    double* o = out + (size_t)i * 6;
+    if (kind == 3) {
+      so3_exp(mean + 3, R1); so3_exp(X + 3, R2);
+      mat3_mul(R1, R2, R3, 0, 0);
+      for (int k = 0; k < 3; ++k) o[k] = mean[k] + X[k];
+      so3_log(R3, o + 3);
+      continue;
+    }
+    for (int r = 0; r < 6; ++r) X[r] += mean[r];
+    const double* p = src + (size_t)(i % n_src) * 6;
+    so3_exp(p + 3, R1); so3_exp(X + 3, R2);
+    if (!reverse) {
+      mat3_mul(R1, R2, R3, 0, 0);
+      for (int k = 0; k < 3; ++k) o[k] = p[k] + R1[k * 3] * X[0] + R1[k * 3 + 1] * X[1] + R1[k * 3 + 2] * X[2];
+    } else {
+      mat3_mul(R1, R2, R3, 0, 1);
+      for (int k = 0; k < 3; ++k) o[k] = p[k] - (R3[k * 3] * X[0] + R3[k * 3 + 1] * X[1] + R3[k * 3 + 2] * X[2]);
+    }
+    so3_log(R3, o + 3);
+  }
+}
+
+/* residual of the relative-pose factors (R:ext/Images/ScatterAlignPose2.jl:216-231, body of RoME's Pose2Pose2):
+ *   q^ = p o exp_e0(X);  out = vee(M, q, log(M, q, q^))   with the product exponential / logarithm of SpecialEuclidean(n). */
+int cb2o_se_residual(int dim, const double* X, const double* p, const double* q, int K, double* out) {
+  if ((dim != 2 && dim != 3) || K <= 0) return -1;
+  for (int i = 0; i < K; ++i) {
+    if (dim == 2) {
+      const double *x = X + (size_t)i * 3, *pp = p + (size_t)i * 3, *qq = q + (size_t)i * 3;
+      const double sn = sin(pp[2]), cs = cos(pp[2]);
+      out[(size_t)i * 3] = pp[0] + cs * x[0] - sn * x[1] - qq[0];
+      out[(size_t)i * 3 + 1] = pp[1] + sn * x[0] + cs * x[1] - qq[1];
+      out[(size_t)i * 3 + 2] = wrap_pi(pp[2] + x[2] - qq[2]);
+    } else {
+      const double *x = X + (size_t)i * 6, *pp = p + (size_t)i * 6, *qq = q + (size_t)i * 6;
+      double Rp[9], Rx[9], Rq[9], Rh[9], Re[9];
+      so3_exp(pp + 3, Rp); so3_exp(x + 3, Rx); so3_exp(qq + 3, Rq);
+      mat3_mul(Rp, Rx, Rh, 0, 0);
+      mat3_mul(Rq, Rh, Re, 1, 0);
+      for (int k = 0; k < 3; ++k) out[(size_t)i * 6 + k] = pp[k] + Rp[k * 3] * x[0] + Rp[k * 3 + 1] * x[1] + Rp[k * 3 + 2] * x[2] - qq[k];
+      so3_log(Re, out + (size_t)i * 6 + 3);
+    }
+  }
+  return 0;
+}
+
 int cb2o_approx_conv(int kind, int reverse, int N, const double* src, int n_src, const double* aux, int n_aux,
                      uint32_t stream, const double* mean, const double* chol, uint64_t seed, double* out) {
-  if (kind < 0 || kind > 2 || N <= 0) return -1;
+  if (kind < 0 || kind > 4 || N <= 0) return -1;
+  if (kind >= 3) { approx_conv_pose3(kind, reverse, N, src, n_src, stream, mean, chol, seed, out); return 0; }
   for (int i = 0; i < N; ++i) {
     double z[3], nz[3];
     for (int k = 0; k < 3; ++k) z[k] = cb2o_normal(seed, (uint32_t)i, (uint32_t)k, stream, 4, 53);

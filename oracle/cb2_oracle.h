@@ -90,6 +90,9 @@ const double* cb2o_tree_level_wt(const cb2o_tree* t, int level);   /* cnt */
 int cb2o_approx_conv(int kind, int reverse, int N, const double* src, int n_src, const double* aux, int n_aux,
                      uint32_t stream, const double* mean, const double* chol, uint64_t seed, double* out);
 
+/* residual of the relative-pose factors, K particles (R:ext/Images/ScatterAlignPose2.jl:216-231); coordinates as cb2_se_residual_batch */
+int cb2o_se_residual(int dim, const double* X, const double* p, const double* q, int K, double* out);
+
 /* ICP branch of ScatterAlign: simpleICP as vendored in R:src/3rdParty/_PCL/services/ICP_Simple.jl:239-332.
  * fix: nf x 3, mov: nm x 3; perturb: K x 6 coordinates (or NULL) applied to mov with backward = 1 before the alignment
  * (R:ext/Images/ScatterAlignPose2.jl:195-196).  H_out: K x 16 (row-major 4 x 4, fix_H_mov); stats_out: K x 4 =
