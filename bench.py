@@ -248,9 +248,14 @@ def main():
     # device result == host-API result for the same seed (the two arms run the same kernels)
     assert np.isfinite(pin_out[0].numpy()).all() and (bw_out[0] > 0).all()
 
+    strong = strong_scaling(args, cb, ctx, L, torch, dist if world > 1 else None, tstream, rank, world, descs, circ, dev_out, dev_lab, dev_bwo,
+                            ms_total / args.steps)
     extra = {}
     if not args.no_extras:
         extra = mmd_extras(cb, ctx, torch, tstream, rank, world, dist if world > 1 else None)
+        lp = large_product(cb, ctx, L, torch, dist if world > 1 else None, tstream, rank, world, make_variable(0), circ)  # the same product on every rank
+        if lp:
+            extra["large_product"] = lp
 
     if rank != 0:
         if world > 1:
@@ -264,15 +269,16 @@ def main():
     except Exception:
         pass
     sm_mhz_max = float(peaks.get("sm_max_mhz", 1965.0))
-    fp32_peak = 148 * 128 * 2 * sm_mhz_max * 1e6 / 1e12   # TFLOP/s
-    sfu_peak = 148 * 16 * sm_mhz_max * 1e6                # MUFU ops/s
+    n_sm = ctx.sm_count
+    fp32_peak = n_sm * 128 * 2 * sm_mhz_max * 1e6 / 1e12   # TFLOP/s
+    sfu_peak = n_sm * 16 * sm_mhz_max * 1e6                # MUFU ops/s
     evals = gibbs_evals_per_variable() * V
     gibbs_ms = stage["gibbs"] / args.steps
     ach = evals * FP32_FLOPS_PER_EVAL / (gibbs_ms * 1e-3) / 1e12 if gibbs_ms > 0 else None
     roofline = {
         "kernel": "gibbs_kernel<float,6,0x38>", "bound": "fp32+sfu (compute-bound; SURVEY 8d: not hbm; the leaf level runs on the tensor cores but K = 16 keeps them 6 % busy)",
         "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (ach / fp32_peak) if ach else None,
-        "peak_source": f"148 SM x 128 FP32 lanes x 2 x {sm_mhz_max:.0f} MHz (clocks.max.sm of MEASURED_PEAKS.json); "
+        "peak_source": f"{n_sm} SM (cb2_device_sm_count) x 128 FP32 lanes x 2 x {sm_mhz_max:.0f} MHz (clocks.max.sm of MEASURED_PEAKS.json); "
                        "MEASURED_PEAKS has no FP32 figure, bf16/HBM peaks do not bound this kernel",
         "algorithmic": {"kernel_evals_per_launch": evals, "flops_per_eval": FP32_FLOPS_PER_EVAL, "sfu_per_eval": 1,
                         "evals_per_s": evals / (gibbs_ms * 1e-3) if gibbs_ms > 0 else None,
@@ -303,13 +309,104 @@ def main():
         "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "timer": "host perf_counter around the synchronous C-ABI call"},
-        "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+        "roofline": roofline, "cpu_baseline": cpu, "strong": strong, "extra": extra,
     }
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_scaling(args, cb, ctx, L, torch, dist, tstream, rank, world, descs, circ, dev_out, dev_lab, dev_bwo, weak_ms):
+    """BASELINE's literal C5 split: the SAME 256 variables dealt over the ranks (256 / world per GPU), every rank's points, labels
+    and bandwidths all-gathered over NCCL inside the timed region.  efficiency = (one GPU's 256-variable step / world) / this step;
+    the one-GPU step is this run's own weak step (every rank just timed 256 variables)."""
+    import ctypes as C
+    if world == 1 or args.vars_per_gpu % world:
+        return None
+    Vs = args.vars_per_gpu // world
+    with torch.cuda.stream(tstream):
+        mine_p = torch.stack(dev_out[:Vs]); mine_l = torch.stack(dev_lab[:Vs]); mine_b = torch.stack(dev_bwo[:Vs])
+        all_p = torch.empty((world,) + tuple(mine_p.shape), dtype=mine_p.dtype, device="cuda")
+        all_l = torch.empty((world,) + tuple(mine_l.shape), dtype=mine_l.dtype, device="cuda")
+        all_b = torch.empty((world,) + tuple(mine_b.shape), dtype=mine_b.dtype, device="cuda")
+
+        def step(seed):
+            ctx.check(L.cb2_product_batch_dev(ctx._h, descs, Vs, circ.ctypes.data_as(C.c_void_p), DIM, seed))
+            torch.stack(dev_out[:Vs], out=mine_p); torch.stack(dev_lab[:Vs], out=mine_l); torch.stack(dev_bwo[:Vs], out=mine_b)
+            dist.all_gather_into_tensor(all_p, mine_p)
+            dist.all_gather_into_tensor(all_l, mine_l)
+            dist.all_gather_into_tensor(all_b, mine_b)
+        for it in range(2):
+            step(300 + it)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = max(3, args.steps)
+        e0.record(tstream)
+        for it in range(n):
+            step(400 + it)
+        e1.record(tstream)
+        tstream.synchronize()
+        stage = {k: ctx.stage_ms(k) for k in ("tree", "gibbs", "bw")}
+    t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ok = bool(torch.isfinite(all_p).all().item())
+    return {"variables_total": args.vars_per_gpu, "variables_per_gpu": Vs, "ms_per_step": ms, "samples_per_s": args.vars_per_gpu * N_OUT / (ms * 1e-3),
+            "one_gpu_ms_per_step": weak_ms, "efficiency": weak_ms / world / ms, "stage_ms_rank0": stage, "finite": ok,
+            "gathered_bytes_per_step": int(all_p.numel() * 8 + all_l.numel() * 4 + all_b.numel() * 8),
+            "note": "strong scaling: 256 variables over the ranks, NCCL all-gather of points + labels + bandwidths inside the timed region"}
+
+
+def large_product(cb, ctx, L, torch, dist, tstream, rank, world, dens, circ):
+    """ONE product with many output samples, the samples split over the ranks (messages replicated, Philox sample
+    index = global index), slices all-gathered over NCCL; the gathered result must equal the single-GPU result bit for bit."""
+    import ctypes as C
+    from importlib import import_module
+    dd = import_module("caesar_jl_b200.distributed")
+    res = {}
+    with torch.cuda.stream(tstream):
+        pts = [torch.from_numpy(p).cuda() for p, _ in dens]
+        bws = [torch.from_numpy(b).cuda() for _, b in dens]
+        arr = (cb.Density * D_MSG)(*[cb.Density(N_KER, pts[j].data_ptr(), bws[j].data_ptr(), None) for j in range(D_MSG)])
+
+        def run_desc(desc):
+            ctx.check(L.cb2_product_batch_dev(ctx._h, desc, 1, circ.ctypes.data_as(C.c_void_p), DIM, 77))
+
+        def make(s0, n, pp, lp):
+            ds = (cb.ProductDesc * 1)()
+            ds[0].dens, ds[0].D, ds[0].Nout, ds[0].niter, ds[0].stream, ds[0].sample_offset = arr, D_MSG, n, 1, 5, s0
+            ds[0].pts_out, ds[0].labels_out, ds[0].bw_out = pp, lp, None
+            return ds
+        for Nout in (32768, 262144):
+            full_p = torch.empty((Nout, DIM), dtype=torch.float64, device="cuda")
+            full_l = torch.empty((Nout, D_MSG), dtype=torch.int32, device="cuda")
+            single = make(0, Nout, full_p.data_ptr(), full_l.data_ptr())
+            run_desc(single)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(tstream); run_desc(single); e1.record(tstream); tstream.synchronize()
+            one_ms = e0.elapsed_time(e1)
+            entry = {"one_gpu_ms": one_ms, "one_gpu_samples_per_s": Nout / (one_ms * 1e-3)}
+            if dist is not None:
+                dd.product_sharded_dev(make, Nout, DIM, D_MSG, dist, torch, run_desc)
+                torch.cuda.synchronize(); dist.barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(tstream)
+                sp, sl = dd.product_sharded_dev(make, Nout, DIM, D_MSG, dist, torch, run_desc)
+                g1.record(tstream); tstream.synchronize()
+                t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sh_ms = float(t.item())
+                same = bool(torch.equal(sp, full_p)) and bool(torch.equal(sl, full_l))
+                entry.update({"sharded_ms": sh_ms, "world": world, "efficiency": one_ms / world / sh_ms, "bit_identical_to_one_gpu": same,
+                              "gathered_bytes": int(Nout * (DIM * 8 + D_MSG * 4))})
+            res[f"Nout{Nout}"] = entry
+    if rank != 0:
+        return None
+    res["shape"] = f"D={D_MSG} messages x N={N_KER} kernels, d={DIM}; output samples split over the ranks, NCCL all-gather of points + labels"
+    return res
 
 
 def mmd_extras(cb, ctx, torch, tstream, rank=0, world=1, dist=None):
@@ -329,11 +426,9 @@ def mmd_extras(cb, ctx, torch, tstream, rank=0, world=1, dist=None):
     with torch.cuda.stream(tstream):
         da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
         out = torch.zeros(3, dtype=torch.float64, device="cuda")
-        r0, r1 = shard_range(P, rank, world)
-
-        def run():
-            ctx.check(L.cb2_mmd_sums_dev(ctx._h, C.c_void_p(da.data_ptr()), P, C.c_void_p(db.data_ptr()), P, 3, 1.0, r0, r1, r0, r1,
-                                         C.c_void_p(out.data_ptr())))
+        def run():  # this rank's share of the symmetric tile list, then the 3-value all-reduce
+            ctx.check(L.cb2_mmd_sums_shard_dev(ctx._h, C.c_void_p(da.data_ptr()), P, C.c_void_p(db.data_ptr()), P, 3, 1.0, rank, world,
+                                               C.c_void_p(out.data_ptr())))
             if dist is not None:
                 dist.all_reduce(out, op=dist.ReduceOp.SUM)
         for _ in range(2):
@@ -354,29 +449,41 @@ def mmd_extras(cb, ctx, torch, tstream, rank=0, world=1, dist=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     sharded_value = sums[0] / (P * P) - 2 * sums[1] / (P * P) + sums[2] / (P * P)
+    # end to end from HOST arrays on every rank: upload of both clouds, this rank's tile shard, NCCL all-reduce of the 3 sums
+    dmmd = import_module("caesar_jl_b200.distributed").mmd
+    dmmd(a, b, 1.0, ctx, dist)
+    if dist is not None:
+        torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    v = dmmd(a, b, 1.0, ctx, dist)
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
     if rank != 0:
         return {}
-    t0 = time.perf_counter()
-    v = cb.mmd(a, b, 1.0, ctx=ctx)
-    e2e_s = time.perf_counter() - t0
     # CPU restatement on a bounded row sample of the same clouds
     rows = 1500
     t0 = time.perf_counter()
-    oracle.mmd_rows(a, b, 1.0, (0, rows), (0, rows))
+    osums = oracle.mmd_rows(a, b, 1.0, (0, rows), (0, rows))
     cpu_s = time.perf_counter() - t0
-    sfu_peak = 148 * 16 * 1965e6
-    # pairs the kernel really evaluates: a full self pair sum (single GPU) uses k(p,q) = k(q,p): diagonal 1024-row blocks
-    # once, the blocks above them once with weight 2; row-sharded runs evaluate every pair of their rows
-    if world == 1:
-        self_eval = sum(min(1024, P - r) * (P - r) for r in range(0, P, 1024))
-        evaluated = 2.0 * self_eval + float(P) * P
-    else:
-        evaluated = pairs
-    assert abs(sharded_value - v) <= 1e-6 * max(abs(v), 1e-3), (sharded_value, v)
-    out = {"mmd_pairs_per_s": pairs / (ms * 1e-3), "mmd_ms": ms, "mmd_points": P, "mmd_value": v, "mmd_row_shards": world,
-           "mmd_e2e_pairs_per_s": pairs / e2e_s, "mmd_evaluated_pairs_per_s": evaluated / (ms * 1e-3),
-           "mmd_sfu_frac": evaluated / (ms * 1e-3) / sfu_peak,
-           "mmd_note": "pairs = N^2+NM+M^2 as the reference evaluates them (SURVEY 8d); sfu_frac uses the pairs the kernel evaluates",
+    # the device against the CPU oracle on that row sample of the SAME 1e5-point clouds (full column count); the full-size
+    # oracle comparison (3e10 pairs, ~20 s of CPU) is tests/test_gpu_configs.py::test_mmd_1e5_points_against_the_full_oracle
+    gsums = cb.mmd_sums(a, b, 1.0, (0, rows), (0, rows), ctx=ctx)
+    assert np.allclose(gsums, np.asarray(osums, dtype=np.float64), rtol=1e-5), (gsums, osums)
+    sfu_peak = ctx.sm_count * 16 * 1965e6
+    # pairs the kernels really evaluate: the self sums use k(p,q) = k(q,p) (diagonal 1024-row blocks once, the blocks above them
+    # once with weight 2); the tile list is dealt over the ranks, so every GPU evaluates 1/world of them
+    self_eval = sum(min(1024, P - r) * (P - r) for r in range(0, P, 1024))
+    evaluated = 2.0 * self_eval + float(P) * P
+    assert abs(sharded_value - v) <= 1e-9 * max(abs(v), 1e-3), (sharded_value, v)
+    out = {"mmd_pairs_per_s": pairs / (ms * 1e-3), "mmd_ms": ms, "mmd_points": P, "mmd_value": v, "mmd_tile_shards": world,
+           "mmd_e2e_pairs_per_s": pairs / e2e_s, "mmd_e2e_s": e2e_s, "mmd_evaluated_pairs_per_s": evaluated / (ms * 1e-3),
+           "mmd_sfu_frac_per_gpu": evaluated / world / (ms * 1e-3) / sfu_peak,
+           "mmd_note": "pairs = N^2+NM+M^2 as the reference evaluates them (SURVEY 8d); sfu_frac_per_gpu = pairs one GPU evaluates "
+                       "(symmetric tile list / world) per second over that GPU's MUFU peak; e2e = host arrays in, value out, on every rank",
+           "mmd_row_sample_vs_oracle_max_rel": float(np.max(np.abs(gsums - osums) / np.abs(osums))),
            "mmd_cpu_pairs_per_s": 3.0 * rows * P / cpu_s, "mmd_cpu_cores": oracle.num_threads(),
            "mmd_cpu_sample": f"rows [0,{rows}) of each of the three pair sums against all {P} columns"}
     # K2: one BFGS evaluation batch of ScatterAlignPose3 = K=13 candidate transforms (value + 2*6 finite-difference

@@ -82,6 +82,11 @@ class Context:
     def sm_count(self):
         return int(_capi.lib().cb2_device_sm_count(self._h))
 
+    def debug_counter(self, which=0, reset=False):
+        v = C.c_uint64()
+        self.check(_capi.lib().cb2_debug_counter(self._h, int(which), int(bool(reset)), C.byref(v)))
+        return int(v.value)
+
     def stage_ms(self, name):
         return float(_capi.lib().cb2_last_stage_ms(self._h, name.encode()))
 
@@ -214,6 +219,17 @@ def mmd_sums(a, b, bw, rows_a=None, rows_b=None, ctx=None):
     out = np.zeros(3)
     ctx.check(_capi.lib().cb2_mmd_sums(ctx._h, ptr(a), a.shape[0], ptr(b), b.shape[0], a.shape[1], float(bw),
                                        ra[0], ra[1], rb[0], rb[1], ptr(out)))
+    return out
+
+
+def mmd_sums_shard(a, b, bw, shard, nshards, ctx=None):
+    """Shard `shard` of `nshards` of the three pair sums (tile list of the symmetric evaluation dealt round-robin): what one GPU
+    of a multi-GPU mmd computes before the 3-value all-reduce."""
+    ctx = ctx or context()
+    a, b = f64(np.atleast_2d(a)), f64(np.atleast_2d(b))
+    out = np.zeros(3)
+    ctx.check(_capi.lib().cb2_mmd_sums_shard(ctx._h, ptr(a), a.shape[0], ptr(b), b.shape[0], a.shape[1], float(bw),
+                                             int(shard), int(nshards), ptr(out)))
     return out
 
 

@@ -16,6 +16,8 @@
 
 template <typename T, int N> struct alignas(16) VecRec { T v[N]; };
 
+__device__ unsigned long long g_pick_fallthrough = 0ull;  // pass-2 re-sums that ended short of their target (see chunk_pick)
+
 struct GibbsArgs {
   const DensMeta* metas;
   const ProdDev* prods;
@@ -411,6 +413,11 @@ __device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, in
       }
     }
   }
+  // The cumulative re-sum fell short of the target: pass 1 and pass 2 round differently (chunk sums are added in another
+  // order; with the tensor-core leaf pass the pass-1 scores come from a 3 x TF32 product, pass 2 from FP32 FMAs, equal to ~1e-6).
+  // The draw then takes the last candidate with mass in the chunk -- the neighbour of the exact answer.  Counted, so that the
+  // tests can bound how often it happens (cb2_debug_counter).
+  if (pick < 0) atomicAdd(&g_pick_fallthrough, 1ull);
   return pick < 0 ? lastpos : pick;
 }
 

@@ -375,7 +375,7 @@ template <typename T, int MODE>
 int run_pairs_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev, int M, int d, double scale,
                   const std::vector<SubSpec>& specs, const std::vector<T>& xf_host, double** result_dev,
                   size_t extra_bytes, void** extra_ptr, bool reuse_prev = false, const double* dim_scale = nullptr,
-                  uint32_t wrap_mask = 0) {
+                  uint32_t wrap_mask = 0, int shard = 0, int nshards = 1) {
   // reuse_prev: the previous call on this context had the same clouds, sub-problems and sizes and nothing else touched
   // the arena since (consecutive cost evaluations of one BFGS batch): the arena layout is a pure function of the
   // sizes, so the converted records and the tile tables are still in place -- only the transforms are uploaded again.
@@ -401,6 +401,20 @@ int run_pairs_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev,
     }
   }
   sub_tile0.push_back((int)tiles.size());
+  if (nshards > 1) {
+    // multi-GPU sharding of the TILE LIST: shard r keeps every nshards-th tile, so the symmetric halving of the self
+    // terms survives the split and every GPU evaluates (N^2/2 + N M + M^2/2) / nshards pairs; tiles stay grouped by sub-problem
+    std::vector<Tile> mine;
+    std::vector<int> st0(specs.size() + 1, 0);
+    for (size_t s = 0; s < specs.size(); ++s) {
+      st0[s] = (int)mine.size();
+      for (int t = sub_tile0[s]; t < sub_tile0[s + 1]; ++t)
+        if (t % nshards == shard) mine.push_back(tiles[t]);
+    }
+    st0[specs.size()] = (int)mine.size();
+    tiles.swap(mine);
+    sub_tile0.swap(st0);
+  }
   const int ntiles = (int)tiles.size(), nsub = (int)specs.size();
 
   size_t need = cb2_align(sizeof(T) * rec * (size_t)N) + cb2_align(sizeof(T) * rec * (size_t)M) +
@@ -460,10 +474,11 @@ __global__ void gather_sums3_kernel(const double* __restrict__ res, double* __re
 
 template <typename T>
 int mmd_sums_dev_impl(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev, int M, int d, double bw,
-                      int ra0, int ra1, int rb0, int rb1, double* sums3_dev) {
+                      int ra0, int ra1, int rb0, int rb1, double* sums3_dev, int shard = 0, int nshards = 1) {
   std::vector<SubSpec> specs = {{0, 0, ra0, ra1, N, -1}, {0, 1, ra0, ra1, M, -1}, {1, 1, rb0, rb1, M, -1}};
   double* res = nullptr;
-  int rc = run_pairs_dev<T, 0>(ctx, a_dev, N, b_dev, M, d, sqrt(bw * CB2_LOG2E), specs, std::vector<T>(), &res, 0, nullptr);
+  int rc = run_pairs_dev<T, 0>(ctx, a_dev, N, b_dev, M, d, sqrt(bw * CB2_LOG2E), specs, std::vector<T>(), &res, 0, nullptr, false, nullptr,
+                               0, shard, nshards);
   if (rc) return rc;
   gather_sums3_kernel<<<1, 32, 0, ctx->stream>>>(res, sums3_dev);
   CB2_CHECK_LAUNCH(ctx, "gather_sums3_kernel");
@@ -609,6 +624,23 @@ extern "C" int cb2_mmd_sums_dev(cb2_ctx* ctx, const double* a_dev, int N, const 
                                     : mmd_sums_dev_impl<float>(ctx, a_dev, N, b_dev, M, d, bw, ra0, ra1, rb0, rb1, sums3_dev);
 }
 
+// Shard `shard` of `nshards` of the three pair sums of mmd(a, b): the tile list of the full (symmetric) evaluation dealt
+// round-robin.  Summing the nshards results (ncclAllReduce of 3 doubles) gives exactly the sums cb2_mmd_sums returns for the
+// full row ranges; each shard evaluates 1/nshards of the pairs the single-GPU kernel evaluates (self terms once per pair).
+extern "C" int cb2_mmd_sums_shard_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev, int M, int d, double bw,
+                                      int shard, int nshards, double* sums3_dev) {
+  if (!ctx) return CB2_ERR_INVALID;
+  cb2_lock g(ctx->mu);
+  int rc = check_cloud_args(ctx, a_dev, N, b_dev, M, d);
+  if (rc) return rc;
+  CB2_REQUIRE(ctx, sums3_dev, "null output");
+  CB2_REQUIRE(ctx, bw > 0 && isfinite(bw), "bw must be positive");
+  CB2_REQUIRE(ctx, nshards >= 1 && shard >= 0 && shard < nshards, "shard %d outside 0..%d", shard, nshards - 1);
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  return ctx->precision == CB2_FP64 ? mmd_sums_dev_impl<double>(ctx, a_dev, N, b_dev, M, d, bw, 0, N, 0, M, sums3_dev, shard, nshards)
+                                    : mmd_sums_dev_impl<float>(ctx, a_dev, N, b_dev, M, d, bw, 0, N, 0, M, sums3_dev, shard, nshards);
+}
+
 // uploads host Float64 arrays into the context's I/O block; used by the (synchronous) host-pointer API
 static int upload_block(cb2_ctx* ctx, const std::vector<const double*>& src, const std::vector<size_t>& count,
                         std::vector<double*>& dev, double** block) {
@@ -653,6 +685,29 @@ extern "C" int cb2_mmd_sums(cb2_ctx* ctx, const double* a, int N, const double* 
     cudaStreamSynchronize(ctx->stream);
   }
   cudaFree(block);
+  return rc;
+}
+
+extern "C" int cb2_mmd_sums_shard(cb2_ctx* ctx, const double* a, int N, const double* b, int M, int d, double bw, int shard,
+                                  int nshards, double* sums3) {
+  if (!ctx) return CB2_ERR_INVALID;
+  cb2_lock g(ctx->mu);
+  int rc = check_cloud_args(ctx, a, N, b, M, d);
+  if (rc) return rc;
+  CB2_REQUIRE(ctx, sums3, "null output");
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<double*> dev;
+  double* block = nullptr;
+  rc = upload_block(ctx, {a, b, nullptr}, {(size_t)N * d, (size_t)M * d, 3}, dev, &block);
+  if (rc) return rc;
+  rc = cb2_mmd_sums_shard_dev(ctx, dev[0], N, dev[1], M, d, bw, shard, nshards, dev[2]);
+  if (rc == CB2_OK) {
+    cudaError_t e = cudaMemcpyAsync(sums3, dev[2], 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = cb2_fail(ctx, CB2_ERR_CUDA, "mmd readback: %s", cudaGetErrorString(e));
+  } else {
+    cudaStreamSynchronize(ctx->stream);
+  }
   return rc;
 }
 

@@ -1043,3 +1043,21 @@ extern "C" int cb2_tree_debug(cb2_ctx* ctx, const cb2_density* den, int d, int l
   cudaFree(blk);
   return rc;
 }
+
+// Diagnostic counters of the Gibbs kernel (tests only).  which = 0: categorical draws whose pass-2 re-sum of the selected chunk
+// ended short of the target and therefore took the chunk's last candidate with mass (gibbs.cuh chunk_pick) since the last reset.
+extern "C" int cb2_debug_counter(cb2_ctx* ctx, int which, int reset, uint64_t* value) {
+  if (!ctx) return CB2_ERR_INVALID;
+  cb2_lock g(ctx->mu);
+  CB2_REQUIRE(ctx, which == 0 && value, "unknown counter %d or null value", which);
+  CB2_CUDA(ctx, cudaSetDevice(ctx->device));
+  CB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  unsigned long long v = 0;
+  CB2_CUDA(ctx, cudaMemcpyFromSymbol(&v, g_pick_fallthrough, sizeof(v)));
+  *value = v;
+  if (reset) {
+    const unsigned long long z = 0;
+    CB2_CUDA(ctx, cudaMemcpyToSymbol(g_pick_fallthrough, &z, sizeof(z)));
+  }
+  return CB2_OK;
+}

@@ -38,6 +38,43 @@ def mmd_sharded(a, b, bw, sums_fn, dist=None, device=None):
     return part[0] / (N * N) - 2.0 * part[1] / (N * M) + part[2] / (M * M), part
 
 
+def mmd(a, b, bw, ctx, dist=None):
+    """`mmd(M, a, b, N, M; bw)` from HOST arrays on every rank of a multi-GPU job: both clouds are uploaded to each GPU (they are
+    KBs to MBs), every rank evaluates its share of the symmetric tile list (cb2_mmd_sums_shard), and the three FP64 partial sums
+    are all-reduced over NCCL.  Every rank returns the same value."""
+    import torch
+    from . import mmd_sums_shard, mmd_combine
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    part = mmd_sums_shard(a, b, bw, rank, world, ctx=ctx)
+    if dist is not None and world > 1:
+        t = torch.from_numpy(part)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        part = t.cpu().numpy()
+    return mmd_combine(part, len(a), len(b))
+
+
+def product_sharded_dev(descs_fn, Nout, d, D, dist, torch, ctx_call):
+    """One large product with its OUTPUT SAMPLES split over the ranks, everything on the device: rank r runs the chains
+    [s0, s1) of the product into its slice of the full output tensors (Philox sample index = global index, so the result does
+    not depend on the world size) and the slices are all-gathered over NCCL.  descs_fn(s0, n, pts_ptr, lab_ptr) builds the
+    device-pointer descriptor of that slice; ctx_call(desc) launches it.  Returns (pts Nout x d, labels Nout x D) CUDA tensors,
+    identical on every rank."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cap = -(-Nout // world)
+    pts = torch.zeros((world * cap, d), dtype=torch.float64, device="cuda")
+    lab = torch.zeros((world * cap, D), dtype=torch.int32, device="cuda")
+    s0, s1 = min(rank * cap, Nout), min((rank + 1) * cap, Nout)
+    if s1 > s0:
+        ctx_call(descs_fn(s0, s1 - s0, pts[rank * cap:].data_ptr(), lab[rank * cap:].data_ptr()))
+    if world > 1:
+        dist.all_gather_into_tensor(pts, pts[rank * cap:(rank + 1) * cap].clone())
+        dist.all_gather_into_tensor(lab, lab[rank * cap:(rank + 1) * cap].clone())
+    return pts[:Nout], lab[:Nout]
+
+
 def product_sharded(dens, circular, Nout, seed, product_fn, dist=None, device=None, stream=0, niter=1):
     """One large product with its output samples split across ranks and all-gathered.
     product_fn(dens, circular, n, seed=, niter=, stream=, sample_offset=) -> (pts n x d, labels n x D)."""

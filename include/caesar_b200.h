@@ -80,6 +80,13 @@ int cb2_mmd_sums(cb2_ctx* ctx, const double* a, int N, const double* b, int M, i
                  int ra0, int ra1, int rb0, int rb1, double* sums3);
 int cb2_mmd_sums_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev, int M, int d, double bw,
                      int ra0, int ra1, int rb0, int rb1, double* sums3_dev);
+/* shard `shard` of `nshards` of the same three sums, for multi-GPU mmd that keeps the symmetry of the self terms: the tile list
+ * of the full evaluation is dealt round-robin, so every GPU evaluates (N^2/2 + N M + M^2/2) / nshards pairs; the nshards
+ * results add up (ncclAllReduce of 3 doubles) to what cb2_mmd_sums returns for the full row ranges. */
+int cb2_mmd_sums_shard(cb2_ctx* ctx, const double* a, int N, const double* b, int M, int d, double bw,
+                       int shard, int nshards, double* sums3);
+int cb2_mmd_sums_shard_dev(cb2_ctx* ctx, const double* a_dev, int N, const double* b_dev, int M, int d, double bw,
+                           int shard, int nshards, double* sums3_dev);
 
 /* mmd between beliefs on a product of lines and circles (Pose2 / Pose3 beliefs as a test metric,
  * R:test/ICRA2022_tests/multihypo_corners.jl:201-202): dist^2 = sum over Euclidean coordinates of d^2 plus
@@ -152,6 +159,11 @@ int cb2_wait(cb2_ctx* ctx, cb2_ticket ticket);
  * perm: N leaf-position -> kernel index; mean/var: nodes x d per level, wt: nodes; level in [0, depth]. */
 int cb2_tree_debug(cb2_ctx* ctx, const cb2_density* den, int d, int level, int32_t* depth_out, int32_t* count_out,
                    int32_t* perm, double* mean, double* var, double* wt);
+
+/* diagnostic counters of the Gibbs kernel (tests).  which = 0: categorical draws since the last reset whose second pass (re-sum
+ * of the selected chunk) ended short of the target because the two passes round differently, and took the chunk's last
+ * candidate with mass instead -- the neighbour of the exact draw.  Waits for the stream. */
+int cb2_debug_counter(cb2_ctx* ctx, int which, int reset, uint64_t* value);
 
 /* ---- ScatterAlign getSample (a1): fresh samples from both clouds + BFGS over SE(2)/SE(3) coords ---------------
  * cloud1/cloud2: KDE beliefs over R^dim (dim = 2 | 3); sample_count points are drawn from each

@@ -270,3 +270,43 @@ def test_scatter_align_pose3_getsample_icp_branch(cb, ctx32):
         cb.icp_align_batch(fix, mov, correspondences=5, ctx=ctx32)
     with pytest.raises(ValueError):
         cb.icp_align_batch(fix[:, :2], mov, ctx=ctx32)
+
+
+# ------------------------------------------------------------------------------------------------ round 2: headline sizes
+def test_mmd_tile_shards_add_up_to_the_full_sums(cb, ctx):
+    """Multi-GPU mmd keeps the symmetry of the self terms: the tile list is dealt round-robin (cb2_mmd_sums_shard); the shards
+    of any world size add up to the full sums, and one shard of one is the plain call."""
+    rng = np.random.default_rng(7)
+    a, b = rng.normal(size=(5000, 3)), rng.normal(size=(3100, 3)) + 0.5
+    full = cb.mmd_sums(a, b, 0.8, ctx=ctx)
+    want = oracle.mmd(a, b, 0.8, return_sums=True)[1]
+    tol = 1e-5 if ctx.precision == "fp32" else 1e-12
+    assert np.allclose(full, want, rtol=tol)
+    assert np.allclose(cb.mmd_sums_shard(a, b, 0.8, 0, 1, ctx=ctx), full, rtol=1e-14)
+    for world in (2, 3, 8):
+        parts = [cb.mmd_sums_shard(a, b, 0.8, r, world, ctx=ctx) for r in range(world)]
+        assert np.allclose(np.sum(parts, axis=0), full, rtol=1e-6 if ctx.precision == "fp32" else 1e-13)
+    with pytest.raises(cb.CB2Error):
+        cb.mmd_sums_shard(a, b, 0.8, 2, 2, ctx=ctx)
+
+
+def test_mmd_1e5_points_against_the_full_oracle(cb, ctx32):
+    """C3 at the headline size: mmd of two 1e5-point ScatterAlignPose3 clouds (3e10 kernel evaluations) against the FULL CPU oracle
+    (about 20 s on 16 cores), 1e-5 relative on the three pair sums; and the K2 cost + gradient of one transform at that size."""
+    oracle.use_all_cores()
+    rng = np.random.default_rng(3)
+    P = 100000
+    a = rng.normal(size=(P, 3))
+    b = oracle.transform_points(3, np.array([2.0, 0, 2.0, 0, 0, np.pi / 10]), rng.normal(size=(P, 3)), backward=False)
+    want, sums = oracle.mmd(a, b, 1.0, return_sums=True)
+    got_sums = cb.mmd_sums(a, b, 1.0, ctx=ctx32)
+    assert np.allclose(got_sums, sums, rtol=1e-5, atol=0), (got_sums, sums)
+    scale = (sums[0] + 2 * sums[1] + sums[2]) / P**2
+    assert abs(cb.mmd(a, b, 1.0, ctx=ctx32) - want) <= 1e-5 * scale
+    parts = [cb.mmd_sums_shard(a, b, 1.0, r, 8, ctx=ctx32) for r in range(8)]
+    assert np.allclose(np.sum(parts, axis=0), sums, rtol=1e-5)
+    c = np.array([[2.05, 0.02, 1.9, 0.01, -0.02, np.pi / 10 + 0.03]])
+    v, g = cb.mmd_se_batch(a, b, 1.0, c, backward=True, ctx=ctx32)
+    ov, og = oracle.mmd_se_batch(a, b, 1.0, c, backward=True)
+    assert abs(v[0] - ov[0]) <= 1e-5 * scale
+    assert np.allclose(g, og, rtol=2e-4, atol=1e-5 * np.abs(og).max())

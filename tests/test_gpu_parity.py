@@ -583,3 +583,19 @@ def test_product_dimension_above_six_is_rejected_before_any_work(cb, ctx):
     with pytest.raises(cb.CB2Error) as ei:
         cb.product_points(dens, (0,) * 7, 16, seed=1, ctx=ctx)
     assert ei.value.code == -5 and ctx.kernel_launches == launches
+
+
+def test_tensor_core_leaf_pass_second_pass_consistency_is_quantified(cb, ctx32):
+    """With the tensor-core leaf pass the first pass scores leaves with a 3 x TF32 product and the second pass (re-sum of the
+    selected chunk) with FP32 FMAs: equal to ~1e-6, not bit for bit.  A draw whose target sits within that of a chunk boundary ends
+    its re-sum short and takes the chunk's last candidate with mass -- the neighbour of the exact draw.  Count how often."""
+    dens = _c5_variable(5)
+    circ = (0, 0, 0, 1, 1, 1)
+    ctx32.debug_counter(0, reset=True)
+    pts, lab = cb.product_points(dens, circ, 4096, seed=41, stream=1, ctx=ctx32)
+    short = ctx32.debug_counter(0, reset=True)
+    draws = 4096 * 8 * 2 * 13  # chains x messages x sweeps x level visits
+    assert short / draws < 2e-4, (short, draws)
+    # the chains still follow the oracle's
+    opts, olab = oracle.product(dens, 128, seed=41, circular=list(circ), stream=1, ubits=24)
+    assert (lab[:128] == olab).mean() > 0.97
