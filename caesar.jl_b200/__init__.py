@@ -82,6 +82,10 @@ class Context:
     def sm_count(self):
         return int(_capi.lib().cb2_device_sm_count(self._h))
 
+    def set_level_down(self, mode):
+        """1 (default): weight-proportional random child on the way down the trees; 0: always the first child."""
+        self.check(_capi.lib().cb2_set_level_down(self._h, int(mode)))
+
     def debug_counter(self, which=0, reset=False):
         v = C.c_uint64()
         self.check(_capi.lib().cb2_debug_counter(self._h, int(which), int(bool(reset)), C.byref(v)))

@@ -80,6 +80,7 @@ def lib():
             "cb2_approx_conv_batch": (i32, [vp, C.POINTER(ConvDesc), i32, u64]),
             "cb2_se_residual_batch": (i32, [vp, i32, vp, vp, vp, i32, vp]),
             "cb2_debug_counter": (i32, [vp, i32, i32, C.POINTER(u64)]),
+            "cb2_set_level_down": (i32, [vp, i32]),
             "cb2_device_alloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
             "cb2_device_free": (i32, [vp, vp]),
             "cb2_upload": (i32, [vp, vp, vp, C.c_size_t]),
@@ -104,7 +105,7 @@ EXPORTS = ["cb2_create", "cb2_destroy", "cb2_last_error", "cb2_precision", "cb2_
            "cb2_product_batch_submit", "cb2_wait", "cb2_tree_debug", "cb2_scatter_align", "cb2_approx_conv_batch",
            "cb2_mmd_manifold", "cb2_device_alloc", "cb2_device_free", "cb2_upload", "cb2_download", "cb2_approx_conv_batch_dev",
            "cb2_kde_bw_loo_batch_dev", "cb2_icp_align_batch", "cb2_se_residual_batch",
-           "cb2_mmd_sums_shard", "cb2_mmd_sums_shard_dev", "cb2_debug_counter"]
+           "cb2_mmd_sums_shard", "cb2_mmd_sums_shard_dev", "cb2_debug_counter", "cb2_set_level_down"]
 
 
 def f64(x):

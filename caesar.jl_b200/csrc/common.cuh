@@ -38,6 +38,7 @@ struct cb2_ctx {
   size_t pinned_cap = 0;
   double* small_dev = nullptr;  // 64 doubles of persistent device scratch (scalar results of nested calls)
   uint64_t launches = 0;
+  int level_down = 1;  // Gibbs levelDown rule: 1 = weight-proportional random child, 0 = first child (cb2_set_level_down)
   std::string err;
   std::recursive_mutex mu;  // recursive: host-pointer entry points hold it across their nested _dev calls
   std::map<std::string, double> stage_ms;

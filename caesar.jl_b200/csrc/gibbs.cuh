@@ -26,6 +26,7 @@ struct GibbsArgs {
   const void* node_pool;
   uint32_t k0, k1;
   uint32_t circ_mask;
+  int level_down;       // 1: weight-proportional random child on the way down, 0: first child
   const double* stat;   // per-message statistics scratch of the tree build; its last 16 doubles = circular ranges
   size_t stat_stride;
 };
@@ -789,16 +790,36 @@ gibbs_kernel(const GibbsArgs a) {
 #endif
 
   for (int step = 1; step <= L; ++step) {
-    // levelDown: a leaf stays itself, otherwise move to the first child
+    // levelDown: a leaf stays itself, otherwise move to one of the node's children, drawn in proportion to their weights (one
+    // uniform per chain, message and level: Philox tag 2 -- the (Niter + 2)-th uniform upstream reserves per level, see
+    // oracle/cb2_oracle.c).  Always descending to the first child would pin every chain to the left half of a tree whose halves
+    // do not overlap.
     for (int k = 0; k < D; ++k) {
       const int depth = sm[k].depth;
       if (step <= depth) {
+        const bool toleaf = step == depth;
+        const T* crec = pool + sm[k].rec_off(step);
+        const int crl = toleaf ? RECL : RECN, cwo = toleaf ? DIM : 2 * DIM;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          int node = ind_s[k * kS + col[r]];
-          if (step == depth) { int lo, n; node_range(sm[k].N, step - 1, node, lo, n); node = lo; }
-          else node = 2 * node;
-          ind_s[k * kS + col[r]] = (ind_t)node;
+          int node = ind_s[k * kS + col[r]], c0, nch = 2, lo, n;
+          node_range(sm[k].N, step - 1, node, lo, n);  // leaves under the current node
+          if (toleaf) { c0 = lo; nch = n; }
+          else c0 = 2 * node;
+          int pick = c0;
+          if (nch > 1 && a.level_down) {
+            T w0, w1;
+            if (sm[k].uniform) {  // equal kernel weights: the children weigh their leaf counts (left = ceil(n / 2)), no loads
+              w0 = (T)((n + 1) >> 1); w1 = (T)(n - ((n + 1) >> 1));
+            } else {
+              w0 = fast_exp2(crec[(size_t)c0 * crl + cwo]); w1 = fast_exp2(crec[(size_t)(c0 + 1) * crl + cwo]);
+            }
+            uint32_t rnd[4];
+            philox4x32_10(sid[r], (uint32_t)((step - 1) * D + k), pstream, 2u, a.k0, a.k1, rnd);
+            const T u = u01<T>(rnd[0], rnd[1]);
+            if (!(w0 >= u * (w0 + w1))) pick = c0 + 1;
+          }
+          ind_s[k * kS + col[r]] = (ind_t)pick;
         }
       }
     }

@@ -654,7 +654,7 @@ int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const
   CB2_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
   GibbsArgs ga;
   ga.metas = lay.metas; ga.prods = lay.prods; ga.work = lay.work; ga.int_pool = lay.int_pool; ga.node_pool = lay.node_pool;
-  ga.k0 = (uint32_t)seed; ga.k1 = (uint32_t)(seed >> 32); ga.circ_mask = mask;
+  ga.k0 = (uint32_t)seed; ga.k1 = (uint32_t)(seed >> 32); ga.circ_mask = mask; ga.level_down = ctx->level_down;
   ga.stat = lay.stat; ga.stat_stride = stat_stride;
   int rc = launch_gibbs<T>(ctx, d, mask, (int)pl.work.size(), ga);
   if (rc) return rc;
@@ -1059,5 +1059,14 @@ extern "C" int cb2_debug_counter(cb2_ctx* ctx, int which, int reset, uint64_t* v
     const unsigned long long z = 0;
     CB2_CUDA(ctx, cudaMemcpyToSymbol(g_pick_fallthrough, &z, sizeof(z)));
   }
+  return CB2_OK;
+}
+
+// levelDown rule of the multiscale Gibbs sampler (SURVEY App. A.3 leaves it open): 1 = a chain descends to a child of its node
+// drawn in proportion to the children's weights (default), 0 = always the first child.
+extern "C" int cb2_set_level_down(cb2_ctx* ctx, int mode) {
+  if (!ctx) return CB2_ERR_INVALID;
+  cb2_lock g(ctx->mu);
+  ctx->level_down = mode ? 1 : 0;
   return CB2_OK;
 }

@@ -38,8 +38,13 @@ class PriorPose2:
 
 @dataclass
 class Pose2Pose2:
+    """`multihypo = [1, p_1, .., p_H]` over labels [x, h_1, .., h_H] (IIF `addFactor!(...; multihypo)`,
+    R:test/ICRA2022_tests/multihypo_corners.jl:55-60): the second variable of the relative factor is h_k with probability p_k, chosen
+    per particle.  `nullhypo = p`: with probability p a particle treats the factor as uninformative (:103)."""
     mean: np.ndarray  # [dx, dy, dtheta] in the first pose's frame
     cov: np.ndarray
+    multihypo: object = None
+    nullhypo: float = 0.0
 
 
 @dataclass
@@ -121,11 +126,70 @@ def approx_conv(fg, labels, factor, target, rng):
     raise TypeError(f"unsupported factor {type(factor).__name__}")
 
 
-def conv_desc(fg, labels, factor, target, stream):
+SPREAD_NH = 3.0  # IIF solver default `spreadNH`: how far (in factor sigmas) null-hypothesis particles are scattered
+
+
+def _host_pts(fg, label):
+    b = fg.variables[label].belief
+    if hasattr(b, "to_host"):
+        raise NotImplementedError("multihypo / nullhypo factors mix particles on the host: use a host-pointer backend")
+    return b.pts
+
+
+def _hypo_desc(fg, labels, factor, target, stream, rng):
+    """Pose2Pose2 with fractional associations.  The association is drawn per particle on the host (same
+    generator for every backend); the convolution itself stays one closed-form device launch.  Returns the descriptor plus a
+    `post` rule (keep_mask, own_points, scatter): particles under `keep_mask` do not take the factor's proposal but one of the
+    target's current points, scattered by `scatter` sigmas of the factor noise when the particle chose the null hypothesis."""
+    N = fg.N
+    chol = np.linalg.cholesky(factor.cov)
+    own = fg.variables[target].belief
+    own_pts = None if own is None else _resample(_host_pts(fg, target), N, rng)
+    keep = np.zeros(N, dtype=bool)
+    scatter = np.zeros(N)
+    if factor.multihypo is not None:
+        p = np.asarray(factor.multihypo[1:], dtype=np.float64)
+        hyp = rng.choice(len(p), size=N, p=p / p.sum())
+        if target == labels[0]:  # the certain variable: every particle is solved from the hypothesis it drew
+            src = np.empty((N, 3))
+            for k in range(len(p)):
+                sel = np.flatnonzero(hyp == k)
+                pk = _host_pts(fg, labels[1 + k])
+                src[sel] = pk[rng.integers(0, len(pk), size=len(sel))]
+            reverse = True
+        else:  # hypothesis variable k: only the particles that drew k are informed by the factor
+            k = labels.index(target) - 1
+            src, reverse = _host_pts(fg, labels[0]), False
+            keep = hyp != k
+    else:
+        other = labels[0] if labels[1] == target else labels[1]
+        src, reverse = _host_pts(fg, other), target == labels[0]
+    if factor.nullhypo > 0 and own_pts is not None:
+        null = rng.uniform(size=N) < factor.nullhypo
+        scatter[null & ~keep] = SPREAD_NH
+        keep = keep | null
+    desc = dict(kind=1, reverse=reverse, N=N, mean=factor.mean, chol=chol, stream=stream, src=src, aux=None)
+    if own_pts is not None and keep.any():
+        desc["post"] = (keep, own_pts, scatter, np.sqrt(np.diag(factor.cov)), rng.standard_normal((N, 3)))
+    return desc
+
+
+def _apply_post(out, post):
+    keep, own, scatter, sig, z = post
+    out = np.array(out, copy=True)
+    rep = own + (scatter[:, None] * sig[None, :]) * z
+    rep[:, 2] = _wrap(rep[:, 2])
+    out[keep] = rep[keep]
+    return out
+
+
+def conv_desc(fg, labels, factor, target, stream, rng=None):
     """Descriptor of one closed-form convolution for a backend's `approx_conv_batch` (device: `approxConvBatch`)."""
     N = fg.N
     if isinstance(factor, PriorPose2):
         return dict(kind=0, reverse=False, N=N, mean=factor.mean, chol=np.linalg.cholesky(factor.cov), stream=stream, src=None, aux=None)
+    if isinstance(factor, Pose2Pose2) and (factor.multihypo is not None or factor.nullhypo > 0):
+        return _hypo_desc(fg, labels, factor, target, stream, rng)
     other = labels[0] if labels[1] == target else labels[1]
     src = fg.variables[other].belief.pts
     if isinstance(factor, Pose2Pose2):
@@ -143,7 +207,10 @@ def _convolve(fg, backend, items, rng, seed, stream0):
     """items: [(labels, factor, target)].  Uses the backend's batched closed-form convolution when it has one
     (device: one cb2_approx_conv_batch launch), else the NumPy fallback of this harness."""
     if hasattr(backend, "approx_conv_batch"):
-        return backend.approx_conv_batch([conv_desc(fg, ls, f, t, stream0 + i) for i, (ls, f, t) in enumerate(items)], seed)
+        descs = [conv_desc(fg, ls, f, t, stream0 + i, rng) for i, (ls, f, t) in enumerate(items)]
+        posts = [d.pop("post", None) for d in descs]
+        outs = backend.approx_conv_batch(descs, seed)
+        return [o if p is None else _apply_post(o, p) for o, p in zip(outs, posts)]
     return [approx_conv(fg, ls, f, t, rng) for ls, f, t in items]
 
 
@@ -168,7 +235,7 @@ def solveGraph(fg, backend, gibbs_iters=3, seed=0, stats=None):
     stats.update(products=0, shapes={}, product_calls=0, t_products=0.0, t_bandwidth=0.0)
     t0 = time.perf_counter()
     # forward initialisation (initAll!): a variable is initialised from the first factor whose other end already is
-    pending = list(fg.variables)
+    pending = [v for v in fg.variables if fg.variables[v].belief is None]  # (a re-solve after adding to the graph keeps the rest)
     while pending:
         progressed = False
         for v in list(pending):
@@ -223,6 +290,43 @@ def solveGraph(fg, backend, gibbs_iters=3, seed=0, stats=None):
         backend.finish(fg)
     stats["seconds"] = time.perf_counter() - t0
     return stats
+
+
+def generateGraph_MultihypoCorners(N=1000, stage=3):
+    """The multimodal Pose2 graph of R:test/ICRA2022_tests/multihypo_corners.jl:14-148 (BASELINE config C4), built in the
+    reference's stages: 0 = four corner poses and two door poses with priors (:17-38); 1 = x0 seen from one of the four corners,
+    multihypo = [1, .25, .25, .25, .25] (:53-60); 2 = x1 with a 50 % null-hypothesis odometry factor and its own corner sighting
+    (:102-111); 3 = x2 (:143-146).  `extend_MultihypoCorners` adds the next stage to a solved graph, as the test does."""
+    fg = FactorGraph(N=N)
+    for st in range(stage + 1):
+        extend_MultihypoCorners(fg, st)
+    return fg
+
+
+def extend_MultihypoCorners(fg, stage):
+    prior = np.diag([0.1, 0.1, 0.01]) ** 2
+    dual = np.diag([1.0, 1.0, np.sqrt(np.pi)]) ** 2
+    odo = np.diag([0.5, 0.5, 0.05]) ** 2
+    corners = ["c0", "c1", "c2", "c3"]
+    mh = [1.0, 0.25, 0.25, 0.25, 0.25]
+    if stage == 0:
+        for lb, mean, cov in (("c0", [0.0, 0, 0], prior), ("c1", [20.0, 0, np.pi / 2], prior), ("c2", [20.0, 10, np.pi], prior),
+                              ("c3", [0.0, 10, -np.pi / 2], prior), ("door_prior", [20.0, 4, 0], prior), ("door_dual", [20.0, 4, np.pi], dual)):
+            fg.addVariable(lb, "Pose2")
+            fg.addFactor([lb], PriorPose2(np.array(mean), cov))
+    elif stage == 1:
+        fg.addVariable("x0", "Pose2")
+        fg.addFactor(["x0"] + corners, Pose2Pose2(np.array([-2.0, -2, 0]), odo, multihypo=mh))
+    elif stage == 2:
+        fg.addVariable("x1", "Pose2")
+        fg.addFactor(["x0", "x1"], Pose2Pose2(np.array([4.0, 0, np.pi / 2]), odo, nullhypo=0.5))
+        fg.addFactor(["x1"] + corners, Pose2Pose2(np.array([-2.0, -4, 0]), odo, multihypo=mh))
+    elif stage == 3:
+        fg.addVariable("x2", "Pose2")
+        fg.addFactor(["x1", "x2"], Pose2Pose2(np.array([16.0, 0, 0]), odo))
+        fg.addFactor(["x2"] + corners, Pose2Pose2(np.array([2.0, -4, np.pi / 2]), odo, multihypo=mh))
+    else:
+        raise ValueError("stage 0..3")
 
 
 def getPPE(belief):

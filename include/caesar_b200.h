@@ -160,6 +160,13 @@ int cb2_wait(cb2_ctx* ctx, cb2_ticket ticket);
 int cb2_tree_debug(cb2_ctx* ctx, const cb2_density* den, int d, int level, int32_t* depth_out, int32_t* count_out,
                    int32_t* perm, double* mean, double* var, double* wt);
 
+/* levelDown rule of the multiscale sampler: when a chain moves one level down the tree of a message it continues from a child
+ * of its current node.  mode 1 (default): the child is drawn in proportion to the children's weights (one more uniform per chain,
+ * message and level); mode 0: always the first child -- deterministic, but a product of beliefs whose modes do not overlap then
+ * keeps only the modes of the first branches.  Upstream's rule is not in the reference tree (KernelDensityEstimate.jl); the
+ * switch exists so that either reading can be selected once real upstream output is available. */
+int cb2_set_level_down(cb2_ctx* ctx, int mode);
+
 /* diagnostic counters of the Gibbs kernel (tests).  which = 0: categorical draws since the last reset whose second pass (re-sum
  * of the selected chunk) ended short of the target because the two passes round differently, and took the chunk's last
  * candidate with mass instead -- the neighbour of the exact draw.  Waits for the stream. */

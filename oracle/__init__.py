@@ -160,6 +160,11 @@ def kde_sample(mu, sigma, n, seed, stream=0, w=None, circular=None, ubits=53):
     return out
 
 
+def set_level_down(mode):
+    """1: a chain descends to a child drawn in proportion to the children's weights (default); 0: always the first child."""
+    lib().cb2o_set_level_down(int(mode))
+
+
 def product(densities, Nout, seed, circular=None, niter=1, stream=0, ubits=53, sample_offset=0):
     """densities: list of (pts N x d, bw d[, w N]).  Returns (pts Nout x d, labels Nout x D)."""
     D = len(densities)

@@ -446,6 +446,12 @@ static void loo_product(const cb2o_tree* const* tr, const int* lev, const int* i
   }
 }
 
+/* levelDown rule (SURVEY App. A.3 leaves it open: "ind[j] <- a child of ind[j]"): 1 = child drawn in proportion to the
+ * children's weights (default), 0 = always the first child.  Process-wide switch for the day real upstream output is at hand. */
+static int g_level_down = 1;
+void cb2o_set_level_down(int mode) { g_level_down = mode ? 1 : 0; }
+int cb2o_get_level_down(void) { return g_level_down; }
+
 int cb2o_product(const cb2o_density* dens, int D, const uint8_t* circ, int d, int Nout, int niter,
                  uint64_t seed, uint32_t stream, int ubits, int sample_offset,
                  double* pts_out, int32_t* labels_out) {
@@ -469,10 +475,23 @@ int cb2o_product(const cb2o_density* dens, int D, const uint8_t* circ, int d, in
       uint32_t sid = (uint32_t)(s + sample_offset);
       for (int j = 0; j < D; ++j) { ind[j] = 0; lev[j] = 0; }
       for (int step = 1; step <= L; ++step) {
-        for (int j = 0; j < D; ++j) { /* levelDown: a leaf stays itself; else move to the first child */
+        for (int j = 0; j < D; ++j) {
+          /* levelDown: a leaf stays itself; else move to one of the node's children, drawn in proportion to their weights.
+           * Upstream pre-generates (Niter + 2) uniforms per (sample, density, level) (randU[N D (Niter+2) L]):
+           * 1 + Niter for the Gibbs sweeps and one more, which is this draw.  Always taking the first child instead would pin
+           * every chain to the left half of the tree whenever the halves do not overlap: the conditional of one density given
+           * the others' nodes cannot cross over later, and a product of two four-mode beliefs keeps only two modes. */
           if (lev[j] < tr[j]->depth) {
-            int lc = lev[j] + 1;
-            ind[j] = (lc == tr[j]->depth) ? tr[j]->start[lev[j]][ind[j]] : 2 * ind[j];
+            int lc = lev[j] + 1, c0, nch;
+            if (lc == tr[j]->depth) { c0 = tr[j]->start[lev[j]][ind[j]]; nch = tr[j]->start[lev[j]][ind[j] + 1] - c0; }
+            else { c0 = 2 * ind[j]; nch = 2; }
+            int pick = c0;
+            if (nch > 1 && g_level_down) {
+              double w0 = tr[j]->wt[lc][c0], w1 = tr[j]->wt[lc][c0 + 1];
+              double u = cb2o_uniform(seed, sid, (uint32_t)((step - 1) * D + j), stream, 2, ubits);
+              if (!(w0 >= u * (w0 + w1))) pick = c0 + 1;
+            }
+            ind[j] = pick;
             lev[j] = lc;
           }
         }

@@ -90,6 +90,10 @@ const double* cb2o_tree_level_wt(const cb2o_tree* t, int level);   /* cnt */
 int cb2o_approx_conv(int kind, int reverse, int N, const double* src, int n_src, const double* aux, int n_aux,
                      uint32_t stream, const double* mean, const double* chol, uint64_t seed, double* out);
 
+/* levelDown rule of the multiscale Gibbs sampler: 1 = weight-proportional random child (default), 0 = first child */
+void cb2o_set_level_down(int mode);
+int cb2o_get_level_down(void);
+
 /* residual of the relative-pose factors, K particles (R:ext/Images/ScatterAlignPose2.jl:216-231); coordinates as cb2_se_residual_batch */
 int cb2o_se_residual(int dim, const double* X, const double* p, const double* q, int K, double* out);
 

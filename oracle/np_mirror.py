@@ -178,7 +178,7 @@ def _combine(trees, lev, ind, skip, circ):
     return M, Cv
 
 
-def product(densities, Nout, seed, circular=None, niter=1, stream=0, ubits=53):
+def product(densities, Nout, seed, circular=None, niter=1, stream=0, ubits=53, level_down=1):
     trees = [build_tree(*dn) for dn in densities]
     D, d = len(trees), trees[0]["d"]
     circ = [0] * d if circular is None else list(circular)
@@ -191,9 +191,21 @@ def product(densities, Nout, seed, circular=None, niter=1, stream=0, ubits=53):
         ind, lev = [0] * D, [0] * D
         for step in range(1, L + 1):
             for j, t in enumerate(trees):
-                if lev[j] < t["depth"]:
-                    ind[j] = t["starts"][lev[j]][ind[j]] if lev[j] + 1 == t["depth"] else 2 * ind[j]
-                    lev[j] += 1
+                if lev[j] < t["depth"]:  # levelDown: a child of the current node, drawn in proportion to the children's weights
+                    lc = lev[j] + 1
+                    if lc == t["depth"]:
+                        c0 = t["starts"][lev[j]][ind[j]]
+                        nch = t["starts"][lev[j]][ind[j] + 1] - c0
+                    else:
+                        c0, nch = 2 * ind[j], 2
+                    pick = c0
+                    if nch > 1 and level_down:
+                        w0, w1 = t["wt"][lc][c0], t["wt"][lc][c0 + 1]
+                        u = uniform(seed, s, (step - 1) * D + j, stream, 2, ubits)
+                        if not (w0 >= u * (w0 + w1)):
+                            pick = c0 + 1
+                    ind[j] = pick
+                    lev[j] = lc
             for it in range(sweeps):
                 for j, t in enumerate(trees):
                     mu, va, wt = t["mean"][lev[j]], t["var"][lev[j]], t["wt"][lev[j]]
