@@ -606,6 +606,20 @@ def mmd_extras(cb, ctx, torch, tstream, rank=0, world=1, dist=None):
                                     "samples_per_s_e2e": 256 * 1000 / c4_s, "cpu_samples_per_s": 4 * 1000 / c4_cpu,
                                     "cpu_sample": "4 of the 256 products (product + LOO bandwidth), oracle on all host cores",
                                     "mass_at_common_corner": near}
+    # C4 as a graph: the multihypo corner graph of R:test/ICRA2022_tests/multihypo_corners.jl:14-148 (N = 1000 particles), four
+    # incremental solves of three Gibbs sweeps each through the caller harness (tests/test_multihypo_graph.py asserts the
+    # reference's density / mmd checks on the same run)
+    fgm = solver.FactorGraph(N=1000)
+    be = solver.DeviceBackend(cb, ctx)
+    t0 = time.perf_counter()
+    nprod = 0
+    for stage in range(4):
+        solver.extend_MultihypoCorners(fgm, stage)
+        nprod += solver.solveGraph(fgm, be, gibbs_iters=3, seed=stage)["products"]
+    c4g_s = time.perf_counter() - t0
+    x0 = fgm.variables["x0"].belief.pts
+    out["c4_multihypo_graph"] = {"N": 1000, "stages": 4, "gibbs_iters": 3, "products": nprod, "solve_s": c4g_s,
+                                 "x0_mass_near_c1_c3": [float((np.linalg.norm(x0[:, :2] - c, axis=1) < 3).mean()) for c in ([18, 2], [2, 8])]}
     return out
 
 

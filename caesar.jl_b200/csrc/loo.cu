@@ -16,6 +16,7 @@
 // The bracket and the update rule follow Ihler's `ksize(..., 'lcv')` / `golden` as restated in oracle/cb2_oracle.c.
 #include "common.cuh"
 #include <type_traits>
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -486,6 +487,121 @@ loo_small_kernel(const LooProblem* __restrict__ probs, const int* __restrict__ i
   }
 }
 
+// Latency variant of the small-problem search for SMALL BATCHES (a Gibbs sweep of a ten-variable graph asks for a few dozen
+// bandwidths at a time: one CTA per problem would leave most of the 148 SMs idle and every search would take the time of N^2 / 2
+// exponentials on one SM).  A thread-block CLUSTER of kLooCluster CTAs works on one problem: every CTA holds all N points in
+// shared memory and owns N / kLooCluster rows (one row per thread, all N columns, no symmetry hand-down); per golden-section
+// step the CTAs exchange their partial sums of log row sums through distributed shared memory (each CTA writes its value into
+// every peer's slot, one cluster barrier per step, slots double-buffered by step parity) and advance identical copies of the
+// search state.  Each CTA sorts its own copy (the bracket needs the smallest neighbour gap).
+constexpr int kLooCluster = 8;
+constexpr int kLooClusterThreads = kSmallN / kLooCluster;  // one row per thread
+template <typename T>
+__global__ void __cluster_dims__(kLooCluster, 1, 1) __launch_bounds__(kLooClusterThreads)
+loo_cluster_kernel(const LooProblem* __restrict__ probs, const int* __restrict__ ids, LooState* __restrict__ st) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int p = ids[blockIdx.x / kLooCluster];
+  const LooProblem pr = probs[p];
+  const int N = pr.N, tid = threadIdx.x;
+  __shared__ double sk[kSmallN];
+  __shared__ T sxs[kSmallN];
+  __shared__ double sred[kLooClusterThreads / 32];
+  __shared__ double slots[2][kLooCluster];
+  __shared__ LooState ss;
+  int P2 = 1;
+  while (P2 < N) P2 <<= 1;
+  for (int i = tid; i < P2; i += kLooClusterThreads) sk[i] = i < N ? pr.x[(size_t)i * pr.stride] : 1.7976931348623157e308;
+  __syncthreads();
+  for (int k = 2; k <= P2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P2; i += kLooClusterThreads) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          double a = sk[i], b = sk[ixj];
+          if ((b < a) == ((i & k) == 0)) { sk[i] = b; sk[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  double mn = 1e300;
+  for (int i = tid; i + 1 < N; i += kLooClusterThreads) mn = fmin(mn, sk[i + 1] - sk[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if ((tid & 31) == 0) sred[tid >> 5] = mn;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < kLooClusterThreads / 32; ++w) mn = fmin(mn, sred[w]);
+    LooState s0;
+    loo_bracket(s0, mn, sk[N - 1] - sk[0]);
+    ss = s0;
+  }
+  const bool circ = pr.circular != 0;
+  const double x_mid = circ ? 0.0 : sk[N >> 1];
+  const bool wraps = circ && !(sk[0] >= -CB2_PI && sk[N - 1] <= CB2_PI && sk[N - 1] - sk[0] <= CB2_PI);
+  const int rows = (N + kLooCluster - 1) / kLooCluster;   // rows of this problem per CTA (<= kLooClusterThreads)
+  const int row = rank * rows + tid;
+  const bool mine = tid < rows && row < N;
+  const int n8 = N & ~7;
+  for (int it = 0; it < 96; ++it) {
+    __syncthreads();
+    if (ss.phase == 3) break;  // identical in every CTA of the cluster: all leave together
+    const double h = ss.h_eval;
+    const double sc = sqrt(0.5 * CB2_LOG2E) / h;
+    const T period = (T)(CB2_TWO_PI * sc);
+    for (int j = tid; j < N; j += kLooClusterThreads) sxs[j] = (T)(((circ ? wrap_pi(sk[j]) : sk[j]) - x_mid) * sc);
+    __syncthreads();
+    double v = 0;
+    if (mine) {
+      const T xi = sxs[row];
+      T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+      if (wraps) {
+        for (int j = 0; j < N; ++j) {
+          T ad = fabs(xi - sxs[j]);
+          T df = fmin(ad, period - ad);
+          a0 += (j == row) ? T(0) : fast_exp2(-(df * df));
+        }
+      } else {
+        for (int j = 0; j < n8; j += 8) {  // the self term (exp2(0) = 1) is summed and taken out below
+#pragma unroll
+          for (int u = 0; u < 8; u += 4) {
+            const T d0 = xi - sxs[j + u], d1 = xi - sxs[j + u + 1], d2 = xi - sxs[j + u + 2], d3 = xi - sxs[j + u + 3];
+            a0 += fast_exp2(-(d0 * d0)); a1 += fast_exp2(-(d1 * d1)); a2 += fast_exp2(-(d2 * d2)); a3 += fast_exp2(-(d3 * d3));
+          }
+        }
+        for (int j = n8; j < N; ++j) { const T d0 = xi - sxs[j]; a0 += fast_exp2(-(d0 * d0)); }
+        a0 -= T(1);
+      }
+      const double a = (double)((a0 + a1) + (a2 + a3));
+      v = log(a > 2.2250738585072014e-308 ? a : 2.2250738585072014e-308);
+    }
+    v = warp_sum(v);
+    if ((tid & 31) == 0) sred[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0;
+      for (int w = 0; w < kLooClusterThreads / 32; ++w) t += sred[w];
+      for (int r = 0; r < kLooCluster; ++r) cluster.map_shared_rank(&slots[it & 1][0], r)[rank] = t;  // my partial into every peer
+    }
+    cluster.sync();
+    if (tid == 0) {
+      double t = 0;
+      for (int r = 0; r < kLooCluster; ++r) t += slots[it & 1][r];  // fixed order: every CTA computes the same total
+      LooState s1 = ss;
+      golden_advance(s1, loo_objective(t, N, h));
+      ss = s1;
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && rank == 0) {
+    LooState s1 = ss;
+    if (s1.phase != 3) { s1.result = s1.f1 < s1.f2 ? s1.x1 : s1.x2; s1.phase = 3; }  // iteration cap: best point so far
+    st[p] = s1;
+  }
+  cluster.sync();  // no CTA leaves while a peer may still write into its shared memory
+}
+
 __global__ void loo_collect_kernel(const LooState* __restrict__ st, int P, double* __restrict__ out) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
@@ -554,9 +670,20 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
     CB2_CUDA(ctx, cudaMemcpyAsync(small_dev, small_ids.data(), sizeof(int) * small_ids.size(), cudaMemcpyHostToDevice, ctx->stream));
   CB2_CUDA(ctx, cudaMemsetAsync(counters, 0, sizeof(int) * 64, ctx->stream));
   if (!small_ids.empty()) {
-    if (f64) loo_small_kernel<double><<<(int)small_ids.size(), kThreads, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
-    else loo_small_kernel<float><<<(int)small_ids.size(), kThreads, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
-    CB2_CHECK_LAUNCH(ctx, "loo_small_kernel");
+    // few problems of a few hundred points (one sweep of a small graph): a cluster of CTAs per problem, for latency; many
+    // problems: one CTA each with the symmetric pair evaluation, for throughput
+    int minN = maxN;
+    for (int id : small_ids) minN = std::min(minN, probs[id].N);
+    const bool use_cluster = !getenv("CB2_NO_LOO_CLUSTER") && minN >= 192 && (int)small_ids.size() * kLooCluster <= 2 * ctx->sm_count;
+    if (use_cluster) {
+      if (f64) loo_cluster_kernel<double><<<(int)small_ids.size() * kLooCluster, kLooClusterThreads, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
+      else loo_cluster_kernel<float><<<(int)small_ids.size() * kLooCluster, kLooClusterThreads, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
+      CB2_CHECK_LAUNCH(ctx, "loo_cluster_kernel");
+    } else {
+      if (f64) loo_small_kernel<double><<<(int)small_ids.size(), kThreads, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
+      else loo_small_kernel<float><<<(int)small_ids.size(), kThreads, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
+      CB2_CHECK_LAUNCH(ctx, "loo_small_kernel");
+    }
   }
   if (!cta_map.empty()) {
   int P2 = 1;

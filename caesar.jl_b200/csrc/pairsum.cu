@@ -325,11 +325,37 @@ __global__ void kde_sample_kernel(const double* __restrict__ mu, const double* _
   }
 }
 
-__global__ void cumsum_serial_kernel(const double* __restrict__ w, int N, double* __restrict__ cdf) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    double c = 0;
-    for (int i = 0; i < N; ++i) { c += w[i]; cdf[i] = c; }
+// inclusive prefix sum of the kernel weights (the sampler's CDF) by one CTA: every thread sums a contiguous chunk, the chunk
+// totals are scanned across the block (shuffles within the warps, then across the warps), and each thread writes its chunk's
+// running sums on top of its offset.  Deterministic; differs from a sequential sum by FP64 rounding only.
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) cumsum_block_kernel(const double* __restrict__ w, int N, double* __restrict__ cdf) {
+  __shared__ double warp_tot[kScanThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int chunk = (N + kScanThreads - 1) / kScanThreads;
+  const int i0 = min(N, tid * chunk), i1 = min(N, i0 + chunk);
+  double tot = 0;
+  for (int i = i0; i < i1; ++i) tot += w[i];
+  double incl = tot;  // inclusive scan of the chunk totals within the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
   }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    double v = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    warp_tot[lane] = v;
+  }
+  __syncthreads();
+  double c = (incl - tot) + (wid > 0 ? warp_tot[wid - 1] : 0.0);  // sum of everything before this thread's chunk
+  for (int i = i0; i < i1; ++i) { c += w[i]; cdf[i] = c; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -857,7 +883,7 @@ extern "C" int cb2_kde_sample(cb2_ctx* ctx, const double* mu, const double* sigm
   for (int k = 0; k < d; ++k) { sg[k] = sigma[k]; if (circular && circular[k]) mask |= 1u << k; }
   double* cdf = nullptr;
   if (w) {
-    cumsum_serial_kernel<<<1, 1, 0, ctx->stream>>>(dev[1], N, dev[2]);
+    cumsum_block_kernel<<<1, kScanThreads, 0, ctx->stream>>>(dev[1], N, dev[2]);
     ctx->launches++;
     cdf = dev[2];
   }
@@ -1035,7 +1061,7 @@ extern "C" int cb2_scatter_align(cb2_ctx* ctx, const cb2_density* cloud1, const 
   for (int c = 0; c < 2 && rc == CB2_OK; ++c) {
     double* cdf = nullptr;
     if (cl[c]->w) {
-      cumsum_serial_kernel<<<1, 1, 0, ctx->stream>>>(dev[c * 3 + 1], cl[c]->N, dev[c * 3 + 2]);
+      cumsum_block_kernel<<<1, kScanThreads, 0, ctx->stream>>>(dev[c * 3 + 1], cl[c]->N, dev[c * 3 + 2]);
       ctx->launches++;
       cdf = dev[c * 3 + 2];
     }

@@ -599,3 +599,23 @@ def test_tensor_core_leaf_pass_second_pass_consistency_is_quantified(cb, ctx32):
     # the chains still follow the oracle's
     opts, olab = oracle.product(dens, 128, seed=41, circular=list(circ), stream=1, ubits=24)
     assert (lab[:128] == olab).mean() > 0.97
+
+
+@pytest.mark.parametrize("N", [192, 500, 1000, 1024])
+def test_bandwidth_cluster_kernel_matches_single_cta_kernel_and_oracle(cb, ctx, N, monkeypatch):
+    """Small batches of a few hundred points take the thread-block-cluster search (eight CTAs per coordinate, partial sums
+    exchanged through distributed shared memory); it must walk the same golden-section path as the single-CTA kernel."""
+    rng = np.random.default_rng(N)
+    pts = np.c_[rng.normal(size=(N, 2)) * [3.0, 0.5] + (rng.uniform(size=(N, 1)) < 0.4) * [6.0, 0.0], rng.normal(size=N) * 0.4 + 3.0]
+    pts[:, 2] = (pts[:, 2] + np.pi) % (2 * np.pi) - np.pi   # heading straddles the +-pi cut
+    launches = ctx.kernel_launches
+    got = cb.kde_bandwidth(pts, "Pose2", ctx=ctx)
+    assert ctx.kernel_launches > launches
+    monkeypatch.setenv("CB2_NO_LOO_CLUSTER", "1")
+    single = cb.kde_bandwidth(pts, "Pose2", ctx=ctx)
+    monkeypatch.delenv("CB2_NO_LOO_CLUSTER")
+    want = oracle.kde_bw_loo(pts, circular=[0, 0, 1])
+    if ctx.precision == "fp64":
+        assert np.allclose(got, single, rtol=1e-9) and np.allclose(got, want, rtol=1e-6)
+    else:
+        assert np.allclose(got, single, rtol=2e-2) and np.allclose(got, want, rtol=3e-2)

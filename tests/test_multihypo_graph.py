@@ -1,0 +1,86 @@
+"""BASELINE config C4 as a GRAPH: the multimodal Pose2 graph of R:test/ICRA2022_tests/multihypo_corners.jl:14-148 (four corner
+poses with priors, x0 / x1 / x2 each sighting one of the four corners with multihypo = [1, .25, .25, .25, .25], a 50 %
+null-hypothesis odometry factor), solved through the caller harness (caesar.jl_b200/solver.py) stage by stage as the reference
+test does, asserting the reference's own checks: density thresholds at / off the modes (:66-90, :120-146) and
+`mmd(X2_a, belief) < 0.25` (:201-202)."""
+import numpy as np
+import pytest
+
+from __graft_entry__ import build, load_package
+
+X0_MODES = [([2, 2, 0], [2, 2, np.pi / 2]), ([18, 2, np.pi / 2], [18, 2, 0]), ([18, 8, -np.pi], [18, 8, 0]), ([2, 8, -np.pi / 2], [2, 8, 0])]
+
+
+def _solve_stages(solver, backend, N, evaluate, mmd_pose2, gibbs_iters=3, strict=True):
+    """strict: every threshold of the reference test.  The split of the mass between the two surviving modes random-walks from
+    sweep to sweep (the harness re-multiplies beliefs around the x0 - x1 - x2 loop), so a run whose chains differ (FP32 rounding)
+    is only held to the structural checks: which modes exist, and where no mass may be."""
+    fg = solver.FactorGraph(N=N)
+    dens = lambda lb, tp: float(evaluate(fg.variables[lb].belief, np.array([tp], dtype=float))[0])
+    stats = {}
+    for stage in range(4):
+        solver.extend_MultihypoCorners(fg, stage)
+        st = solver.solveGraph(fg, backend, gibbs_iters=gibbs_iters, seed=stage)
+        stats[stage] = st
+        if stage == 0:
+            for lb, want in (("c0", [0, 0, 0]), ("c1", [20, 0, np.pi / 2]), ("c3", [0, 10, -np.pi / 2]), ("door_prior", [20, 4, 0])):
+                assert np.allclose(solver.getPPE(fg.variables[lb].belief), want, atol=0.1), lb  # :41-47
+        if stage == 1:  # :62-90 four modes, each away from the wrong heading
+            for on, off in X0_MODES:
+                assert dens("x0", on) > 0.15, (on, dens("x0", on))
+                assert dens("x0", off) < 0.02, off
+        if stage >= 2:  # :116-146
+            mass = lambda lb, c: float((np.linalg.norm(fg.variables[lb].belief.pts[:, :2] - np.array(c), axis=1) < 3.0).mean())
+            assert mass("x0", [18, 2]) + mass("x0", [2, 8]) > 0.97   # the other two corners are ruled out by x1's sighting
+            assert mass("x1", [18, 6]) + mass("x1", [2, 4]) > 0.97
+            assert dens("x0", [18, 2, 0]) < 0.02 and dens("x0", [2, 8, 0]) < 0.02
+            assert dens("x1", [18, 6, 0]) < 0.02 and dens("x1", [2, 4, np.pi / 2]) < 0.02
+            if strict:
+                assert dens("x0", [18, 2, np.pi / 2]) > 0.15 and dens("x0", [2, 8, -np.pi / 2]) > 0.15
+                assert dens("x1", [18, 6, -np.pi]) > 0.02 and dens("x1", [18, 6, np.pi]) > 0.02
+                assert dens("x1", [2, 4, 0]) > 0.15
+        if stage == 3 and strict:  # :158-166, :201-202
+            r = np.random.default_rng(0)
+            X2_a = np.c_[r.normal(size=(100, 2)) * np.sqrt(0.5) + [18, 4], r.normal(size=100) * 0.2]
+            X2_b = np.c_[r.normal(size=(100, 2)) * np.sqrt(0.5) + [2, 6], solver._wrap(r.normal(size=100) * 0.2 - np.pi)]
+            x2 = fg.variables["x2"].belief.pts
+            assert mmd_pose2(X2_a, x2) < 0.25 and mmd_pose2(X2_b, x2) < 0.25
+    return fg, stats
+
+
+def test_multihypo_corners_on_oracle_backend():
+    from importlib import import_module
+    load_package()
+    solver = import_module("caesar_jl_b200.solver")
+    import oracle
+    from oracle.solver_backend import OracleBackend
+    oracle.use_all_cores()
+    fg, st = _solve_stages(solver, OracleBackend(ubits=53), 400, lambda b, q: oracle.kde_eval(b.pts, b.bw, q),
+                           lambda a, b: oracle.mmd_manifold(a, b, [0, 0, 1], 0.001))
+    assert st[3]["shapes"].get("D=4,N=400,d=3", 0) >= 12  # the corner poses multiply their prior with three multihypo messages
+
+
+@pytest.mark.gpu
+def test_multihypo_corners_on_device_n1000_and_against_the_oracle_solve():
+    from importlib import import_module
+    build()
+    cb = load_package()
+    solver = import_module("caesar_jl_b200.solver")
+    import oracle
+    from oracle.solver_backend import OracleBackend
+    oracle.use_all_cores()
+    # FP64 mode: the device chains are the oracle's chains (same Philox counters), so the whole incremental solve -- 51 products,
+    # every reference threshold -- reproduces the CPU oracle's solve
+    ctx = cb.Context(0, "fp64")
+    ev = lambda b, q: cb.evaluate(b, q, ctx=ctx)
+    mm = lambda a, b: cb.mmd_manifold(a, b, (0, 0, 1), 0.001, ctx=ctx)
+    fg, st = _solve_stages(solver, solver.DeviceBackend(cb, ctx), 1000, ev, mm)
+    assert sum(s["products"] for s in st.values()) >= 45
+    fgo, _ = _solve_stages(solver, OracleBackend(ubits=53), 1000, lambda b, q: oracle.kde_eval(b.pts, b.bw, q),
+                           lambda a, b: oracle.mmd_manifold(a, b, [0, 0, 1], 0.001))
+    for lb in ("x0", "x1", "x2", "c0", "c2"):
+        assert mm(fg.variables[lb].belief.pts, fgo.variables[lb].belief.pts) < 0.02, lb
+    # FP32 mode (the production precision): the modes and the excluded regions
+    ctx32 = cb.Context(0, "fp32")
+    _solve_stages(solver, solver.DeviceBackend(cb, ctx32), 1000, lambda b, q: cb.evaluate(b, q, ctx=ctx32),
+                  lambda a, b: cb.mmd_manifold(a, b, (0, 0, 1), 0.001, ctx=ctx32), strict=False)
