@@ -250,6 +250,9 @@ __device__ __forceinline__ float fast_rsq(float x) {
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// UW: every node of the level carries the same weight (equal kernel weights and N a power of two): log2 w cancels in the
+// normalisation and its load (the fourth LDS of the record: the shared-memory pipe is as busy as the FMA pipe here) is dropped
+template <bool UW>
 __device__ __forceinline__ float score_node_rsq(const f32x2 (&q)[8], const PackedConst& c, float nm, float& mul) {
   const f32x2 sq = pack2(c.nqs, c.nqs);
   const f32x2 d0 = fma2(q[0], sq, c.a[0]), d1 = fma2(q[1], sq, c.a[1]), d2 = fma2(q[2], sq, c.a[2]);
@@ -263,34 +266,35 @@ __device__ __forceinline__ float score_node_rsq(const f32x2 (&q)[8], const Packe
   unpack2(den, dx, dy);
   unpack2(q[6], lw, p1);
   const float rx = fast_rsq(dx), ry = fast_rsq(dy);
-  float e = lw + nm;
+  float e = UW ? nm : lw + nm;
   e = fma(-nx, rx * rx, e);
   e = fma(-ny, ry * ry, e);
   mul = rx * ry;
   return e;
 }
 
-// MODE 0: coarse level, 1: leaf level with per-kernel weights, 2: leaf level with uniform weights
-template <int DIM, int MODE> struct RecLen { static constexpr int value = MODE == 0 ? (2 * DIM + 1 + 3) / 4 * 4 : (DIM + 1 + 3) / 4 * 4; };
+// MODE 0: coarse level, 1: leaf level with per-kernel weights, 2: leaf level with uniform weights, 3: coarse level whose nodes
+// all weigh the same (packed loops only)
+template <int DIM, int MODE> struct RecLen { static constexpr int value = (MODE == 0 || MODE == 3) ? (2 * DIM + 1 + 3) / 4 * 4 : (DIM + 1 + 3) / 4 * 4; };
 
 // whether a scoring path returns the probability as mul * exp2(e) (CB2_COARSE_RSQ) instead of exp2(e)
-template <int MODE, bool PACK> struct HasMul { static constexpr bool value = CB2_COARSE_RSQ && PACK && MODE == 0; };
+template <int MODE, bool PACK> struct HasMul { static constexpr bool value = CB2_COARSE_RSQ && PACK && (MODE == 0 || MODE == 3); };
 
 template <typename T, int DIM, int MODE, bool PACK>
 __device__ __forceinline__ T score_regs(const RecR<T, RecLen<DIM, MODE>::value, PACK>& r, const ChainConst<T, DIM>& c,
                                         const PackedConst& pc, uint32_t circ, T nm, T& mul) {
   mul = T(1);
   if constexpr (PACK) {
-    if constexpr (MODE == 0) {
+    if constexpr (MODE == 0 || MODE == 3) {
 #if CB2_COARSE_RSQ
-      return score_node_rsq(r.q, pc, nm, mul);
+      return score_node_rsq<MODE == 3>(r.q, pc, nm, mul);
 #else
       return score_node_p(r.q, pc, nm);
 #endif
     }
     else return score_leaf_p<MODE == 2>(r.q, pc, nm);
   } else {
-    if constexpr (MODE == 0) return score_node<T, DIM>(r.v, c, circ, nm);
+    if constexpr (MODE == 0 || MODE == 3) return score_node<T, DIM>(r.v, c, circ, nm);
     else return score_leaf<T, DIM, MODE == 2>(r.v, c, circ, nm);
   }
 }
@@ -829,6 +833,7 @@ gibbs_kernel(const GibbsArgs a) {
         const int lev = min(step, dj.depth);
         const bool leaf = lev == dj.depth;
         const int cnt = level_count(dj.N, dj.depth, lev);
+        const bool cw = dj.uniform != 0 && (dj.N & (dj.N - 1)) == 0;  // every node of a coarse level weighs the same
         const T* lrec = pool + dj.rec_off(lev);
         const int rec = leaf ? RECL : RECN;
         const int TN = leaf ? TN_LEAF : TN_NODE;
@@ -905,7 +910,10 @@ gibbs_kernel(const GibbsArgs a) {
           // with the tensor-core leaf pass compiled in, the packed leaf loops would only serve warp-flat passes of CTAs that are
           // not flat as a whole: they take the wrapped loops instead and the kernel stays smaller (instruction cache)
           if (flat && !(kTC && leaf)) {  // Euclidean arithmetic on every coordinate: same values as the wrapped form, fewer instructions
-            if (!leaf) tile_pass<T, DIM, 0, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
+            if (!leaf) {
+              if (kPack && cw) tile_pass<T, DIM, 3, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
+              else tile_pass<T, DIM, 0, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
+            }
             else if constexpr (!kTC) {
               if (!dj.uniform) tile_pass<T, DIM, 1, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
               else tile_pass<T, DIM, 2, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
@@ -946,8 +954,14 @@ gibbs_kernel(const GibbsArgs a) {
           // pass 2 must reproduce the scores of pass 1 bit for bit, so it takes the same (packed or wrapped) scorer
           int pick;
           if (flat && !(kTC && leaf)) {
-            if (!leaf) pick = chunk_pick<T, DIM, 0, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
+            if (!leaf) pick = (kPack && cw) ? chunk_pick<T, DIM, 3, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
+                                            : chunk_pick<T, DIM, 0, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
             else if constexpr (!kTC) {
+              pick = !dj.uniform ? chunk_pick<T, DIM, 1, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
+                                 : chunk_pick<T, DIM, 2, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
+            } else pick = z0;
+          } else if (kTC && done_tc) {  // tensor-core leaf pass: the CTA is wrap-free, the packed FP32 leaf scorer applies
+            if constexpr (kTC) {
               pick = !dj.uniform ? chunk_pick<T, DIM, 1, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
                                  : chunk_pick<T, DIM, 2, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
             } else pick = z0;
