@@ -370,7 +370,6 @@ def _manifoldProductPartial(ff, manifold, Niter, N, seed, stream, ctx):
     manifold = manifold if manifold is not None else first.manifold
     topo = _topology(manifold, d)
     N = int(N) if N is not None else max(m.N for m in ff)
-    rng = np.random.default_rng(seed)
     cols, bws = [None] * d, np.zeros(d)
     batches = {0: [], 1: []}  # 1-D products grouped by topology (one circular mask per batched call)
     for i in range(d):
@@ -378,9 +377,8 @@ def _manifoldProductPartial(ff, manifold, Niter, N, seed, stream, ctx):
         if not use:
             use = [first]
         marg = [ManifoldKernelDensity((topo[i],), m.pts[:, i:i + 1], m.bw[i:i + 1], m.weights) for m in use]
-        if len(marg) == 1:  # a single informed input: its own samples (resampled to N), upstream early-out per dimension
-            src = marg[0].pts[:, 0]
-            cols[i] = src if len(src) == N else src[rng.integers(0, len(src), size=N)]
+        if len(marg) == 1:  # a single informed input: N fresh draws from that marginal (device sampler, Philox: reproducible)
+            cols[i] = sample(marg[0], N, seed=seed, stream=stream * 16 + i, ctx=ctx)[0][:, 0]
             bws[i] = marg[0].bw[0]
         else:
             batches[topo[i]].append((i, marg))

@@ -38,7 +38,7 @@ def mmd_sharded(a, b, bw, sums_fn, dist=None, device=None):
     return part[0] / (N * N) - 2.0 * part[1] / (N * M) + part[2] / (M * M), part
 
 
-def mmd(a, b, bw, ctx, dist=None):
+def mmd(a, b, bw, ctx, dist=None, shard_fn=None):
     """`mmd(M, a, b, N, M; bw)` from HOST arrays on every rank of a multi-GPU job: both clouds are uploaded to each GPU (they are
     KBs to MBs), every rank evaluates its share of the symmetric tile list (cb2_mmd_sums_shard), and the three FP64 partial sums
     are all-reduced over NCCL.  Every rank returns the same value."""
@@ -46,7 +46,8 @@ def mmd(a, b, bw, ctx, dist=None):
     from . import mmd_sums_shard, mmd_combine
     rank = dist.get_rank() if dist is not None else 0
     world = dist.get_world_size() if dist is not None else 1
-    part = mmd_sums_shard(a, b, bw, rank, world, ctx=ctx)
+    # shard_fn(a, b, bw, shard, nshards) -> the three partial sums of that shard (tests: a CPU stand-in for the device call)
+    part = np.asarray(shard_fn(a, b, bw, rank, world), dtype=np.float64) if shard_fn else mmd_sums_shard(a, b, bw, rank, world, ctx=ctx)
     if dist is not None and world > 1:
         t = torch.from_numpy(part)
         if dist.get_backend() == "nccl":

@@ -197,10 +197,37 @@ end
 function ApproxManifoldProducts.manifoldProduct(ff::AbstractVector{<:ManifoldKernelDensity}, M::AbstractManifold = ff[1].manifold;
                                                 Niter::Int = 1, N::Int = maximum(Npts.(ff)), kw...)
   length(ff) == 1 && return ff[1]                     # upstream early-out: one input is returned unchanged
+  if any(f -> f._partial !== nothing, ff)             # partial-dimension inputs: dimension-wise products, as upstream does
+    return _partial_product(ff, M; Niter, N)
+  end
   outs, bws, _ = b200_products([collect(ff)], M; N = [N], Niter)
   e0 = identity_element(M)
   pts = [exp(M, e0, hat(M, e0, view(outs[1], :, i))) for i in 1:N]
   return manikde!(M, pts; bw = bws[1])
+end
+
+# Inputs that inform only some coordinates (`_partial`): coordinate i of the result is the 1-D product of the marginals of every
+# input that informs it; a coordinate informed by a single input is a fresh draw of N samples from that marginal (device
+# sampler, Philox), as the Python mirror does (caesar.jl_b200/__init__.py `_manifoldProductPartial`).
+function _partial_product(ff, M; Niter::Int, N::Int, ctx::Context = context())
+  d = manifold_dimension(M)
+  circ = _circular(M)
+  cols = Vector{Vector{Float64}}(undef, d); bws = zeros(d)
+  for i in 1:d
+    use = [f for f in ff if f._partial === nothing || i in f._partial]
+    isempty(use) && (use = [ff[1]])
+    M1 = circ[i] != 0 ? RealCircleGroup() : TranslationGroup(1)
+    marg = [manikde!(M1, [SA[c[i]] for c in eachcol(_coords(getPoints(f.belief)))]; bw = [getBW(f.belief)[i, 1]]) for f in use]
+    if length(marg) == 1
+      cols[i] = vec(b200_sample(marg[1], N; ctx)); bws[i] = getBW(marg[1].belief)[1, 1]
+    else
+      o, b, _ = b200_products([marg], M1; N = [N], Niter, ctx)
+      cols[i] = vec(o[1]); bws[i] = b[1][1]
+    end
+  end
+  e0 = identity_element(M)
+  pts = [exp(M, e0, hat(M, e0, [cols[i][k] for i in 1:d])) for k in 1:N]
+  return manikde!(M, pts; bw = bws)
 end
 
 # ------------------------------------------------------------------------------------------------ approxConv (closed form)
@@ -215,10 +242,14 @@ struct CB2ConvDesc
   aux::Ptr{Float64}
   n_aux::Int32
   stream::UInt32
-  mean::NTuple{3,Float64}
-  chol::NTuple{9,Float64}      # lower Cholesky factor, row-major
+  mean::NTuple{6,Float64}      # Pose2 kinds use the first 3 entries, Pose3 kinds (3 = prior, 4 = Pose3Pose3) all 6
+  chol::NTuple{36,Float64}     # lower Cholesky factor, row-major n x n in the first n^2 entries (n = 3 | 6)
   out::Ptr{Float64}
 end
+_pad(v, n) = ntuple(i -> i <= length(v) ? Float64(v[i]) : 0.0, n)
+CB2ConvDesc(kind, reverse, N, src, n_src, aux, n_aux, stream, mean, chol, out) =
+  CB2ConvDesc(Int32(kind), Int32(reverse), Int32(N), Int32(n_src), src, aux, Int32(n_aux), UInt32(stream), _pad(mean, 6),
+              _pad(vec(permutedims(chol)), 36), out)   # Julia matrices are column-major: the library reads L row-major
 
 function b200_approx_conv!(descs::Vector{CB2ConvDesc}; seed::UInt64 = rand(UInt64), ctx::Context = context())
   lock(ctx.lk) do
@@ -227,6 +258,37 @@ function b200_approx_conv!(descs::Vector{CB2ConvDesc}; seed::UInt64 = rand(UInt6
   end
   return nothing
 end
+
+# ------------------------------------------------------------------------------------------------ factor residual
+# (cf::CalcFactor{<:ScatterAlignPose2/3})(X, p, q) (ext/Images/ScatterAlignPose2.jl:216-231, the Pose2Pose2 body) for K particles in
+# one launch.  X, p, q: ncoord x K coordinate matrices ([x, y, theta] or [t; rotation vector]).  A single evaluation inside a
+# per-particle nonlinear solve should stay the three lines of Julia it is upstream: a kernel launch costs more than the arithmetic.
+function b200_se_residual(dim::Int, X::Matrix{Float64}, p::Matrix{Float64}, q::Matrix{Float64}; ctx::Context = context())
+  out = similar(X)
+  lock(ctx.lk) do
+    _check(ctx, ccall((:cb2_se_residual_batch, libcb2), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}),
+                      ctx.h, dim, X, p, q, size(X, 2), out))
+  end
+  return out
+end
+
+# ------------------------------------------------------------------------------------------------ multi-GPU mmd
+# shard `shard` (0-based) of `nshards` of the three pair sums {aa, ab, bb}: the symmetric tile list dealt round-robin.  One
+# Julia process per GPU computes its shard; MPI.Allreduce / NCCL over the 3 doubles, then aa/N^2 - 2ab/(NM) + bb/M^2.
+function b200_mmd_sums_shard(a, b, shard::Integer, nshards::Integer; bw::AbstractVector{<:Real} = SA[0.001;], ctx::Context = context())
+  A, B = _coords(a), _coords(b)
+  sums = zeros(3)
+  lock(ctx.lk) do
+    _check(ctx, ccall((:cb2_mmd_sums_shard, libcb2), Cint,
+                      (Ptr{Cvoid}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Cint, Float64, Cint, Cint, Ptr{Float64}),
+                      ctx.h, A, size(A, 2), B, size(B, 2), size(A, 1), Float64(bw[1]), shard, nshards, sums))
+  end
+  return sums
+end
+
+# levelDown rule of the multiscale Gibbs sampler (include/caesar_b200.h): 1 = weight-proportional random child (default), 0 = first child
+b200_set_level_down(mode::Integer; ctx::Context = context()) =
+  lock(() -> _check(ctx, ccall((:cb2_set_level_down, libcb2), Cint, (Ptr{Cvoid}, Cint), ctx.h, mode)), ctx.lk)
 
 # ------------------------------------------------------------------------------------------------ ScatterAlign getSample
 # drop-in body for Caesar's getSample(cf::CalcFactor{<:ScatterAlignPose2/3}) (ext/Images/ScatterAlignPose2.jl:155-187):

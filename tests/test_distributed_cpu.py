@@ -35,7 +35,16 @@ def _worker(rank, world, port, q):
                                                                                   stream=stream, sample_offset=sample_offset)
     pts, lab = cbd.product_sharded(dens, (0, 0), 101, 5, pf, dist, stream=3)
     mine = cbd.assign_round_robin(7, rank, world)
-    q.put((rank, val, sums, pts, lab, mine))
+    # the host-array entry point of the multi-GPU mmd (tile shards on the device; here: interleaved rows on the oracle)
+    def shard(a, b, bw, r, w):
+        s = np.zeros(3)
+        for i in range(r, len(a), w):
+            s[:2] += oracle.mmd_rows(a, b, bw, (i, i + 1), (0, 0))[:2]
+        for i in range(r, len(b), w):
+            s[2] += oracle.mmd_rows(a, b, bw, (0, 0), (i, i + 1))[2]
+        return s
+    val2 = cbd.mmd(a, b, 0.6, None, dist, shard_fn=shard)
+    q.put((rank, val, sums, pts, lab, mine, val2))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -56,8 +65,9 @@ def test_world2_sharding_matches_single_process():
     want, wsums = oracle.mmd(a, b, 0.6, return_sums=True)
     dens = [(rng.normal(size=(64, 2)), np.array([0.3, 0.3])), (rng.normal(size=(50, 2)) + 0.5, np.array([0.2, 0.4]))]
     wpts, wlab = oracle.product(dens, 101, 5, circular=[0, 0], stream=3)
-    for rank, val, sums, pts, lab, mine in res:
+    for rank, val, sums, pts, lab, mine, val2 in res:
         assert np.isclose(val, want, rtol=1e-12) and np.allclose(sums, wsums, rtol=1e-12)
+        assert np.isclose(val2, want, rtol=1e-10, atol=1e-14)
         assert np.array_equal(pts, wpts) and np.array_equal(lab, wlab)  # identical for any world size
     assert sorted(res[0][5] + res[1][5]) == list(range(7))
 
