@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 D_MSG, N_KER, DIM, N_OUT = 8, 4096, 6, 4096
 CIRC = (0, 0, 0, 1, 1, 1)
 VARS_PER_GPU = 256
-TRAFFIC_NCU = {256: 2060.2e6}  # dram bytes of one gibbs_kernel launch, ncu --set full, by variables per launch
+TRAFFIC_NCU = {256: 2006.96e6}  # dram bytes (read + write) of one gibbs_kernel launch, ncu --set full (profiles/r02_ncu_full_summary.csv), by variables per launch
 FP32_FLOPS_PER_EVAL = 4 * DIM + 3  # product kernel-eval ~ (4d+3) flops + 1 SFU
 
 
@@ -276,7 +276,7 @@ def main():
     gibbs_ms = stage["gibbs"] / args.steps
     ach = evals * FP32_FLOPS_PER_EVAL / (gibbs_ms * 1e-3) / 1e12 if gibbs_ms > 0 else None
     roofline = {
-        "kernel": "gibbs_kernel<float,6,0x38>", "bound": "fp32+sfu (compute-bound; SURVEY 8d: not hbm; the leaf level runs on the tensor cores but K = 16 keeps them 6 % busy)",
+        "kernel": "gibbs_kernel<float,6,0x38>", "bound": "fp32+sfu (compute-bound; SURVEY 8d: not hbm; the leaf level runs on the tensor cores but K = 16 keeps them 5 % busy)",
         "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (ach / fp32_peak) if ach else None,
         "peak_source": f"{n_sm} SM (cb2_device_sm_count) x 128 FP32 lanes x 2 x {sm_mhz_max:.0f} MHz (clocks.max.sm of MEASURED_PEAKS.json); "
                        "MEASURED_PEAKS has no FP32 figure, bf16/HBM peaks do not bound this kernel",
@@ -285,7 +285,7 @@ def main():
                         "sfu_frac": evals / (gibbs_ms * 1e-3) / sfu_peak if gibbs_ms > 0 else None},
         "launch_ms": gibbs_ms, "share_of_step": gibbs_ms * args.steps / ms_total if ms_total else None,
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}, "traffic": TRAFFIC_NCU.get(args.vars_per_gpu),
-        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one gibbs_kernel launch, ncu --set full (profiles/r01_ncu_full_summary.csv); "
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one gibbs_kernel launch, ncu --set full (profiles/r02_ncu_full_summary.csv); "
                         "bytes: the kernel is compute-bound, its algorithmic HBM traffic is the node pool (3.1 MB per variable) and the leaf feature tiles (4.2 MB per variable) read once",
         # the same launch against the HBM roofline the contract names, to show why it is not the bound: algorithmic bytes = the
         # level records read once + inputs' permutations + outputs, per launch
@@ -293,8 +293,11 @@ def main():
                                     "frac": b / (gibbs_ms * 1e-3) / 1e9 / pk, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks
                                     else "B200_PROFILING.md fallback"})(
             V * (3.146e6 + D_MSG * N_KER * 128 + D_MSG * N_KER * 4 + N_OUT * (DIM * 8 + D_MSG * 4)), float(peaks.get("hbm_gbs", 6550.0))) if gibbs_ms > 0 else None,
-        "ncu": {"issue_active_pct": 59.8, "pipe_fma_cycles_pct": 49.7, "pipe_xu_pct": 60.0, "lsu_wavefronts_pct": 48.3, "pipe_tensor_pct": 5.6,
-                "warp_instructions": 1.30e11, "source": "profiles/r01_ncu_full_summary.csv (r01_gibbs_v9, 256 variables)"},
+        "ncu": {"issue_active_pct": 59.0, "pipe_fma_cycles_pct": 51.9, "pipe_xu_pct": 52.1, "lsu_wavefronts_pct": 50.9,
+                "warp_instructions": 1.17e11, "registers": 126, "launch_ms": 182.9,
+                "source": "profiles/r02_ncu_full_summary.csv (r02_gibbs_final, 256 variables); launch shares: profiles/r02_launch_summary.csv"},
+        "phases_under_full_load": {"pass1_coarse": 0.59, "pass1_leaf_tensor_core": 0.226, "pass2": 0.083, "combine": 0.062, "cdf": 0.029, "other": 0.01,
+                                   "source": "in-kernel clock64 profile of a CTA from the middle of the grid (-DCB2_GIBBS_PROF), DESIGN.md sec. 4"},
     }
 
     cpu = None

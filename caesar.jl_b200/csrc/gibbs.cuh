@@ -1,18 +1,24 @@
 // gibbs.cuh -- the multiscale Gibbs product kernel (included by product.cu inside its anonymous namespace).
 //
-// Per-candidate instruction budget (what bounds this kernel is the issue rate, 1 warp-instruction / clk / SMSP,
-// and the XU pipe for MUFU): with the per-chain constants pre-folded,
-//   leaf level    : Euclidean dim = 2 FFMA, circular dim = FFMA + FADD + FMNMX + FFMA, then FADD + MUFU.EX2 + FADD
-//   coarser levels: the node variances differ, so 1/(var+C) is needed per node: dims are handled in groups of
-//                   three over a common denominator (1 MUFU.RCP + 1 MUFU.LG2 per group instead of 3 + 3).
+// One thread = one chain; a CTA advances 128 chains (4 warps) in lock step through (level, sweep, message); four CTAs share an SM
+// (126 registers per thread, 54 KB of shared memory and 128 tensor-memory columns per CTA).  Per-candidate budget of the loops:
+//   leaf level    : FP32 d = 6 wrap-free CTAs score the leaves on the tensor cores (leaf_pass_tc: 3 x TF32 products of per-chain
+//                   coefficient rows with per-leaf feature tiles, accumulators in tensor memory); a chain then spends FADD +
+//                   MUFU.EX2 + FADD + a share of the running maximum per leaf: bound by the XU pipe (16 MUFU / clk / SM).
+//                   Everything else: Euclidean dim = 2 FFMA, circular dim = FFMA + FADD + FMNMX + FFMA, then FADD + EX2 + FADD.
+//   coarser levels: node variances differ, so 1 / (var + C) is needed per node.  Packed FP32 d = 6 loops: coordinate pairs in
+//                   f32x2 registers (FFMA2 / FMUL2), the two groups of three coordinates over common denominators D_x, D_y,
+//                   p = r_x r_y exp2(.. - N_x r_x^2 - N_y r_y^2) with r = rsqrt(D): 15 packed + 8 scalar FMA-pipe
+//                   instructions, 3 MUFU and 3 LDS.128 per candidate.  Measured under full load: 60 clk per candidate and
+//                   SM sub-partition against 37 clk of FMA pipe and 29 clk-equivalents of the SM-wide shared-memory pipe (a
+//                   warp-broadcast LDS.128 costs 2.4 clk of it, bench/micro/lds_bcast.cu) -- both pipes are near their limit there.
 // Circular coordinates are stored wrapped to [-pi, pi] (tree_build_kernel) and the chain mean comes out of atan2,
 // so |mu - M| <= 2 pi and the wrapped distance is min(|df|, 2 pi - |df|): no rounding instruction needed.
 // When every chain of a warp can prove from the message's coordinate range (tree_build_kernel) that no candidate is
 // more than pi away from its mean, the warp takes the all-Euclidean loop (`flat`): identical values, 2
 // instructions per circular dimension fewer.  Beliefs that do not straddle the +-pi cut always qualify.
-// Shared-memory bandwidth is the other limiter (a warp-broadcast LDS.128 costs 2.4 clk of the SM-wide pipe,
-// bench/micro/lds_bcast.cu; doubling the record loads of the d = 6 kernel cost +56 %), so the FP32 d = 6 kernel runs
-// two chains per thread: every record register is used by both chains (kChains<T, DIM>).
+// (Two chains per thread -- every record register used twice -- halve the shared-memory loads but leave too few warps to hide
+// latency: measured slower, profiles/r01_gibbs_two_chains_experiment.md; the path stays compilable with -DCB2_GIBBS_R=2.)
 
 template <typename T, int N> struct alignas(16) VecRec { T v[N]; };
 
@@ -31,8 +37,7 @@ struct GibbsArgs {
   size_t stat_stride;
 };
 
-// what the kernel needs of each message, staged once per CTA in shared memory (kept small: with two chains per thread the
-// CTA has 64 threads and seven CTAs share an SM, so the shared-memory footprint per CTA decides the occupancy)
+// what the kernel needs of each message, staged once per CTA in shared memory
 template <typename T> struct SMeta {
   uint32_t rec_off32[kMaxLev + 1];  // level record offsets in units of 32 elements (validate_and_plan aligns them)
   uint32_t feat_off32;              // leaf feature tiles of the tensor-core path (units of 32 elements) or 0xffffffff
@@ -475,13 +480,20 @@ __device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta<
 // ---- leaf level on the tensor cores (FP32, d = 6, CTA-wide wrap-free passes; compiled in with -DCB2_GIBBS_TC=1) ----------------
 // The leaf score is bilinear in per-chain coefficients and per-leaf features:
 //   log2 w - sum_i (a_i x_i - b_i)^2 = [x_i^2 (6), x_i (6), 1, log2 w, 0, 0] . [-a_i^2 (6), 2 a_i b_i (6), -sum b_i^2, 1, 0, 0],
-// a 128-chain x 64-leaf x 16 product per feature tile.  Both operands are split into TF32 hi + lo parts and three products
-// (hi.hi + hi.lo + lo.hi) are accumulated in FP32 in tensor memory: tcgen05.mma kind::tf32, M = 128, N = 64, K = 8, six
-// instructions per tile issued by one thread; operands K-major without swizzle (8 x 16-byte core matrices, LBO = 128 B between
-// the K halves, SBO = 512 B between 8-row groups).  The feature tiles come from the tree build (product.cu, kTcTile) by the same
-// 1-D bulk copies as the records; every thread writes its chain's coefficient row into shared memory once per pass.  Each
-// chain then reads ITS row of the accumulator (TMEM lane = thread) with tcgen05.ld and continues with the usual running-max /
-// chunk-sum bookkeeping: no per-thread record loads and one FADD instead of twelve FMA-pipe instructions per evaluation.
+// a 128-chain x kTcTile-leaf x 16 product per feature tile (kTcTile = 128: one accumulator of 128 tensor-memory columns per CTA).
+// Both operands are split into TF32 hi + lo parts and three products (hi.hi + hi.lo + lo.hi) are accumulated in FP32 in tensor
+// memory: tcgen05.mma kind::tf32, M = 128, N = kTcTile, K = 8, six instructions per tile; operands K-major without swizzle
+// (8 x 16-byte core matrices, LBO = 128 B between the K halves, SBO = 512 B between 8-row groups).  The feature tiles come from the
+// tree build (product.cu, kTcTile) by the same 1-D bulk copies as the records; every thread writes its chain's coefficient row
+// into shared memory once per pass.  Each chain then reads ITS row of the accumulator (TMEM lane = thread) with tcgen05.ld, 32
+// leaves at a time.  What the measurements say about this pass (bench/micro/tcgen05_issue_probe.cu, -DCB2_TC_PROF):
+//   * a tcgen05.mma of this shape keeps its ISSUING warp for ~75 clk (N = 64 and N = 128 alike; 150 clk when the descriptors
+//     are not warp-uniform), dependent or not: the six MMAs of a tile cost the issuing warp ~540 clk and complete ~70 clk later;
+//   * with two accumulator buffers of 64 leaves the MMA of the next tile does overlap the sums of this one, but the issuing warp
+//     is itself a consumer, so every tile still costs (sums + issue) on that warp and the other warps wait for it: measured no
+//     faster than one buffer of 128 leaves, which halves the MMA instructions per leaf (195.9 vs 192.4 ms per 256 variables);
+//     a dedicated issuing warp would need a fifth warp of registers that the four CTAs per SM do not have;
+//   * under full load the exposed MMA latency is covered by the other three CTAs of the SM: the pass runs at ~70 % of the XU limit.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
          ((uint64_t)1 << 46);

@@ -148,8 +148,11 @@ int cb2_product_batch(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const 
 /* same, every pointer inside descs (pts, bw, w, pts_out, labels_out, bw_out) is a DEVICE pointer */
 int cb2_product_batch_dev(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d,
                           uint64_t seed);
-/* asynchronous pair for cooperative callers (Julia Tasks): submit returns immediately with a ticket,
- * cb2_wait blocks until that batch's outputs are in the caller's host buffers. */
+/* asynchronous pair for cooperative callers (Julia Tasks): submit enqueues the batch and returns a ticket, cb2_wait blocks
+ * until that batch's outputs are in the caller's host buffers.  Every pointer inside descs must stay valid until cb2_wait.
+ * submit returns before the work has finished only when the input and output arrays are PINNED host memory and no bw_out is
+ * requested: copies to or from pageable memory wait for the stream, and the bandwidth search of N > 1024 results polls a
+ * device counter every eight golden-section steps. */
 typedef int64_t cb2_ticket;
 int cb2_product_batch_submit(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d,
                              uint64_t seed, cb2_ticket* ticket);
