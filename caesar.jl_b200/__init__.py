@@ -533,4 +533,4 @@ def tree_levels(pts, bw, w=None, ctx=None):
 from .factors import (ScatterAlign, ScatterAlignPose2, ScatterAlignPose3, CalcFactor, preambleCache, getSample,  # noqa: E402
                       HeatmapGridDensity, ScatterAlignPose2_from_images, getManifold, parchDistribution, packScatterAlign,
                       unpackScatterAlign, BlobStoreGraph)
-from .serialization import packDistribution, unpackDistribution  # noqa: E402
+from .serialization import packDistribution, unpackDistribution, multiplyDistributions, solveTree  # noqa: E402

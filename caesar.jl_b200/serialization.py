@@ -54,3 +54,21 @@ def multiplyDistributions(requestDict, seed=0, ctx=None):
     resObj = {"dim": 1, "kernelType": "Gaussian", "bandwidth": [float(b) for b in pqr.bw],
               "weights": [1.0 / n] * n, "points": [float(x) for x in pqr.pts[:, 0]]}
     return {"status": "OK", "payload": resObj}
+
+
+def solveTree(configDict, fg, requestDict, backend=None, gibbs_iters=3, seed=0):
+    """The ZMQ verb `solveTree` (R:ext/services/session.jl:133-140): solves the session's graph and replies with the start / end
+    time, the duration in seconds and `status`.  Upstream calls IIF's `solveTree!`; here the graph is a `solver.FactorGraph` and
+    the solve is the caller harness `solver.solveGraph` on the device product path (`backend`: default `solver.DeviceBackend`)."""
+    import datetime
+    from . import solver
+    if backend is None:
+        import sys
+        backend = solver.DeviceBackend(sys.modules[__package__])
+    resp = {"startTime": datetime.datetime.now().isoformat()}
+    solver.solveGraph(fg, backend, gibbs_iters=gibbs_iters, seed=seed)
+    end = datetime.datetime.now()
+    resp["endTime"] = end.isoformat()
+    resp["durationSec"] = (end - datetime.datetime.fromisoformat(resp["startTime"])).total_seconds()
+    resp["status"] = "OK"
+    return resp

@@ -93,3 +93,16 @@ def test_hex_solve_with_device_resident_beliefs_equals_the_host_pointer_solve(pr
         a, b = fa.variables[k].belief, fb.variables[k].belief
         assert np.array_equal(a.pts, b.pts), k
         assert np.array_equal(a.bw, b.bw), k
+
+
+def test_solve_tree_verb_on_oracle_backend():
+    """ZMQ verb `solveTree` (R:ext/services/session.jl:133-140): reply fields and a solved graph."""
+    from importlib import import_module
+    load_package()
+    solver = import_module("caesar_jl_b200.solver")
+    ser = import_module("caesar_jl_b200.serialization")
+    from oracle.solver_backend import OracleBackend
+    fg = solver.generateGraph_Hexagonal(N=60)
+    resp = ser.solveTree({}, fg, {"request": "solveTree"}, backend=OracleBackend(), gibbs_iters=2, seed=3)
+    assert resp["status"] == "OK" and resp["durationSec"] > 0 and set(resp) == {"startTime", "endTime", "durationSec", "status"}
+    assert np.abs(solver.getPPE(fg.variables["x3"].belief)[:2] - [10, 17.32]).max() < 2.0
