@@ -1,1 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err; echo "bench rc=$?"; tail -2 gpurun_out/r02_bench_n8.err; cut -c1-200 gpurun_out/r02_bench_n8.json
+for n in 48 192 296; do echo "copy CTAs $n"; CB2_LIB=$PWD/caesar.jl_b200/variants/lib_cp$n.so timeout 200 python bench/micro/e2e_probe.py 256 2>&1 | grep "call 3"; done

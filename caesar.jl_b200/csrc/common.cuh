@@ -43,6 +43,10 @@ struct cb2_ctx {
   std::recursive_mutex mu;  // recursive: host-pointer entry points hold it across their nested _dev calls
   std::map<std::string, double> stage_ms;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // host-pointer product batches: the arrays move on a second stream, chunk by chunk, while the trees of the chunks that have
+  // arrived are built (and the sample points travel back while the bandwidths are searched)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::map<int64_t, cb2_pending> pending;
   int64_t next_ticket = 1;
 };

@@ -56,12 +56,17 @@ extern "C" int cb2_create(int device, int precision, cb2_ctx** out) {
   }
   ctx->stream = ctx->own_stream;
   for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->small_dev, 64 * sizeof(double));
   if (e != cudaSuccess) {  // unwind whatever was created
     const int code = e == cudaErrorMemoryAllocation ? CB2_ERR_NOMEM : CB2_ERR_CUDA;
     cudaGetLastError();
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) {
       if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+      if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return cb2_fail(nullptr, code, "cb2_create: events / scratch: %s", cudaGetErrorString(e));
@@ -78,8 +83,11 @@ extern "C" void cb2_destroy(cb2_ctx* ctx) {
     if (kv.second.done) cudaEventDestroy(kv.second.done);
     if (kv.second.dev_block) cudaFree(kv.second.dev_block);
   }
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 8; ++i) {
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+  }
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->io.base) cudaFree(ctx->io.base);
   if (ctx->small_dev) cudaFree(ctx->small_dev);

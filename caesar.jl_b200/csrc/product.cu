@@ -17,6 +17,7 @@
 //   Randomness: counter-based Philox4x32-10 keyed by (seed; sample, draw, stream, tag): results do not depend on
 //   batching, CTA shape or output-sample sharding across GPUs.
 #include "common.cuh"
+#include <functional>
 
 int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t* N, int B, int d,
                         const uint8_t* circular, double* sigma_out_dev, void* scratch, size_t scratch_bytes,
@@ -457,6 +458,27 @@ __global__ void __launch_bounds__(256) copy_segments_kernel(const CopySeg* __res
     reinterpret_cast<int*>(sg.dst)[2 * n] = reinterpret_cast<const int*>(sg.src)[2 * n];
 }
 
+// The same copy with a SMALL grid that loops over the segments: a transfer over the host link needs a few hundred KB in flight,
+// not the whole GPU.  Used when the copy runs beside compute (chunked uploads under the tree build, sample points travelling home
+// under the bandwidth search): the 2-D launch above floods every SM with link-stalled warps and the other kernel cannot start.
+#ifndef CB2_COPY_CTAS
+#define CB2_COPY_CTAS 48
+#endif
+constexpr int kCopyStreamCtas = CB2_COPY_CTAS;
+__global__ void __launch_bounds__(256) copy_segments_stream_kernel(const CopySeg* __restrict__ segs, int nseg) {
+  for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+    const CopySeg sg = segs[s];
+    const unsigned long long n = sg.bytes >> 3;
+    unsigned long long i = threadIdx.x;
+    for (; i + 3 * 256 < n; i += 4 * 256) {
+      const double a = sg.src[i], b = sg.src[i + 256], c = sg.src[i + 512], e = sg.src[i + 768];
+      sg.dst[i] = a; sg.dst[i + 256] = b; sg.dst[i + 512] = c; sg.dst[i + 768] = e;
+    }
+    for (; i < n; i += 256) sg.dst[i] = sg.src[i];
+    if ((sg.bytes & 4) && threadIdx.x == 0) reinterpret_cast<int*>(sg.dst)[2 * n] = reinterpret_cast<const int*>(sg.src)[2 * n];
+  }
+}
+
 // copies one level of the FP64 statistics scratch out for cb2_tree_debug
 __global__ void tree_debug_copy_kernel(const double* __restrict__ sbase, int d, int level_node0, int cnt,
                                        double* __restrict__ mean, double* __restrict__ var, double* __restrict__ wt) {
@@ -599,10 +621,14 @@ struct DevLayout {
 };
 
 // Core: descriptors hold DEVICE pointers (pts, w, outputs); bw values are read from `bw_host[b][j]` (host copies).
+// inputs of a host-pointer batch that arrive chunk by chunk on the copy stream: messages [0, msg_end[c]) are on the device once
+// ev[c] has fired
+struct InputChunks { std::vector<int> msg_end; std::vector<cudaEvent_t> ev; };
+
 template <typename T>
 int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const std::vector<std::vector<const double*>>& bw_host,
                        const double* const* bw_ptrs_dev, uint32_t mask, int d, uint64_t seed, BatchPlan& pl, char* base, size_t bytes,
-                       size_t* needed, DevLayout* lay_out) {
+                       size_t* needed, DevLayout* lay_out, const InputChunks* chunks = nullptr) {
   const int nd = 2 * d + 1;
   const size_t stat_stride = (size_t)pl.max_nodes * nd + 16;  // + circular coordinate ranges (min[8], max[8])
   size_t off = 0;
@@ -648,9 +674,23 @@ int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const
   size_t tree_smem = (size_t)pl.maxP2 * 13 + 64;
   cudaError_t e = cudaFuncSetAttribute(tree_build_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem);
   if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "tree smem attribute (%zu bytes): %s", tree_smem, cudaGetErrorString(e));
-  tree_build_kernel<T><<<(int)pl.metas.size(), kTreeThreads, tree_smem, ctx->stream>>>(lay.metas, d, lay.int_pool, (T*)lay.node_pool,
-                                                                                          lay.stat, stat_stride, mask);
-  CB2_CHECK_LAUNCH(ctx, "tree_build_kernel");
+  if (chunks && !chunks->msg_end.empty()) {  // build the trees of every chunk as soon as its arrays have landed
+    int m0 = 0;
+    for (size_t c = 0; c < chunks->msg_end.size(); ++c) {
+      const int m1 = chunks->msg_end[c];
+      CB2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, chunks->ev[c], 0));
+      if (m1 > m0) {
+        tree_build_kernel<T><<<m1 - m0, kTreeThreads, tree_smem, ctx->stream>>>(lay.metas + m0, d, lay.int_pool, (T*)lay.node_pool,
+                                                                                 lay.stat + (size_t)m0 * stat_stride, stat_stride, mask);
+        CB2_CHECK_LAUNCH(ctx, "tree_build_kernel");
+      }
+      m0 = m1;
+    }
+  } else {
+    tree_build_kernel<T><<<(int)pl.metas.size(), kTreeThreads, tree_smem, ctx->stream>>>(lay.metas, d, lay.int_pool, (T*)lay.node_pool,
+                                                                                            lay.stat, stat_stride, mask);
+    CB2_CHECK_LAUNCH(ctx, "tree_build_kernel");
+  }
   CB2_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
   GibbsArgs ga;
   ga.metas = lay.metas; ga.prods = lay.prods; ga.work = lay.work; ga.int_pool = lay.int_pool; ga.node_pool = lay.node_pool;
@@ -673,7 +713,8 @@ void record_product_stages(cb2_ctx* ctx, bool with_bw) {
 
 // runs tree + gibbs (+ LOO bandwidth of the outputs) with every data pointer on the device
 int product_batch_dev_locked(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const uint8_t* circular, int d, uint64_t seed,
-                             const std::vector<std::vector<const double*>>* bw_host_in, DevLayout* lay_out) {
+                             const std::vector<std::vector<const double*>>* bw_host_in, DevLayout* lay_out,
+                             const InputChunks* chunks = nullptr, const std::function<int()>* on_samples = nullptr) {
   BatchPlan pl;
   uint32_t mask = 0;
   int rc = validate_and_plan(ctx, descs, B, circular, d, pl, &mask);
@@ -717,9 +758,13 @@ int product_batch_dev_locked(cb2_ctx* ctx, const cb2_product_desc* descs, int B,
   }
   char* base = (char*)cb2_arena_alloc(ctx, need_prod);
   if (!base) return cb2_fail(ctx, CB2_ERR_NOMEM, "product scratch exhausted");
-  rc = f64 ? product_batch_core<double>(ctx, descs, B, bw_host, bw_ptrs_dev, mask, d, seed, pl, base, need_prod, nullptr, lay_out)
-           : product_batch_core<float>(ctx, descs, B, bw_host, bw_ptrs_dev, mask, d, seed, pl, base, need_prod, nullptr, lay_out);
+  rc = f64 ? product_batch_core<double>(ctx, descs, B, bw_host, bw_ptrs_dev, mask, d, seed, pl, base, need_prod, nullptr, lay_out, chunks)
+           : product_batch_core<float>(ctx, descs, B, bw_host, bw_ptrs_dev, mask, d, seed, pl, base, need_prod, nullptr, lay_out, chunks);
   if (rc) return rc;
+  if (on_samples) {  // points and labels are final: the host-pointer path sends them home while the bandwidths are searched
+    rc = (*on_samples)();
+    if (rc) return rc;
+  }
   if (!bw_mu.empty()) {
     double* bw_dev = (double*)cb2_arena_alloc(ctx, bw_out_bytes);
     void* scratch = cb2_arena_alloc(ctx, need_loo);
@@ -833,6 +878,8 @@ static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B
   // 196 KB array); pageable arrays of the same batch keep their individual copies.
   const bool direct = !own && !packed && n_arrays >= 64 && !getenv("CB2_NO_DIRECT");
   std::vector<CopySeg> seg_in, seg_out;
+  std::vector<int> seg_msg;  // message index of every entry of seg_in
+  int cur_msg = 0;
   CopySeg* tab_in = (CopySeg*)take(sizeof(CopySeg) * n_arrays);
   CopySeg* tab_out = (CopySeg*)take(sizeof(CopySeg) * n_arrays);
   // many pageable inputs (first array not mapped): pack them into pinned staging and upload the input range with ONE copy
@@ -841,7 +888,7 @@ static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B
   auto h2d = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
     if (stage_in) { memcpy(ctx->pinned + ((char*)dst - p), src, bytes); return cudaSuccess; }
     void* mp = direct ? mapped_host_ptr(src) : nullptr;
-    if (mp) { seg_in.push_back({(const double*)mp, (double*)dst, bytes}); return cudaSuccess; }
+    if (mp) { seg_in.push_back({(const double*)mp, (double*)dst, bytes}); seg_msg.push_back(cur_msg); return cudaSuccess; }
     return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
   };
   // pageable outputs of a synchronous call: ONE copy of the contiguous output range into pinned staging, then host memcpy
@@ -873,11 +920,41 @@ static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B
         ddens[b][j].w = wp;
       }
       if (e != cudaSuccess) { rc = cb2_fail(ctx, CB2_ERR_CUDA, "H2D copy: %s", cudaGetErrorString(e)); break; }
+      ++cur_msg;
       bw_host[b].push_back(dn.bw);
     }
     dd[b].dens = ddens[b].data();
   }
-  if (rc == CB2_OK) rc = launch_copy_segments(ctx, seg_in, tab_in, ctx->stream);
+  // pinned + mapped inputs: the gather runs chunk by chunk on the copy stream (small persistent grid) and the trees of a chunk are
+  // built as soon as it has landed, so the upload hides behind the tree build instead of preceding it
+  InputChunks chunks;
+  const bool overlap = direct && !seg_in.empty() && ctx->copy_stream && !getenv("CB2_NO_COPY_OVERLAP");
+  if (rc == CB2_OK && overlap) {
+    cudaError_t ce = cudaEventRecord(ctx->copy_ev[7], ctx->stream);  // earlier work on the main stream may still read the I/O block
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[7], 0);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(tab_in, seg_in.data(), sizeof(CopySeg) * seg_in.size(), cudaMemcpyHostToDevice, ctx->copy_stream);
+    const int NC = 4;
+    size_t s0 = 0;
+    int msgs_total = 0;
+    for (int b = 0; b < B; ++b) msgs_total += descs[b].D;
+    for (int c = 0; c < NC && ce == cudaSuccess; ++c) {
+      const int m_end = (int)((long long)msgs_total * (c + 1) / NC);  // chunk boundaries on message boundaries
+      size_t s1 = s0;
+      while (s1 < seg_in.size() && seg_msg[s1] < m_end) ++s1;
+      if (s1 > s0) {
+        copy_segments_stream_kernel<<<kCopyStreamCtas, 256, 0, ctx->copy_stream>>>(tab_in + s0, (int)(s1 - s0));
+        ctx->launches++;
+        ce = cudaGetLastError();
+      }
+      if (ce == cudaSuccess) ce = cudaEventRecord(ctx->copy_ev[c], ctx->copy_stream);
+      chunks.msg_end.push_back(m_end);
+      chunks.ev.push_back(ctx->copy_ev[c]);
+      s0 = s1;
+    }
+    if (ce != cudaSuccess) rc = cb2_fail(ctx, CB2_ERR_CUDA, "chunked H2D copy: %s", cudaGetErrorString(ce));
+  } else if (rc == CB2_OK) {
+    rc = launch_copy_segments(ctx, seg_in, tab_in, ctx->stream);
+  }
   const size_t in_bytes = off;
   if (rc == CB2_OK && stage_in && in_bytes) {
     e = cudaMemcpyAsync(p, ctx->pinned, in_bytes, cudaMemcpyHostToDevice, ctx->stream);
@@ -892,7 +969,36 @@ static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B
     dd[b].labels_out = descs[b].labels_out ? (int32_t*)take(sizeof(int32_t) * (size_t)descs[b].Nout * descs[b].D) : nullptr;
     dd[b].bw_out = descs[b].bw_out ? (double*)take(sizeof(double) * d) : nullptr;
   }
-  if (rc == CB2_OK) { cudaEventRecord(ctx->ev[5], ctx->stream); rc = product_batch_dev_locked(ctx, dd.data(), B, circular, d, seed, &bw_host, nullptr); }
+  // results that live in pinned + mapped arrays: the sample points and labels go home on the copy stream as soon as the Gibbs
+  // kernel has finished, under the bandwidth search of the same batch; only the bandwidths are copied afterwards
+  std::vector<char> sent_early(B, 0);
+  size_t n_early = 0;  // entries of tab_out taken by the early copy (the later one must not overwrite a table still being read)
+  std::function<int()> send_samples = [&]() -> int {
+    std::vector<CopySeg> segs;
+    for (int b = 0; b < B; ++b) {
+      void* mp = mapped_host_ptr(descs[b].pts_out);
+      void* ml = descs[b].labels_out ? mapped_host_ptr(descs[b].labels_out) : nullptr;
+      if (!mp || (descs[b].labels_out && !ml)) continue;
+      segs.push_back({(const double*)dd[b].pts_out, (double*)mp, sizeof(double) * (size_t)descs[b].Nout * d});
+      if (ml) segs.push_back({(const double*)dd[b].labels_out, (double*)ml, sizeof(int32_t) * (size_t)descs[b].Nout * descs[b].D});
+      sent_early[b] = 1;
+    }
+    if (segs.empty()) return CB2_OK;
+    n_early = segs.size();
+    CB2_CUDA(ctx, cudaEventRecord(ctx->copy_ev[6], ctx->stream));
+    CB2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[6], 0));
+    CB2_CUDA(ctx, cudaMemcpyAsync(tab_out, segs.data(), sizeof(CopySeg) * segs.size(), cudaMemcpyHostToDevice, ctx->copy_stream));
+    copy_segments_stream_kernel<<<kCopyStreamCtas, 256, 0, ctx->copy_stream>>>(tab_out, (int)segs.size());
+    CB2_CHECK_LAUNCH(ctx, "copy_segments_stream_kernel");
+    return CB2_OK;
+  };
+  const bool early_out = overlap && !own;
+  if (rc == CB2_OK) {
+    cudaEventRecord(ctx->ev[5], ctx->stream);
+    rc = product_batch_dev_locked(ctx, dd.data(), B, circular, d, seed, &bw_host, nullptr, overlap ? &chunks : nullptr,
+                                  early_out ? &send_samples : nullptr);
+  }
+  if (overlap) cudaStreamSynchronize(ctx->copy_stream);  // (also on failure: nothing of this call may still be in flight)
   if (rc != CB2_OK) { cudaStreamSynchronize(ctx->stream); if (own) cudaFree(blk); return rc; }
   cudaEventRecord(ctx->ev[6], ctx->stream);
   if (packed) {
@@ -909,12 +1015,14 @@ static int product_batch_host(cb2_ctx* ctx, const cb2_product_desc* descs, int B
     // (by now the stream has consumed the input staging: the products ran after it; a growing reserve synchronises anyway)
     stage_out = !own && B >= 4 && out_bytes <= ((size_t)1 << 30) && cb2_pinned_reserve(ctx, out_bytes + 256) == CB2_OK;
     for (int b = 0; b < B && e == cudaSuccess; ++b) {
-      e = d2h(descs[b].pts_out, dd[b].pts_out, sizeof(double) * (size_t)descs[b].Nout * d);
-      if (e == cudaSuccess && descs[b].labels_out)
-        e = d2h(descs[b].labels_out, dd[b].labels_out, sizeof(int32_t) * (size_t)descs[b].Nout * descs[b].D);
+      if (!sent_early[b]) {
+        e = d2h(descs[b].pts_out, dd[b].pts_out, sizeof(double) * (size_t)descs[b].Nout * d);
+        if (e == cudaSuccess && descs[b].labels_out)
+          e = d2h(descs[b].labels_out, dd[b].labels_out, sizeof(int32_t) * (size_t)descs[b].Nout * descs[b].D);
+      }
       if (e == cudaSuccess && descs[b].bw_out) e = d2h(descs[b].bw_out, dd[b].bw_out, sizeof(double) * d);
     }
-    if (e == cudaSuccess && launch_copy_segments(ctx, seg_out, tab_out, ctx->stream) != CB2_OK) e = cudaErrorUnknown;
+    if (e == cudaSuccess && launch_copy_segments(ctx, seg_out, tab_out + n_early, ctx->stream) != CB2_OK) e = cudaErrorUnknown;
     if (e == cudaSuccess && !staged.empty()) {
       e = cudaMemcpyAsync(ctx->pinned, p + in_bytes, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -215,8 +215,8 @@ def test_product_batch_is_independent_of_batching_and_sharding(cb, ctx):
 
 
 def test_product_batch_from_pinned_host_arrays_uses_the_single_launch_copies(cb, ctx, monkeypatch):
-    """Batches of >= 64 arrays in pinned (mapped) host memory are gathered / scattered by one kernel per direction that reads and
-    writes the caller's arrays in place; results must equal the per-array copy path bit for bit.  Nout * D is odd for the labels
+    """Batches of >= 64 arrays in pinned (mapped) host memory are gathered / scattered by kernels that read and write the caller's
+    arrays in place (chunked on a second stream so that the upload hides behind the tree build); results must equal the per-array copy path bit for bit.  Nout * D is odd for the labels
     (4-byte tail of the 8-byte-word copy) and the bandwidth outputs are pageable (mixed batch)."""
     import ctypes as C
     import torch
@@ -247,7 +247,17 @@ def test_product_batch_from_pinned_host_arrays_uses_the_single_launch_copies(cb,
     launches0 = L.cb2_kernel_launches(ctx._h)
     plain = run()
     n_plain = L.cb2_kernel_launches(ctx._h) - launches0
-    assert n_direct == n_plain + 2  # one gather and one scatter launch
+    # gather and scatter kernels instead of per-array copies: four upload chunks on the copy stream (the trees of a chunk are built
+    # as soon as it has landed: three more tree launches) and one scatter of the sample points and labels
+    assert n_direct == n_plain + 8, (n_direct, n_plain)
+    monkeypatch.setenv("CB2_NO_COPY_OVERLAP", "1")
+    monkeypatch.delenv("CB2_NO_DIRECT")
+    launches0 = L.cb2_kernel_launches(ctx._h)
+    serial = run()
+    assert L.cb2_kernel_launches(ctx._h) - launches0 == n_plain + 2  # one gather and one scatter launch on the main stream
+    for a, b in zip(serial, plain):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
     for a, b in zip(direct, plain):
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
