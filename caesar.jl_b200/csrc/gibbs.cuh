@@ -553,7 +553,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 template <typename T, int DIM>
 __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int cnt, int CH, const ChainConst<T, DIM>& cc, bool uniform,
                                              unsigned char* smem_tiles, int tile_bytes, uint64_t* bars, uint32_t& use0, uint32_t& use1,
-                                             TcState& tc, float* __restrict__ chunk, int tid, float& m, float& csum, int& cidx) {
+                                             TcState& tc, float* __restrict__ chunk, int tid, float& m, float& csum, int& cidx,
+                                             const float* __restrict__ cur_rec) {
   const int ntl = (cnt + kTcTile - 1) / kTcTile;
   auto load_tile = [&](int t) {  // thread 0: one bulk copy (hi + lo parts of kTcTile leaves)
     const int b = t % kTcBufs;
@@ -575,7 +576,20 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
     }
     // with uniform weights log2 w is the same for every leaf and is dropped, exactly as score_leaf<UW> does (pass 2 must see
     // the same reference); the padding leaves of the last tile are masked below instead of relying on their log2 w = -1e30
-    u[12] = -sb; u[13] = uniform ? 0.f : 1.f; u[14] = 0.f; u[15] = 0.f;
+    // The reference of the pass is the score of the leaf this chain holds at the moment (a likely one), and it rides in the
+    // constant coefficient: the accumulator then IS score - m and the sums below need no subtraction per leaf (one FMA-pipe
+    // instruction less on the pipe the coarse levels of the other CTAs are waiting for).  A later raise of the reference is
+    // carried separately (`extra`).
+    {
+      float e0 = uniform ? 0.f : cur_rec[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float df = fmaf(cur_rec[i], (float)cc.a[i], -(float)cc.b[i]);
+        e0 = fmaf(-df, df, e0);
+      }
+      m = e0;
+    }
+    u[12] = -sb - m; u[13] = uniform ? 0.f : 1.f; u[14] = 0.f; u[15] = 0.f;
     float* rowp = tc.sA + (tid >> 3) * 128 + (tid & 7) * 4;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -607,6 +621,7 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
     if (kTcBufs > 1 && ntl > 1) issue_mma(1);
   }
   const uint32_t lane_base = (uint32_t)((tid >> 5) * 32) << 16;
+  float extra = 0.f;  // how far this chain has raised its reference above the one folded into the coefficient row
 #ifdef CB2_TC_PROF
   long long pw = 0, pc_ = 0, ps = 0, p0, pld = 0, pfree = 0, pissue = 0;
 #endif
@@ -624,10 +639,10 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
     if (tid == 0 && t + kTcBufs < ntl) load_tile(t + kTcBufs);   // MMA(t) is complete: its stage may be refilled
     const float csum0 = csum;
     const int cidx0 = cidx;
-    bool init = t == 0;  // the reference starts at the score of the level's first leaf
     for (;;) {
-      float nm = -m;
       float gmax = -INFINITY;
+      const bool shifted = __any_sync(0xffffffffu, extra != 0.f);  // some chain of the warp has raised its reference in this pass
+      const float nx = -extra;
 #pragma unroll 1  // one copy of the 32-leaf body: the kernel is large enough to miss in the instruction cache
       for (int c0 = 0; c0 < kTcTile; c0 += 32) {
         const int z0 = t * kTcTile + c0;
@@ -641,18 +656,26 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
 #ifdef CB2_TC_PROF
         pld += clock64() - q0;
 #endif
-        if (init) { m = __uint_as_float(r[0]); nm = -m; init = false; }
         if (z0 + 32 > cnt) {  // the block that straddles the end of the level: padding leaves carry no mass
 #pragma unroll
           for (int g = 0; g < 32; ++g)
             if (z0 + g >= cnt) r[g] = 0xff800000u;  // -inf
         }
         float s[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!shifted) {
 #pragma unroll
-        for (int g = 0; g < 32; ++g) {
-          const float e = __uint_as_float(r[g]) + nm;
-          gmax = fmaxf(gmax, e);
-          s[g & 3] += fast_exp2(e);
+          for (int g = 0; g < 32; ++g) {
+            const float e = __uint_as_float(r[g]);
+            gmax = fmaxf(gmax, e);
+            s[g & 3] += fast_exp2(e);
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 32; ++g) {
+            const float e = __uint_as_float(r[g]) + nx;
+            gmax = fmaxf(gmax, e);
+            s[g & 3] += fast_exp2(e);
+          }
         }
         csum += (s[0] + s[1]) + (s[2] + s[3]);
         if (((z0 + 32) & (CH - 1)) == 0 && z0 + 32 <= cnt) { chunk[cidx * kS + tid] = csum; csum = 0.f; ++cidx; }
@@ -662,6 +685,7 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
       if (gmax > 60.f) {
         const float up = gmax, sc = fast_exp2(-up);
         m += up;
+        extra += up;
         csum = csum0 * sc;
         for (int c = 0; c < cidx0; ++c) chunk[c * kS + tid] *= sc;
       } else {
@@ -897,7 +921,8 @@ gibbs_kernel(const GibbsArgs a) {
             if (cta_flat) {
               if (CH < 32) CH = 32;  // the tensor-core pass sums blocks of 32 leaves (pass 2 below scans the same chunks)
               leaf_pass_tc<T, DIM>(reinterpret_cast<const float*>(pool) + (size_t)dj.feat_off32 * 32, cnt, CH, cc[0], dj.uniform != 0, smem_raw, TILE_BYTES,
-                                   bars, use0, use1, tc, reinterpret_cast<float*>(chunk), tid, m[0], csum[0], cidx);
+                                   bars, use0, use1, tc, reinterpret_cast<float*>(chunk), tid, m[0], csum[0], cidx,
+                                   reinterpret_cast<const float*>(lrec) + (size_t)ind_s[j * kS + tid] * RECL);
               done_tc = true;
             }
           }
