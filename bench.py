@@ -301,7 +301,7 @@ def main():
     }
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # (the contract: rank 0 at N = 1 only)
         val, sec, thr = cpu_reference_arm(1, 0)
         cpu = {"value": val, "unit": "samples/s", "cores": thr, "kind": "port",
                "sample": f"1 variable of the same workload (8x4096 -> 4096 samples + LOO bandwidth), {sec:.1f} s on the host"}
