@@ -324,3 +324,54 @@ def test_mmd_1e5_points_against_the_full_oracle(cb, ctx32):
     ov, og = oracle.mmd_se_batch(a, b, 1.0, c, backward=True)
     assert abs(v[0] - ov[0]) <= 1e-5 * scale
     assert np.allclose(g, og, rtol=2e-4, atol=1e-5 * np.abs(og).max())
+
+
+def test_full_size_properties_mmd_1e5(cb, ctx32):
+    """Size-independent properties at the headline size (two 1e5-point clouds, FP32): mmd(a, a) = 0, mmd(a, b) = mmd(b, a), a rigid
+    motion applied to both clouds leaves the value unchanged, and the eight tile shards of a multi-GPU split add up to the whole."""
+    rng = np.random.default_rng(11)
+    P = 100000
+    a = rng.normal(size=(P, 3))
+    b = rng.normal(size=(P, 3)) * 1.1 + [0.3, 0.0, -0.2]
+    s_ab = cb.mmd_sums(a, b, 1.0, ctx=ctx32)
+    scale = (s_ab[0] + 2 * s_ab[1] + s_ab[2]) / P**2
+    assert abs(cb.mmd(a, a, 1.0, ctx=ctx32)) <= 2e-6 * scale
+    v_ab, v_ba = cb.mmd(a, b, 1.0, ctx=ctx32), cb.mmd(b, a, 1.0, ctx=ctx32)
+    assert abs(v_ab - v_ba) <= 2e-6 * scale and v_ab > 0
+    c = np.array([4.0, -3.0, 2.0, 0.3, -0.2, 0.5])
+    ta, tb = oracle.transform_points(3, c, a, backward=False), oracle.transform_points(3, c, b, backward=False)
+    assert abs(cb.mmd(ta, tb, 1.0, ctx=ctx32) - v_ab) <= 1e-5 * scale
+    parts = np.sum([cb.mmd_sums_shard(a, b, 1.0, r, 8, ctx=ctx32) for r in range(8)], axis=0)
+    assert np.allclose(parts, s_ab, rtol=1e-6)
+
+
+def test_full_size_product_closed_form_gaussians(cb, ctx32):
+    """C5 shape (D = 8 messages x N = 4096 kernels, d = 6, N_out = 4096, FP32, tensor-core leaf pass) on inputs with a closed form:
+    message j holds samples of N(m_j, S_j), so the product is Gaussian with precision sum_j (S_j + bw_j^2)^-1."""
+    rng = np.random.default_rng(12)
+    D, N, d = 8, 4096, 6
+    dens, prec, pm = [], np.zeros(d), np.zeros(d)
+    for j in range(D):
+        mj = rng.normal(size=d) * 0.2
+        sj = rng.uniform(0.4, 0.8, size=d)
+        pts = mj + rng.normal(size=(N, d)) * sj
+        bw = 1.06 * pts.std(0) * N ** -0.2
+        dens.append((pts, bw))
+        lam = 1.0 / (pts.var(0) + bw**2)
+        prec += lam
+        pm += lam * pts.mean(0)
+    want_mean, want_var = pm / prec, 1.0 / prec
+    pts, lab = cb.product_points(dens, (0,) * d, 4096, seed=3, ctx=ctx32)
+    # (the multiscale sampler with Niter = 1 carries a residual bias of 0.1 - 0.2 sigma on the oracle as well: DESIGN.md sec. 2)
+    assert np.all(np.abs(pts.mean(0) - want_mean) < 0.25 * np.sqrt(want_var)), (pts.mean(0), want_mean)
+    opts, olab = oracle.product(dens, 512, seed=3, circular=[0] * d, ubits=24)
+    assert np.all(np.abs(pts[:512].mean(0) - opts.mean(0)) < 0.1 * np.sqrt(want_var))   # and agrees with the oracle chains
+    # variance: with Niter = 1 and eight messages the multiscale sampler is over-dispersed against the exact product (by ~40 % here,
+    # on the oracle and the device alike: two sweeps per level do not mix eight label chains fully); the device must show the
+    # oracle's spread, and both stay within a factor of the closed form
+    assert np.allclose(pts.var(0), opts.var(0), rtol=0.2)
+    assert np.all(pts.var(0) > 0.9 * want_var) and np.all(pts.var(0) < 2.0 * want_var)
+    # the chains spread over the kernels near the product's mode exactly as the oracle's do (FP32 flips a fraction of a percent)
+    assert lab.min() >= 0 and lab.max() < N
+    assert np.mean(lab[:512] == olab) > 0.98
+    assert len(np.unique(lab[:, 0])) >= len(np.unique(olab[:, 0]))
