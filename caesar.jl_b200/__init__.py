@@ -437,12 +437,15 @@ def product_points(dens, circular, Nout, seed=0, niter=1, stream=0, sample_offse
 
 
 FACTOR_PRIOR_POSE2, FACTOR_POSE2POSE2, FACTOR_POSE2POINT2_BEARINGRANGE, FACTOR_PRIOR_POSE3, FACTOR_POSE3POSE3 = 0, 1, 2, 3, 4
+FACTOR_PRIOR_POINT2, FACTOR_POINT2POINT2_RANGE = 5, 6
 
 
 def _conv_dims(kind, rev):
     """(coordinates of the noise / mean, coordinates of the target) of a closed-form convolution."""
-    if kind >= FACTOR_PRIOR_POSE3:
+    if kind in (FACTOR_PRIOR_POSE3, FACTOR_POSE3POSE3):
         return 6, 6
+    if kind in (FACTOR_PRIOR_POINT2, FACTOR_POINT2POINT2_RANGE):
+        return 3, 2
     return 3, (2 if (kind == FACTOR_POSE2POINT2_BEARINGRANGE and not rev) else 3)
 
 

@@ -6,6 +6,8 @@
 
 namespace {
 
+__host__ __device__ inline bool is_pose3(int kind) { return kind == CB2_FACTOR_PRIOR_POSE3 || kind == CB2_FACTOR_POSE3POSE3; }
+
 struct ConvDev {
   int kind, reverse, N, n_src, n_aux;
   uint32_t stream;
@@ -123,11 +125,21 @@ __global__ void approx_conv_kernel(const ConvDev* __restrict__ descs, uint32_t k
   const ConvDev c = descs[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.N) return;
-  if (c.kind >= CB2_FACTOR_PRIOR_POSE3) { conv_pose3(c, i, k0, k1); return; }
+  if (is_pose3(c.kind)) { conv_pose3(c, i, k0, k1); return; }
   double z[3], nz[3];
   normal3((uint32_t)i, c.stream, k0, k1, z);
   for (int r = 0; r < 3; ++r) nz[r] = c.mean[r] + c.chol[r * 3] * z[0] + c.chol[r * 3 + 1] * z[1] + c.chol[r * 3 + 2] * z[2];
-  if (c.kind == CB2_FACTOR_PRIOR_POSE2) {
+  if (c.kind == CB2_FACTOR_PRIOR_POINT2) {
+    c.out[(size_t)i * 2] = nz[0]; c.out[(size_t)i * 2 + 1] = nz[1];
+  } else if (c.kind == CB2_FACTOR_POINT2POINT2_RANGE) {  // ring around the known point: nz[0] = range, direction uniform (draw 2)
+    const double* p = c.src + (size_t)(i % c.n_src) * 2;
+    uint32_t o[4];
+    philox4x32_10((uint32_t)i, 2u, c.stream, 4u, k0, k1, o);
+    double sn, cs;
+    sincospi(2.0 * u01<double>(o[0], o[1]) - 1.0, &sn, &cs);
+    c.out[(size_t)i * 2] = p[0] + nz[0] * cs;
+    c.out[(size_t)i * 2 + 1] = p[1] + nz[0] * sn;
+  } else if (c.kind == CB2_FACTOR_PRIOR_POSE2) {
     c.out[(size_t)i * 3] = nz[0]; c.out[(size_t)i * 3 + 1] = nz[1]; c.out[(size_t)i * 3 + 2] = wrap_pi(nz[2]);
   } else if (c.kind == CB2_FACTOR_POSE2POSE2) {
     const double* p = c.src + (size_t)(i % c.n_src) * 3;
@@ -163,15 +175,20 @@ __global__ void approx_conv_kernel(const ConvDev* __restrict__ descs, uint32_t k
   }
 }
 
+inline bool is_point2(int kind) { return kind == CB2_FACTOR_PRIOR_POINT2 || kind == CB2_FACTOR_POINT2POINT2_RANGE; }
 inline int out_dim(const cb2_conv_desc& c) {
-  if (c.kind >= CB2_FACTOR_PRIOR_POSE3) return 6;
+  if (is_pose3(c.kind)) return 6;
+  if (is_point2(c.kind)) return 2;
   return (c.kind == CB2_FACTOR_POSE2POINT2_BEARINGRANGE && !c.reverse) ? 2 : 3;
 }
 inline int src_dim(const cb2_conv_desc& c) {
-  if (c.kind >= CB2_FACTOR_PRIOR_POSE3) return 6;
+  if (is_pose3(c.kind)) return 6;
+  if (is_point2(c.kind)) return 2;
   return (c.kind == CB2_FACTOR_POSE2POINT2_BEARINGRANGE && c.reverse) ? 2 : 3;
 }
-inline bool is_prior(const cb2_conv_desc& c) { return c.kind == CB2_FACTOR_PRIOR_POSE2 || c.kind == CB2_FACTOR_PRIOR_POSE3; }
+inline bool is_prior(const cb2_conv_desc& c) {
+  return c.kind == CB2_FACTOR_PRIOR_POSE2 || c.kind == CB2_FACTOR_PRIOR_POSE3 || c.kind == CB2_FACTOR_PRIOR_POINT2;
+}
 
 // residual of the relative-pose factors (ScatterAlignPose2/3, Pose2Pose2, Pose3Pose3): one thread per particle
 __global__ void se_residual_kernel(int dim, const double* __restrict__ X, const double* __restrict__ p, const double* __restrict__ q,
@@ -207,7 +224,7 @@ extern "C" int cb2_approx_conv_batch(cb2_ctx* ctx, const cb2_conv_desc* descs, i
   int maxN = 0;
   for (int b = 0; b < B; ++b) {
     const cb2_conv_desc& c = descs[b];
-    CB2_REQUIRE(ctx, c.kind >= 0 && c.kind <= CB2_FACTOR_POSE3POSE3, "convolution %d: unknown factor kind %d", b, c.kind);
+    CB2_REQUIRE(ctx, c.kind >= 0 && c.kind <= CB2_FACTOR_POINT2POINT2_RANGE, "convolution %d: unknown factor kind %d", b, c.kind);
     CB2_REQUIRE(ctx, c.N > 0 && c.out, "convolution %d: N <= 0 or null out", b);
     if (!is_prior(c)) CB2_REQUIRE(ctx, c.src && c.n_src > 0, "convolution %d: missing source samples", b);
     if (c.kind == CB2_FACTOR_POSE2POINT2_BEARINGRANGE && c.reverse)
@@ -272,7 +289,7 @@ extern "C" int cb2_approx_conv_batch_dev(cb2_ctx* ctx, const cb2_conv_desc* desc
   int maxN = 0;
   for (int b = 0; b < B; ++b) {
     const cb2_conv_desc& c = descs[b];
-    CB2_REQUIRE(ctx, c.kind >= 0 && c.kind <= CB2_FACTOR_POSE3POSE3, "convolution %d: unknown factor kind %d", b, c.kind);
+    CB2_REQUIRE(ctx, c.kind >= 0 && c.kind <= CB2_FACTOR_POINT2POINT2_RANGE, "convolution %d: unknown factor kind %d", b, c.kind);
     CB2_REQUIRE(ctx, c.N > 0 && c.out, "convolution %d: N <= 0 or null out", b);
     if (!is_prior(c)) CB2_REQUIRE(ctx, c.src && c.n_src > 0, "convolution %d: missing source samples", b);
     if (c.kind == CB2_FACTOR_POSE2POINT2_BEARINGRANGE && c.reverse)

@@ -63,6 +63,9 @@ __host__ __device__ inline int node_of(int N, int l, int p) {
 #ifndef CB2_GIBBS_TC
 #define CB2_GIBBS_TC 1
 #endif
+#ifndef CB2_GROUP_OPT
+#define CB2_GROUP_OPT 0
+#endif
 #ifndef CB2_COARSE_RSQ
 #define CB2_COARSE_RSQ 1   // coarse levels of the packed FP32 d = 6 loops: 2 MUFU.RSQ + 1 MUFU.EX2 per candidate (gibbs.cuh)
 #endif

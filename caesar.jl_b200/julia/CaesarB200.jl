@@ -231,8 +231,9 @@ function _partial_product(ff, M; Niter::Int, N::Int, ctx::Context = context())
 end
 
 # ------------------------------------------------------------------------------------------------ approxConv (closed form)
-# Proposals of closed-form relative factors (PriorPose2, Pose2Pose2, Pose2Point2BearingRange), all factors of a Gibbs
-# colour in one launch; hook: IIF.approxConvBelief / sampleFactor for these factor types.
+# Proposals of closed-form relative factors (kinds 0 PriorPose2, 1 Pose2Pose2, 2 Pose2Point2BearingRange, 3 PriorPose3, 4 Pose3Pose3,
+# 5 PriorPoint2, 6 Point2Point2Range), all factors of a Gibbs colour in one launch; hook: IIF.approxConvBelief / sampleFactor for
+# these factor types.
 struct CB2ConvDesc
   kind::Int32
   reverse::Int32
@@ -242,7 +243,7 @@ struct CB2ConvDesc
   aux::Ptr{Float64}
   n_aux::Int32
   stream::UInt32
-  mean::NTuple{6,Float64}      # Pose2 kinds use the first 3 entries, Pose3 kinds (3 = prior, 4 = Pose3Pose3) all 6
+  mean::NTuple{6,Float64}      # Pose2 / Point2 kinds use the first 3 entries (3 x 3 layout), Pose3 kinds (3, 4) all 6
   chol::NTuple{36,Float64}     # lower Cholesky factor, row-major n x n in the first n^2 entries (n = 3 | 6)
   out::Ptr{Float64}
 end

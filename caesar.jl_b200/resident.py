@@ -85,12 +85,13 @@ def upload_belief(mkd, slab, ctx):
 
 def approxConvBatch_dev(convs, slab, seed=0, ctx=None):
     """`approxConvBatch` with device-resident sources: convs[i]['src'] / ['aux'] are DeviceArray (or None); returns DeviceArray."""
+    from . import _conv_dims
     B = len(convs)
     descs = (ConvDesc * B)()
     outs = []
     for b, c in enumerate(convs):
         kind, rev = int(c["kind"]), int(bool(c.get("reverse", False)))
-        nz, dt = (6, 6) if kind >= 3 else (3, 2 if (kind == 2 and not rev) else 3)
+        nz, dt = _conv_dims(kind, rev)
         N = int(c["N"])
         out = DeviceArray(slab.take(N * dt * 8), N, dt)
         outs.append(out)

@@ -54,6 +54,21 @@ class Pose2Point2BearingRange:
 
 
 @dataclass
+class PriorPoint2:
+    mean: np.ndarray
+    cov: np.ndarray
+
+
+@dataclass
+class Point2Point2Range:
+    """RoME.Point2Point2Range(Normal(rho, sigma)): one constraint on two coordinates.  The proposal is the ring of radius ~ N(rho, sigma)
+    around the other variable's particles with a uniform direction (what IIF's per-particle solve produces from scattered starting
+    points; R:test/ICRA2022_tests/insufficient_data.jl:70-85,126-142)."""
+    rho: float
+    sigma: float
+
+
+@dataclass
 class FactorGraph:
     variables: dict = field(default_factory=dict)
     factors: list = field(default_factory=list)  # (labels, factor)
@@ -110,8 +125,14 @@ def approx_conv(fg, labels, factor, target, rng):
         x = rng.multivariate_normal(factor.mean, factor.cov, size=N)
         x[:, 2] = _wrap(x[:, 2])
         return x
+    if isinstance(factor, PriorPoint2):
+        return rng.multivariate_normal(factor.mean, factor.cov, size=N)
     other = labels[0] if labels[1] == target else labels[1]
     src = _resample(fg.variables[other].belief.pts, N, rng)
+    if isinstance(factor, Point2Point2Range):
+        r = factor.rho + factor.sigma * rng.standard_normal(N)
+        th = rng.uniform(-np.pi, np.pi, size=N)
+        return np.c_[src[:, 0] + r * np.cos(th), src[:, 1] + r * np.sin(th)]
     if isinstance(factor, Pose2Pose2):
         X = rng.multivariate_normal(factor.mean, factor.cov, size=N)
         return _compose(src, X) if target == labels[1] else _compose_inv(src, X)
@@ -188,10 +209,17 @@ def conv_desc(fg, labels, factor, target, stream, rng=None):
     N = fg.N
     if isinstance(factor, PriorPose2):
         return dict(kind=0, reverse=False, N=N, mean=factor.mean, chol=np.linalg.cholesky(factor.cov), stream=stream, src=None, aux=None)
+    if isinstance(factor, PriorPoint2):
+        L = np.zeros((3, 3))
+        L[:2, :2] = np.linalg.cholesky(factor.cov)
+        return dict(kind=5, reverse=False, N=N, mean=[factor.mean[0], factor.mean[1], 0.0], chol=L, stream=stream, src=None, aux=None)
     if isinstance(factor, Pose2Pose2) and (factor.multihypo is not None or factor.nullhypo > 0):
         return _hypo_desc(fg, labels, factor, target, stream, rng)
     other = labels[0] if labels[1] == target else labels[1]
     src = fg.variables[other].belief.pts
+    if isinstance(factor, Point2Point2Range):
+        return dict(kind=6, reverse=target == labels[0], N=N, mean=[factor.rho, 0.0, 0.0], chol=np.diag([factor.sigma, 0.0, 0.0]),
+                    stream=stream, src=src, aux=None)
     if isinstance(factor, Pose2Pose2):
         return dict(kind=1, reverse=target == labels[0], N=N, mean=factor.mean, chol=np.linalg.cholesky(factor.cov), stream=stream,
                     src=src, aux=None)
@@ -234,6 +262,8 @@ def solveGraph(fg, backend, gibbs_iters=3, seed=0, stats=None):
     stats = stats if stats is not None else {}
     stats.update(products=0, shapes={}, product_calls=0, t_products=0.0, t_bandwidth=0.0)
     t0 = time.perf_counter()
+    if hasattr(backend, "begin"):
+        backend.begin(fg)
     # forward initialisation (initAll!): a variable is initialised from the first factor whose other end already is
     pending = [v for v in fg.variables if fg.variables[v].belief is None]  # (a re-solve after adding to the graph keeps the rest)
     while pending:
@@ -329,6 +359,37 @@ def extend_MultihypoCorners(fg, stage):
         raise ValueError("stage 0..3")
 
 
+TUT3_POSES = {"x0": (0.0, 0.0), "x1": (50.0, 0.0), "x2": (100.0, 0.0), "x3": (100.0, 50.0), "x4": (100.0, 100.0), "x5": (50.0, 100.0),
+              "x6": (0.0, 100.0), "x7": (0.0, 50.0), "x8": (0.0, -50.0)}
+TUT3_BEACONS = {"l1": (10.0, 30.0), "l2": (30.0, -30.0), "l3": (80.0, 40.0), "l4": (120.0, -50.0)}
+
+
+def generateGraph_Tut3(N=100):
+    """Range-only SLAM of the ICRA 2022 tutorial 3, first stage (R:test/ICRA2022_tests/insufficient_data.jl:9-27,104-134): x0 with
+    no prior, three beacons of which two carry priors, one range measurement to each."""
+    fg = FactorGraph(N=N)
+    for v in ("x0", "l1", "l2", "l3"):
+        fg.addVariable(v, "Point2")
+    for l in ("l1", "l2"):
+        fg.addFactor([l], PriorPoint2(np.array(TUT3_BEACONS[l]), np.eye(2)))
+    for l, sigma in (("l1", 2.0), ("l2", 3.0), ("l3", 3.0)):
+        fg.addFactor(["x0", l], Point2Point2Range(float(np.hypot(*np.subtract(TUT3_BEACONS[l], TUT3_POSES["x0"]))), sigma))
+    return fg
+
+
+def tut3_vehicle_drives(fg, frm, to, measurelimit=150.0):
+    """`vehicle_drives!` of the same test (:66-93): an odometry range to the new position, then a range to every beacon in reach."""
+    if to not in fg.variables:
+        fg.addVariable(to, "Point2")
+        fg.addFactor([frm, to], Point2Point2Range(float(np.hypot(*np.subtract(TUT3_POSES[frm], TUT3_POSES[to]))), 3.0))
+    for l, pos in TUT3_BEACONS.items():
+        rho = float(np.hypot(*np.subtract(pos, TUT3_POSES[to])))
+        if rho < measurelimit:
+            if l not in fg.variables:
+                fg.addVariable(l, "Point2")
+            fg.addFactor([to, l], Point2Point2Range(rho, 3.0))
+
+
 def getPPE(belief):
     """Point estimate: Euclidean mean, circular mean on wrapped coordinates."""
     if hasattr(belief, "to_host"):  # device-resident belief: this is where the host waits
@@ -376,6 +437,12 @@ class DeviceResidentBackend:
 
     def approx_conv_batch(self, convs, seed):
         return self.r.approxConvBatch_dev(convs, self.slab, seed=seed, ctx=self.ctx)
+
+    def begin(self, fg):
+        """A re-solve after the graph has grown starts from host beliefs: they go back to the device first."""
+        for v in fg.variables.values():
+            if v.belief is not None and not hasattr(v.belief, "to_host"):
+                v.belief = self.r.upload_belief(v.belief, self.slab, self.ctx)
 
     def finish(self, fg):
         """Downloads every belief (the one synchronisation of the solve)."""

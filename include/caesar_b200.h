@@ -197,7 +197,11 @@ typedef enum {
   CB2_FACTOR_POSE2POSE2 = 1,                /* forward: x_j = x_i o exp(z);  reverse: x_i = x_j o exp(z)^-1 */
   CB2_FACTOR_POSE2POINT2_BEARINGRANGE = 2,  /* forward: landmark from pose;  reverse: pose position from landmark, heading from aux */
   CB2_FACTOR_PRIOR_POSE3 = 3,               /* Pose3 coordinates [t; rotation vector]: t = mean_t + n_t, R = Exp(mean_w) Exp(n_w) */
-  CB2_FACTOR_POSE3POSE3 = 4                 /* forward: x_j = x_i o exp(z) on SE(3);  reverse: x_i = x_j o exp(z)^-1 */
+  CB2_FACTOR_POSE3POSE3 = 4,                /* forward: x_j = x_i o exp(z) on SE(3);  reverse: x_i = x_j o exp(z)^-1 */
+  CB2_FACTOR_PRIOR_POINT2 = 5,              /* target ~ N(mean[0..1], L L^T), L = chol[0], chol[3], chol[4] (3 x 3 layout), no source */
+  CB2_FACTOR_POINT2POINT2_RANGE = 6         /* range-only (R:test/ICRA2022_tests/insufficient_data.jl:70-85): x_j = x_i + rho (cos t, sin t),
+                                               rho ~ N(mean[0], chol[0]^2), t uniform on the circle -- one constraint on two coordinates,
+                                               the same in both directions */
 } cb2_factor_kind;
 
 typedef struct {

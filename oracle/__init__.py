@@ -160,6 +160,26 @@ def kde_sample(mu, sigma, n, seed, stream=0, w=None, circular=None, ubits=53):
     return out
 
 
+def heatmap_grid_density(img, domain, N, seed):
+    """CPU counterpart of `HeatmapGridDensity(img, (x, y); N)` as caesar.jl_b200/factors.py builds it (upstream's
+    IIF type is not in the reference tree, R:ext/Images/ScatterAlignPose2.jl:23-24 only calls it): grid cells weighted by the clipped
+    image value (cells below 1e-9 of the maximum dropped), N draws from the weighted cell mixture with half a grid spacing of
+    Gaussian jitter, LOO bandwidth of the draws.  Returns (points N x 2, bandwidth 2)."""
+    img = np.asarray(img, dtype=np.float64)
+    x, y = (np.asarray(v, dtype=np.float64) for v in domain)
+    cells, w = [], []
+    top = max(img.max(), 0.0)
+    for i in range(len(x)):
+        for j in range(len(y)):
+            v = max(img[i, j], 0.0)
+            if v > top * 1e-9:
+                cells.append((x[i], y[j]))
+                w.append(v)
+    half = 0.5 * np.array([np.diff(x).mean(), np.diff(y).mean()])
+    pts = kde_sample(np.array(cells), half, int(N), seed, w=np.array(w))
+    return pts, kde_bw_loo(pts)
+
+
 def set_level_down(mode):
     """1: a chain descends to a child drawn in proportion to the children's weights (default); 0: always the first child."""
     lib().cb2o_set_level_down(int(mode))
@@ -222,13 +242,14 @@ def se_residual(dim, X, p, q):
 
 
 def approx_conv(kind, reverse, N, mean, chol, seed, stream=0, src=None, aux=None):
-    """Closed-form approxConv (kind 0 Pose2 prior, 1 Pose2Pose2, 2 Pose2Point2BearingRange, 3 Pose3 prior, 4 Pose3Pose3);
+    """Closed-form approxConv (kind 0 Pose2 prior, 1 Pose2Pose2, 2 Pose2Point2BearingRange, 3 Pose3 prior, 4 Pose3Pose3, 5 Point2 prior,
+    6 Point2Point2Range);
     returns N x d_tgt."""
-    n = 6 if kind >= 3 else 3
+    n = 6 if kind in (3, 4) else 3
     mean, chol = _f64(np.resize(np.asarray(mean, dtype=np.float64), n)), _f64(np.asarray(chol, dtype=np.float64).reshape(n * n))
     src = None if src is None else _f64(src)
     aux = None if aux is None else _f64(aux)
-    dt = 6 if kind >= 3 else (2 if (kind == 2 and not reverse) else 3)
+    dt = 6 if kind in (3, 4) else (2 if (kind in (5, 6) or (kind == 2 and not reverse)) else 3)
     out = np.zeros((N, dt))
     rc = lib().cb2o_approx_conv(kind, int(reverse), N, _p(src), 0 if src is None else src.shape[0], _p(aux),
                                 0 if aux is None else aux.shape[0], stream, _p(mean), _p(chol), C.c_uint64(seed), _p(out))

@@ -648,13 +648,21 @@ int cb2o_se_residual(int dim, const double* X, const double* p, const double* q,
 
 int cb2o_approx_conv(int kind, int reverse, int N, const double* src, int n_src, const double* aux, int n_aux,
                      uint32_t stream, const double* mean, const double* chol, uint64_t seed, double* out) {
-  if (kind < 0 || kind > 4 || N <= 0) return -1;
-  if (kind >= 3) { approx_conv_pose3(kind, reverse, N, src, n_src, stream, mean, chol, seed, out); return 0; }
+  if (kind < 0 || kind > 6 || N <= 0) return -1;
+  if (kind == 3 || kind == 4) { approx_conv_pose3(kind, reverse, N, src, n_src, stream, mean, chol, seed, out); return 0; }
   for (int i = 0; i < N; ++i) {
     double z[3], nz[3];
     for (int k = 0; k < 3; ++k) z[k] = cb2o_normal(seed, (uint32_t)i, (uint32_t)k, stream, 4, 53);
     for (int r = 0; r < 3; ++r) nz[r] = mean[r] + chol[r * 3] * z[0] + chol[r * 3 + 1] * z[1] + chol[r * 3 + 2] * z[2];
-    if (kind == 0) {
+    if (kind == 5) { /* PriorPoint2 */
+      out[(size_t)i * 2] = nz[0]; out[(size_t)i * 2 + 1] = nz[1];
+    } else if (kind == 6) { /* Point2Point2Range (RoME; graph of R:test/ICRA2022_tests/insufficient_data.jl:70-85): a ring around the
+                               known point, range nz[0], direction uniform -- one constraint on two coordinates */
+      const double* p = src + (size_t)(i % n_src) * 2;
+      double th = 0.5 * TWO_PI * (2.0 * cb2o_uniform(seed, (uint32_t)i, 2, stream, 4, 53) - 1.0);
+      out[(size_t)i * 2] = p[0] + nz[0] * cos(th);
+      out[(size_t)i * 2 + 1] = p[1] + nz[0] * sin(th);
+    } else if (kind == 0) {
       out[(size_t)i * 3] = nz[0]; out[(size_t)i * 3 + 1] = nz[1]; out[(size_t)i * 3 + 2] = wrap_pi(nz[2]);
     } else if (kind == 1) {
       const double* p = src + (size_t)(i % n_src) * 3;

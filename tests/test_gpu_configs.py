@@ -52,6 +52,30 @@ def test_c1_heatmap_scatter_align_pose2(cb, ctx):
     assert np.abs(np.median(coords, axis=0) - pCq).max() < 0.5
 
 
+def test_heatmap_grid_density_matches_oracle_counterpart(cb):
+    """the heatmap construction (cell weighting, weighted device sampling with the block-scan CDF, LOO
+    bandwidth) against its CPU counterpart on the C1 grid (301 x 301 cells, N = 1000) and on a ragged small one."""
+    ctx64 = cb.Context(0, "fp64")
+    x = np.arange(-15, 15.0001, 0.1)
+    gx, gy = np.meshgrid(x, x, indexing="ij")
+    f = lambda cx, cy, s: np.exp(-0.5 * ((gx - cx) ** 2 + (gy - cy) ** 2) / s) / (2 * np.pi * s)
+    im = f(3.0, 0.0, 0.1) + f(8.0, 0.0, 0.4) + f(0.0, 5.0, 0.1)
+    hgd = cb.HeatmapGridDensity(im, (x, x), N=1000, seed=5, ctx=ctx64)
+    want_pts, want_bw = oracle.heatmap_grid_density(im, (x, x), 1000, 5)
+    assert hgd.densityFnc.pts.shape == (1000, 2)
+    assert np.allclose(hgd.densityFnc.pts, want_pts, rtol=0, atol=1e-9)
+    assert np.allclose(hgd.densityFnc.bw, want_bw, rtol=1e-6)
+    # mass lands on the three blobs in proportion to their integrals (1 : 1 : 1)
+    share = [np.mean(np.hypot(*(want_pts - c).T) < 2.5) for c in ((3.0, 0.0), (8.0, 0.0), (0.0, 5.0))]
+    assert np.allclose(share, 1 / 3, atol=0.06)
+    rng = np.random.default_rng(0)
+    xs, ys = np.linspace(0, 1, 7), np.linspace(-2, 2, 13)
+    small = rng.uniform(-0.2, 1.0, size=(7, 13))   # negative cells carry no mass
+    h2 = cb.HeatmapGridDensity(small, (xs, ys), N=257, seed=9, ctx=ctx64)
+    p2, b2 = oracle.heatmap_grid_density(small, (xs, ys), 257, 9)
+    assert np.allclose(h2.densityFnc.pts, p2, rtol=0, atol=1e-9) and np.allclose(h2.densityFnc.bw, b2, rtol=1e-6)
+
+
 def test_c3_scatter_align_pose3_clouds(cb, ctx):
     """R:test/testScatterAlignPose3.jl:29-30 / testScatterAlignPose2.jl:271-299: randn(P,3) clouds, moved cloud offset
     pCq = [2,0,2,0,0,pi/10], kde bandwidth 0.1 per axis (testScatterAlignParched.jl:41-42), mmd bw = 1."""
