@@ -307,7 +307,9 @@ __device__ __forceinline__ T score_regs(const RecR<T, RecLen<DIM, MODE>::value, 
 // one scoring pass over the candidates of a level held in a shared-memory tile: chunk partial sums of exp2(e - m) for
 // the R chains of this thread; every record is fetched once and scored against all R chains
 // (a branch-free variant -- sum the tile optimistically, test the largest exponent once per tile, repeat the tile after a raise --
-// was measured slower here: 213 vs 192 ms per 256 variables; the tensor-core leaf pass below does use that scheme per tile)
+// was measured slower here: 213 vs 192 ms per 256 variables, and so was the same scheme per group of eight, 178.5 vs 171.9: with
+// the exponentials taken one by one behind each score the MUFU results arrive late; the tensor-core leaf pass below does use that
+// scheme per tile)
 template <typename T, int DIM, int MODE, bool PACK, int R>
 __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int zbase, int CH, const ChainConst<T, DIM> (&cc)[R],
                                           const PackedConst (&pc)[R], uint32_t circ, T* __restrict__ chunk, int tid, T (&m)[R],
@@ -336,44 +338,6 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
 #pragma unroll
   for (int r = 0; r < R; ++r) nm[r] = -m[r];
   for (int z = 0; z < ntg; z += G) {
-#if CB2_GROUP_OPT
-    // optimistic group: sum against the current reference, test the group's largest exponent afterwards, repeat the group after a raise
-    T cs0[R], gm[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) { cs0[r] = csum[r]; gm[r] = -INFINITY; }
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      RecR<T, REC, PACK> rec;
-      load_recr<true>(tb + (z + g) * REC, rec);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        T mu1;
-        const T e1 = score_regs<T, DIM, MODE, PACK>(rec, cc[r], pc[r], circ, nm[r], mu1);
-        gm[r] = fmax(gm[r], e1);
-        if constexpr (HasMul<MODE, PACK>::value) csum[r] = fma(fast_exp2(e1), mu1, csum[r]);
-        else csum[r] += fast_exp2(e1);
-      }
-    }
-    bool redo = false;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (gm[r] > thr[r]) {
-        const T up = gm[r] - (thr[r] - T(60));
-        const T sc = fast_exp2(-up);
-        cs0[r] *= sc;
-        for (int c = 0; c < cidx; ++c) chunk[c * kS + r * NT + tid] *= sc;
-        m[r] += up;
-        nm[r] = -m[r];
-        redo = true;
-      }
-    }
-    if (redo) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) csum[r] = cs0[r];
-      z -= G;
-      continue;
-    }
-#else
     T e[R][G], mu[R][G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -403,7 +367,6 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
         else csum[r] += fast_exp2(e[r][g]);
       }
     }
-#endif
     if (((zbase + z + G) & (CH - 1)) == 0) {
 #pragma unroll
       for (int r = 0; r < R; ++r) { chunk[cidx * kS + r * NT + tid] = csum[r]; csum[r] = T(0); }

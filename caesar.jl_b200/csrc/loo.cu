@@ -602,6 +602,144 @@ loo_cluster_kernel(const LooProblem* __restrict__ probs, const int* __restrict__
   cluster.sync();  // no CTA leaves while a peer may still write into its shared memory
 }
 
+// Latency variant for the smallest problems (N <= kTinyN: the N = 100 particles IIF solves with by default).  The single-CTA kernel
+// above spends ~2.6 us per golden-section step on 100 points -- a thread per row leaves 60 % of the CTA idle, every step rebuilds
+// a 1024-entry scaled copy and passes the search state through shared memory behind four barriers.  Here the CTA's 256 threads
+// are laid out as (row, column segment): N = 100 gives 128 row slots x 2 segments, N <= 64 four segments, N <= 32 eight; the
+// points are stored once (centred, unscaled: the scale of the step is applied to the difference), the partial row sums meet in
+// shared memory, and EVERY thread advances an identical private copy of the search state from the per-warp sums, so a step
+// costs two barriers.  The bandwidths land in the output array directly (no collect launch).  Same golden-section path as the
+// other kernels; sums are taken in a different order (FP32: 1e-6 relative on the objective).
+constexpr int kTinyN = 128;
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+loo_tiny_kernel(const LooProblem* __restrict__ probs, const int* __restrict__ ids, LooState* __restrict__ st, double* __restrict__ out) {
+  const int p = ids[blockIdx.x];
+  const LooProblem pr = probs[p];
+  const int N = pr.N, tid = threadIdx.x;
+  __shared__ double sk[kTinyN];
+  __shared__ __align__(16) T sx[kTinyN + 4];
+  __shared__ T part[kThreads];
+  __shared__ double sred[kThreads / 32];
+  __shared__ double slogh;
+  int P2 = 2;
+  while (P2 < N) P2 <<= 1;
+  if (tid < P2) sk[tid] = tid < N ? pr.x[(size_t)tid * pr.stride] : 1.7976931348623157e308;
+  __syncthreads();
+  for (int k = 2; k <= P2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int ixj = tid ^ j;
+      if (tid < P2 && ixj > tid) {
+        const double a = sk[tid], b = sk[ixj];
+        if ((b < a) == ((tid & k) == 0)) { sk[tid] = b; sk[ixj] = a; }
+      }
+      __syncthreads();
+    }
+  double mn = 1e300;
+  if (tid + 1 < N) mn = sk[tid + 1] - sk[tid];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if ((tid & 31) == 0) sred[tid >> 5] = mn;
+  const bool circ = pr.circular != 0;
+  const double x_mid = circ ? 0.0 : sk[N >> 1];
+  const bool wraps = circ && !(sk[0] >= -CB2_PI && sk[N - 1] <= CB2_PI && sk[N - 1] - sk[0] <= CB2_PI);
+  // centred, unscaled copy; the padding up to a multiple of four sits far away (its kernel values are exactly zero)
+  if (tid < kTinyN + 4) sx[tid] = tid < N ? (T)((circ ? wrap_pi(sk[tid]) : sk[tid]) - x_mid) : T(1e18);
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) mn = fmin(mn, sred[w]);
+  LooState s;
+  loo_bracket(s, mn, sk[N - 1] - sk[0]);
+  const int NR = (N + 31) & ~31;   // row slots: whole warps
+  const int S = kThreads / NR;     // column segments per row
+  const int row = tid % NR, seg = tid / NR;
+  const int cper = ((N + S - 1) / S + 3) & ~3;   // columns per segment, a multiple of four (16-byte loads)
+  const int c0 = min(N, seg * cper), c1 = seg < S ? min(N, c0 + cper) : c0;
+  const int c1p = (c1 + 3) & ~3;   // the last segment runs into the padding
+  const bool live = row < N && c1 > c0;
+  const T xi = sx[row < N ? row : 0];
+  const T self = (row >= c0 && row < c1) ? T(1) : T(0);   // exp2(0) of the row's own column, summed below and taken out again
+  const double invN = 1.0 / N;
+  __syncthreads();  // the sred values of the bracket have been read by everyone
+#ifdef CB2_LOO_PROF
+  long long tp[4] = {0, 0, 0, 0}, tl = clock64();
+  int nsteps = 0;
+#define LOO_T(k) do { long long t_ = clock64(); tp[k] += t_ - tl; tl = t_; } while (0)
+#else
+#define LOO_T(k) do { } while (0)
+#endif
+  for (int it = 0; it < 96 && s.phase != 3; ++it) {  // s is identical in every thread
+    const double h = s.h_eval;
+    T sc;
+    if constexpr (sizeof(T) == 4) sc = 0.84932180028801904f * __frcp_rn((float)h);  // sqrt(0.5 log2 e) / h
+    else sc = (T)(sqrt(0.5 * CB2_LOG2E) / h);
+    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+    if (live) {
+      if (wraps) {
+        const T period = (T)CB2_TWO_PI;
+        for (int j = c0; j < c1; ++j) {
+          const T ad = fabs(xi - sx[j]);
+          const T df = fmin(ad, period - ad) * sc;
+          a0 += fast_exp2(-(df * df));
+        }
+      } else {
+#pragma unroll 4
+        for (int j = c0; j < c1p; j += 4) {
+          T q[4];
+          if constexpr (sizeof(T) == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(&sx[j]);
+            q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+          } else {
+            const double2 v0 = *reinterpret_cast<const double2*>(&sx[j]), v1 = *reinterpret_cast<const double2*>(&sx[j + 2]);
+            q[0] = v0.x; q[1] = v0.y; q[2] = v1.x; q[3] = v1.y;
+          }
+          const T d0 = (xi - q[0]) * sc, d1 = (xi - q[1]) * sc, d2 = (xi - q[2]) * sc, d3 = (xi - q[3]) * sc;
+          a0 += fast_exp2(-(d0 * d0)); a1 += fast_exp2(-(d1 * d1)); a2 += fast_exp2(-(d2 * d2)); a3 += fast_exp2(-(d3 * d3));
+        }
+      }
+      a0 -= self;
+    }
+    part[tid] = (a0 + a1) + (a2 + a3);
+    LOO_T(0);
+    __syncthreads();
+    LOO_T(1);
+    if (seg == 0) {  // the first NR / 32 warps own the rows: log of every row sum, summed per warp
+      double v = 0;
+      if (row < N) {
+        T tot = part[row];
+        for (int q = 1; q < S; ++q) tot += part[q * NR + row];
+        if constexpr (sizeof(T) == 4) v = (double)(__log2f(fmaxf(tot, 1.17549435e-38f)) * 0.693147180559945309f);
+        else v = log(tot > 2.2250738585072014e-308 ? tot : 2.2250738585072014e-308);
+      }
+      v = warp_sum(v);
+      if ((tid & 31) == 0) sred[tid >> 5] = v;
+    } else if (tid == kThreads - 1) {  // meanwhile a thread of a segment warp takes the double-precision logarithm of the step
+      slogh = log(h);
+    }
+    LOO_T(2);
+    __syncthreads();
+    LOO_T(1);
+    double t = 0;
+    for (int w = 0; w < NR / 32; ++w) t += sred[w];
+    // the objective up to its constants (0.5 log 2 pi + log(N - 1) shift every value alike): nll(h) ~ log h - mean_i log rowsum_i
+    golden_advance(s, slogh - t * invN);
+    LOO_T(3);
+#ifdef CB2_LOO_PROF
+    ++nsteps;
+#endif
+  }
+#ifdef CB2_LOO_PROF
+  if (blockIdx.x == 0 && (tid == 0 || tid == 255))
+    printf("loo tiny prof tid %d N %d steps %d clk/step: pairs %lld barriers %lld owner %lld advance %lld\n", tid, N, nsteps,
+           tp[0] / max(nsteps, 1), tp[1] / max(nsteps, 1), tp[2] / max(nsteps, 1), tp[3] / max(nsteps, 1));
+#endif
+  if (tid == 0) {
+    if (s.phase != 3) { s.result = s.f1 < s.f2 ? s.x1 : s.x2; s.phase = 3; }  // iteration cap: best point so far
+    st[p] = s;
+    if (out) out[p] = s.result;
+  }
+}
+
 __global__ void loo_collect_kernel(const LooState* __restrict__ st, int P, double* __restrict__ out) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
@@ -619,7 +757,8 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
   const int P = B * d;
   std::vector<LooProblem> probs(P);
   std::vector<int2> cta_map;
-  std::vector<int> small_ids;
+  std::vector<int> small_ids, tiny_ids;
+  const bool tiny_ok = !getenv("CB2_NO_LOO_TINY");
   int maxN = 2;
   long long xs_elems = 0, cp_elems = 0;
   for (int b = 0; b < B; ++b)
@@ -636,7 +775,7 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
       xs_elems += pr.nstride;
       cp_elems += (long long)pr.nstride * pr.nrb;
       if (N[b] > maxN) maxN = N[b];
-      if (pr.small) small_ids.push_back(b * d + k);
+      if (pr.small) (tiny_ok && N[b] <= kTinyN ? tiny_ids : small_ids).push_back(b * d + k);
     }
   // row block rb of a problem visits nrb - rb column tiles: launch the heavy CTAs first (largest-first list scheduling)
   for (int rb = 0; rb < (maxN + kThreads * kRI - 1) / (kThreads * kRI); ++rb)
@@ -645,7 +784,7 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
   if (maxN > CB2_MAX_PRODUCT_N) return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "bandwidth search supports N <= %d (got %d)", CB2_MAX_PRODUCT_N, maxN);
   const bool f64 = ctx->precision == CB2_FP64;
   const size_t tsz = f64 ? sizeof(double) : sizeof(float);
-  size_t need = cb2_align(sizeof(LooProblem) * P) + cb2_align(sizeof(LooState) * P) + cb2_align(sizeof(int2) * (cta_map.size() + 1)) + cb2_align(sizeof(int) * (small_ids.size() + 1)) +
+  size_t need = cb2_align(sizeof(LooProblem) * P) + cb2_align(sizeof(LooState) * P) + cb2_align(sizeof(int2) * (cta_map.size() + 1)) + cb2_align(sizeof(int) * (small_ids.size() + tiny_ids.size() + 1)) +
                 cb2_align(sizeof(double) * P) + cb2_align(sizeof(int) * 64) + cb2_align(sizeof(double) * (size_t)xs_elems) +
                 cb2_align(tsz * (size_t)xs_elems) + cb2_align(tsz * (size_t)cp_elems) + 1024;
   if (scratch_needed) *scratch_needed = need;
@@ -657,7 +796,8 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
   LooProblem* probs_dev = (LooProblem*)take(sizeof(LooProblem) * P);
   LooState* st_dev = (LooState*)take(sizeof(LooState) * P);
   int2* map_dev = (int2*)take(sizeof(int2) * (cta_map.size() + 1));
-  int* small_dev = (int*)take(sizeof(int) * (small_ids.size() + 1));
+  int* small_dev = (int*)take(sizeof(int) * (small_ids.size() + tiny_ids.size() + 1));
+  int* tiny_dev = small_dev + small_ids.size();
   double* partial = (double*)take(sizeof(double) * P);
   int* counters = (int*)take(sizeof(int) * 64);
   double* xs_dev = (double*)take(sizeof(double) * (size_t)xs_elems);
@@ -668,6 +808,14 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
     CB2_CUDA(ctx, cudaMemcpyAsync(map_dev, cta_map.data(), sizeof(int2) * cta_map.size(), cudaMemcpyHostToDevice, ctx->stream));
   if (!small_ids.empty())
     CB2_CUDA(ctx, cudaMemcpyAsync(small_dev, small_ids.data(), sizeof(int) * small_ids.size(), cudaMemcpyHostToDevice, ctx->stream));
+  const bool all_tiny = (int)tiny_ids.size() == P;   // then the kernel writes the bandwidths itself and nothing else is launched
+  if (!tiny_ids.empty()) {
+    CB2_CUDA(ctx, cudaMemcpyAsync(tiny_dev, tiny_ids.data(), sizeof(int) * tiny_ids.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (f64) loo_tiny_kernel<double><<<(int)tiny_ids.size(), kThreads, 0, ctx->stream>>>(probs_dev, tiny_dev, st_dev, all_tiny ? sigma_out_dev : nullptr);
+    else loo_tiny_kernel<float><<<(int)tiny_ids.size(), kThreads, 0, ctx->stream>>>(probs_dev, tiny_dev, st_dev, all_tiny ? sigma_out_dev : nullptr);
+    CB2_CHECK_LAUNCH(ctx, "loo_tiny_kernel");
+    if (all_tiny) return CB2_OK;
+  }
   CB2_CUDA(ctx, cudaMemsetAsync(counters, 0, sizeof(int) * 64, ctx->stream));
   if (!small_ids.empty()) {
     // few problems of a few hundred points (one sweep of a small graph): a cluster of CTAs per problem, for latency; many

@@ -63,9 +63,6 @@ __host__ __device__ inline int node_of(int N, int l, int p) {
 #ifndef CB2_GIBBS_TC
 #define CB2_GIBBS_TC 1
 #endif
-#ifndef CB2_GROUP_OPT
-#define CB2_GROUP_OPT 0
-#endif
 #ifndef CB2_COARSE_RSQ
 #define CB2_COARSE_RSQ 1   // coarse levels of the packed FP32 d = 6 loops: 2 MUFU.RSQ + 1 MUFU.EX2 per candidate (gibbs.cuh)
 #endif
@@ -127,6 +124,35 @@ __device__ __forceinline__ bool key_less(unsigned long long oa, uint32_t ta, uns
 #else
 #define TREE_T(slot) do { } while (0)
 #endif
+
+// tensor-core leaf path: feature tiles (see kTcTile) of one message, built from the stored FP32 leaf records
+template <typename T>
+__device__ __forceinline__ void write_feature_tiles(T* __restrict__ feat_base, const T* __restrict__ rec, int N, int RECL, int tid, int nthr) {
+  float* feat = reinterpret_cast<float*>(feat_base);
+  const int npad = (N + kTcTile - 1) / kTcTile * kTcTile;
+  for (int p = tid; p < npad; p += nthr) {
+    double f[16];
+    if (p < N) {
+      for (int i = 0; i < 6; ++i) {
+        const double xf = (double)(float)rec[(size_t)p * RECL + i];
+        f[i] = xf * xf; f[6 + i] = xf;
+      }
+      f[12] = 1.0; f[13] = (double)(float)rec[(size_t)p * RECL + 6]; f[14] = 0.0; f[15] = 0.0;
+    } else {  // padding leaf of the last tile: weight 2^-1e30 = 0
+      for (int k = 0; k < 16; ++k) f[k] = 0.0;
+      f[13] = -1e30;
+    }
+    float* tile = feat + (size_t)(p / kTcTile) * kTcTileFloats;
+    const int r = p % kTcTile;
+    for (int k = 0; k < 16; ++k) {
+      const float hi = tf32_rna((float)f[k]);
+      const float lo = tf32_rna((float)(f[k] - (double)hi));
+      const int off = (r >> 3) * 128 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3);
+      tile[off] = hi;
+      tile[kTcTile * 16 + off] = lo;
+    }
+  }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kTreeThreads, 2)
@@ -336,32 +362,7 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
       for (int i = d; i < RECL; ++i) rec[(size_t)p * RECL + i] = T(0);
       rec[(size_t)p * RECL + d] = (T)(wt > 0 ? log2(wt) : -1e30);
     }
-    if (m.feat_off >= 0 && d == 6) {  // tensor-core leaf path: feature tiles (see kTcTile), built from the stored FP32 values
-      float* feat = reinterpret_cast<float*>(node_pool + m.feat_off);
-      const int npad = (N + kTcTile - 1) / kTcTile * kTcTile;
-      for (int p = tid; p < npad; p += nthr) {
-        double f[16];
-        if (p < N) {
-          for (int i = 0; i < 6; ++i) {
-            const double xf = (double)(float)rec[(size_t)p * RECL + i];
-            f[i] = xf * xf; f[6 + i] = xf;
-          }
-          f[12] = 1.0; f[13] = (double)(float)rec[(size_t)p * RECL + d]; f[14] = 0.0; f[15] = 0.0;
-        } else {  // padding leaf of the last tile: weight 2^-1e30 = 0
-          for (int k = 0; k < 16; ++k) f[k] = 0.0;
-          f[13] = -1e30;
-        }
-        float* tile = feat + (size_t)(p / kTcTile) * kTcTileFloats;
-        const int r = p % kTcTile;
-        for (int k = 0; k < 16; ++k) {
-          const float hi = tf32_rna((float)f[k]);
-          const float lo = tf32_rna((float)(f[k] - (double)hi));
-          const int off = (r >> 3) * 128 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3);
-          tile[off] = hi;
-          tile[kTcTile * 16 + off] = lo;
-        }
-      }
-    }
+    if (m.feat_off >= 0 && d == 6) write_feature_tiles<T>(node_pool + m.feat_off, rec, N, RECL, tid, nthr);
   }
   __syncthreads();
   TREE_T(4);
@@ -433,6 +434,184 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
     printf("tree prof (clk): range %lld fill %lld sort %lld perm %lld leafstat %lld upstat %lld final %lld\n", tprof[0], tprof[1], tprof[2],
            tprof[3], tprof[4], tprof[5], tprof[6]);
 #endif
+}
+
+// ---- trees of small messages (N <= kTreeSmallN: the 100 .. 256 particles of an IIF solve) ---------------------------------------
+// The general kernel above is ~10^4 instructions of straight-line code per level, all of it executed once per level by a CTA
+// that holds 100 points: 80 us, most of it instruction fetch and dependent global round trips.  This kernel is the same
+// algorithm written for latency: one thread per point, points / permutation / statistics in shared memory, loops over the
+// coordinates not unrolled, the order inside the nodes by counting ranks (a 100-element node is 100 compares per thread) instead of
+// a bitonic network.  Same total order (node, value, position), same arithmetic in the statistics: bit-identical output.
+constexpr int kTreeSmallN = 256;
+template <typename T>
+__global__ void __launch_bounds__(kTreeSmallN)
+tree_build_small_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ int_pool, T* __restrict__ node_pool,
+                        double* __restrict__ stat_scratch, size_t stat_stride, uint32_t circ_mask) {
+  extern __shared__ __align__(16) unsigned char smem_small[];
+  const DensMeta m = metas[blockIdx.x];
+  const int N = m.N, depth = m.depth, tid = threadIdx.x;
+  const int nd = 2 * d + 1, RECN = recn_of(d), RECL = recl_of(d);
+  const int nstat = ((1 << depth) - 1 + N) * nd;
+  double* spts = reinterpret_cast<double*>(smem_small);                 // [N][d]
+  double* sstat = spts + (size_t)N * d;                                  // per level: [cnt][mean d, var d, weight]
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(sstat + nstat);  // [N] split coordinate of the point at a position
+  double* ext = reinterpret_cast<double*>(key + N);                      // [nodes of a level <= kTreeSmallN / 2][d]: coordinate ranges
+  int* perm = reinterpret_cast<int*>(ext + (kTreeSmallN / 2) * CB2_MAX_DIM);  // [N]
+  unsigned char* seg_dim = reinterpret_cast<unsigned char*>(perm + N);   // [2^(depth-1)]
+  __shared__ double s_red[kTreeSmallN / 32];
+  __shared__ double s_rng[(kTreeSmallN / 32) * CB2_MAX_DIM * 2];
+  for (int q = tid; q < N * d; q += kTreeSmallN) spts[q] = m.pts[q];
+  if (tid < N) perm[tid] = tid;
+  __syncthreads();
+  for (int l = 0; l < depth; ++l) {
+    const int cnt = 1 << l;
+    // split coordinate of every node: thread (node, coordinate) scans the node's points
+    for (int t = tid; t < cnt * d; t += kTreeSmallN) {
+      const int k = t / d, i = t - k * d;
+      int lo, n;
+      node_range(N, l, k, lo, n);
+      double mn = 1e300, mx = -1e300;
+#pragma unroll 4
+      for (int p = lo; p < lo + n; ++p) {
+        const double v = spts[perm[p] * d + i];
+        mn = fmin(mn, v); mx = fmax(mx, v);
+      }
+      ext[t] = mx - mn;
+    }
+    __syncthreads();
+    for (int k = tid; k < cnt; k += kTreeSmallN) {
+      int best = 0;
+      double bestr = -1.0;
+      for (int i = 0; i < d; ++i) {
+        const double r = ext[k * d + i];
+        if (r > bestr) { bestr = r; best = i; }
+      }
+      seg_dim[k] = (unsigned char)best;
+    }
+    __syncthreads();
+    int lo = 0, n = 0, val = 0;
+    if (tid < N) {
+      const int k = node_of(N, l, tid);
+      node_range(N, l, k, lo, n);
+      val = perm[tid];
+      key[tid] = ordered_bits(spts[val * d + seg_dim[k]]);
+    }
+    __syncthreads();
+    if (tid < N) {
+      const unsigned long long mine = key[tid];
+      int rank = 0;
+#pragma unroll 4
+      for (int q = lo; q < lo + n; ++q) {
+        const unsigned long long o = key[q];
+        rank += (o < mine || (o == mine && q < tid)) ? 1 : 0;
+      }
+      perm[lo + rank] = val;   // every position of the node is written exactly once; `val` was read before the barrier
+    }
+    __syncthreads();
+  }
+  // ---- statistics, bottom-up in FP64 (same arithmetic as tree_build_kernel)
+  double wloc = (m.w && tid < N) ? m.w[tid] : 0.0;
+  wloc = warp_sum(wloc);
+  if ((tid & 31) == 0) s_red[tid >> 5] = wloc;
+  __syncthreads();
+  double wsum = 0;
+  for (int w = 0; w < kTreeSmallN / 32; ++w) wsum += s_red[w];
+  auto lvl_off = [&](int l) { return l < depth ? ((1 << l) - 1) : ((1 << depth) - 1); };
+  double cmn[CB2_MAX_DIM], cmx[CB2_MAX_DIM];
+#pragma unroll
+  for (int i = 0; i < CB2_MAX_DIM; ++i) { cmn[i] = 1e300; cmx[i] = -1e300; }
+  auto centre = [&](int i) { return (sizeof(T) == 4 || !(circ_mask >> i & 1)) ? m.center[i] : 0.0; };
+  {
+    double* sl = sstat + (size_t)lvl_off(depth) * nd;
+    T* rec = node_pool + m.rec_off[depth];
+    if (tid < N) {
+      const int p = tid, idx = perm[p];
+      const double wt = m.w ? m.w[idx] / wsum : 1.0 / N;
+#pragma unroll
+      for (int i = 0; i < CB2_MAX_DIM; ++i) {
+        if (i >= d) break;
+        const double v = spts[idx * d + i];
+        sl[p * nd + i] = v;
+        sl[p * nd + d + i] = m.bw[i] * m.bw[i];
+        const double c = centre(i);
+        const double rv = (circ_mask >> i & 1) ? wrap_pi(v - c) : v - c;
+        rec[(size_t)p * RECL + i] = (T)rv;
+        if (circ_mask >> i & 1) { cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv); }
+      }
+      sl[p * nd + 2 * d] = wt;
+      for (int i = d; i < RECL; ++i) rec[(size_t)p * RECL + i] = T(0);
+      rec[(size_t)p * RECL + d] = (T)(wt > 0 ? log2(wt) : -1e30);
+    }
+    if (m.feat_off >= 0 && d == 6) {
+      __syncthreads();  // the feature tiles read the leaf records back
+      write_feature_tiles<T>(node_pool + m.feat_off, rec, N, RECL, tid, kTreeSmallN);
+    }
+  }
+  __syncthreads();
+  for (int l = depth - 1; l >= 0; --l) {
+    const int cnt = 1 << l;
+    double* sl = sstat + (size_t)lvl_off(l) * nd;
+    const double* sc = sstat + (size_t)lvl_off(l + 1) * nd;
+    T* rec = node_pool + m.rec_off[l];
+    for (int k = tid; k < cnt; k += kTreeSmallN) {
+      int c0, nch;
+      if (l + 1 == depth) { node_range(N, l, k, c0, nch); } else { c0 = 2 * k; nch = 2; }
+      const double* r0 = sc + (size_t)c0 * nd;
+      const double* r1 = r0 + (nch > 1 ? nd : 0);
+      const double w0 = r0[2 * d], w1 = nch > 1 ? r1[2 * d] : 0.0;
+      const double ws = w0 + w1;
+      sl[k * nd + 2 * d] = ws;
+#pragma unroll
+      for (int i = 0; i < CB2_MAX_DIM; ++i) {
+        if (i >= d) break;
+        const double mu0 = r0[i], va0 = r0[d + i], mu1 = r1[i], va1 = r1[d + i];
+        double mm = w0 * mu0;
+        mm += w1 * mu1;
+        mm /= ws;
+        const double d0 = mu0 - mm, d1 = mu1 - mm;
+        double v = w0 * (va0 + d0 * d0);
+        v += w1 * (va1 + d1 * d1);
+        v /= ws;
+        sl[k * nd + i] = mm;
+        sl[k * nd + d + i] = v;
+        const double c = centre(i);
+        const double rv = (circ_mask >> i & 1) ? wrap_pi(mm - c) : mm - c;
+        rec[(size_t)k * RECN + i] = (T)rv;
+        if (circ_mask >> i & 1) { cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv); }
+        rec[(size_t)k * RECN + d + i] = (T)v;
+      }
+      for (int i = 2 * d; i < RECN; ++i) rec[(size_t)k * RECN + i] = T(0);
+      rec[(size_t)k * RECN + 2 * d] = (T)(ws > 0 ? log2(ws) : -1e30);
+    }
+    __syncthreads();
+  }
+  // ranges of the stored circular coordinates, permutation and statistics to their global places
+  double* sbase = stat_scratch + (size_t)blockIdx.x * stat_stride;
+#pragma unroll
+  for (int i = 0; i < CB2_MAX_DIM; ++i) {
+    if (i >= d) break;
+    double a = cmn[i], b = cmx[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = fmin(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if ((tid & 31) == 0) { s_rng[((tid >> 5) * CB2_MAX_DIM + i) * 2] = a; s_rng[((tid >> 5) * CB2_MAX_DIM + i) * 2 + 1] = b; }
+  }
+  __syncthreads();
+  if (tid < d) {
+    double a = 1e300, b = -1e300;
+    for (int w = 0; w < kTreeSmallN / 32; ++w) { a = fmin(a, s_rng[(w * CB2_MAX_DIM + tid) * 2]); b = fmax(b, s_rng[(w * CB2_MAX_DIM + tid) * 2 + 1]); }
+    sbase[stat_stride - 16 + tid] = a;
+    sbase[stat_stride - 8 + tid] = b;
+  }
+  int* perm_g = int_pool + m.perm_off;
+  if (tid < N) perm_g[tid] = perm[tid];
+  for (int q = tid; q < nstat; q += kTreeSmallN) sbase[q] = sstat[q];
+}
+__host__ inline size_t tree_small_smem(int maxN, int max_nodes, int d) {
+  return sizeof(double) * ((size_t)maxN * d + (size_t)max_nodes * (2 * d + 1) + (size_t)(kTreeSmallN / 2) * CB2_MAX_DIM) + 8 * (size_t)maxN + 4 * (size_t)maxN +
+         (size_t)kTreeSmallN + 64;
 }
 
 // metas[i].bw[0..d) = *ptrs[i]: bandwidths that live on the device go straight into the message table (no host round trip)
@@ -675,20 +854,34 @@ int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const
 
   CB2_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   size_t tree_smem = (size_t)pl.maxP2 * 13 + 64;
-  cudaError_t e = cudaFuncSetAttribute(tree_build_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem);
-  if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "tree smem attribute (%zu bytes): %s", tree_smem, cudaGetErrorString(e));
+  int tree_maxN = 0;
+  for (const DensMeta& m : pl.metas) tree_maxN = std::max(tree_maxN, m.N);
+  const size_t small_smem = tree_small_smem(tree_maxN, pl.max_nodes, d);
+  // launches whose messages all hold at most kTreeSmallN points take the latency-oriented kernel
+  const bool tree_small = tree_maxN <= kTreeSmallN && small_smem <= 160 * 1024 && !getenv("CB2_NO_TREE_SMALL");
+  cudaError_t e = tree_small ? cudaFuncSetAttribute(tree_build_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem)
+                             : cudaFuncSetAttribute(tree_build_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem);
+  if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "tree smem attribute (%zu bytes): %s", tree_small ? small_smem : tree_smem, cudaGetErrorString(e));
   if (chunks && !chunks->msg_end.empty()) {  // build the trees of every chunk as soon as its arrays have landed
     int m0 = 0;
     for (size_t c = 0; c < chunks->msg_end.size(); ++c) {
       const int m1 = chunks->msg_end[c];
       CB2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, chunks->ev[c], 0));
       if (m1 > m0) {
+        if (tree_small)
+          tree_build_small_kernel<T><<<m1 - m0, kTreeSmallN, small_smem, ctx->stream>>>(lay.metas + m0, d, lay.int_pool, (T*)lay.node_pool,
+                                                                                         lay.stat + (size_t)m0 * stat_stride, stat_stride, mask);
+        else
         tree_build_kernel<T><<<m1 - m0, kTreeThreads, tree_smem, ctx->stream>>>(lay.metas + m0, d, lay.int_pool, (T*)lay.node_pool,
                                                                                  lay.stat + (size_t)m0 * stat_stride, stat_stride, mask);
         CB2_CHECK_LAUNCH(ctx, "tree_build_kernel");
       }
       m0 = m1;
     }
+  } else if (tree_small) {
+    tree_build_small_kernel<T><<<(int)pl.metas.size(), kTreeSmallN, small_smem, ctx->stream>>>(lay.metas, d, lay.int_pool, (T*)lay.node_pool,
+                                                                                                  lay.stat, stat_stride, mask);
+    CB2_CHECK_LAUNCH(ctx, "tree_build_small_kernel");
   } else {
     tree_build_kernel<T><<<(int)pl.metas.size(), kTreeThreads, tree_smem, ctx->stream>>>(lay.metas, d, lay.int_pool, (T*)lay.node_pool,
                                                                                             lay.stat, stat_stride, mask);

@@ -629,3 +629,59 @@ def test_bandwidth_cluster_kernel_matches_single_cta_kernel_and_oracle(cb, ctx, 
         assert np.allclose(got, single, rtol=1e-9) and np.allclose(got, want, rtol=1e-6)
     else:
         assert np.allclose(got, single, rtol=2e-2) and np.allclose(got, want, rtol=3e-2)
+
+
+@pytest.mark.parametrize("N", [2, 3, 31, 32, 33, 64, 65, 96, 97, 100, 128])
+def test_bandwidth_tiny_kernel_matches_single_cta_kernel_and_oracle(cb, ctx, N, monkeypatch):
+    """N <= 128 (the solver's default 100 particles) takes loo_tiny_kernel: (row, column-segment) thread layout, per-thread copies
+    of the search state, bandwidths written straight to the output.  Same golden-section path as the general single-CTA kernel."""
+    rng = np.random.default_rng(1000 + N)
+    pts = np.c_[rng.normal(size=(N, 2)) * [3.0, 0.5] + (rng.uniform(size=(N, 1)) < 0.4) * [6.0, 0.0], rng.normal(size=N) * 0.4 + 3.0]
+    pts[:, 2] = (pts[:, 2] + np.pi) % (2 * np.pi) - np.pi   # heading straddles the +-pi cut: the wrapped loop
+    launches = ctx.kernel_launches
+    got = cb.kde_bandwidth(pts, "Pose2", ctx=ctx)
+    n_tiny = ctx.kernel_launches - launches
+    monkeypatch.setenv("CB2_NO_LOO_TINY", "1")
+    launches = ctx.kernel_launches
+    single = cb.kde_bandwidth(pts, "Pose2", ctx=ctx)
+    assert ctx.kernel_launches - launches == n_tiny + 1   # the general path also launches loo_collect_kernel
+    monkeypatch.delenv("CB2_NO_LOO_TINY")
+    want = oracle.kde_bw_loo(pts, circular=[0, 0, 1])
+    if ctx.precision == "fp64":
+        assert np.allclose(got, single, rtol=1e-9) and np.allclose(got, want, rtol=1e-6)
+    else:
+        assert np.allclose(got, single, rtol=2e-2) and np.allclose(got, want, rtol=3e-2)
+    # a batch that mixes tiny and larger densities goes through both kernels and the collect launch
+    big = rng.normal(size=(300, 3))
+    both = cb.kde_bandwidth_batch([pts, big], "Pose2", ctx=ctx)
+    assert np.allclose(both[0], got, rtol=1e-12) and np.allclose(both[1], cb.kde_bandwidth(big, "Pose2", ctx=ctx), rtol=1e-12)
+
+
+@pytest.mark.parametrize("N,d", [(2, 2), (3, 3), (100, 3), (100, 2), (129, 6), (255, 3), (256, 6), (200, 5)])
+def test_small_tree_build_equals_general_tree_build(cb, ctx, N, d, monkeypatch):
+    """Messages of N <= 256 points build their tree in shared memory (rank ordering inside the nodes instead of the bitonic
+    network): same permutation and statistics as the general kernel, bit for bit, and the same tree as the oracle."""
+    rng = np.random.default_rng(7 * N + d)
+    pts = rng.normal(size=(N, d)) * rng.uniform(0.3, 4.0, size=d)
+    pts[: N // 3] = pts[N // 3: 2 * (N // 3)]      # duplicated points: ties are broken by position
+    bw = rng.uniform(0.05, 0.3, size=d)
+    w = rng.uniform(0.5, 1.5, size=N) if N % 2 else None
+    depth, perm, levels = cb.tree_levels(pts, bw, w, ctx=ctx)
+    monkeypatch.setenv("CB2_NO_TREE_SMALL", "1")
+    depth2, perm2, levels2 = cb.tree_levels(pts, bw, w, ctx=ctx)
+    monkeypatch.delenv("CB2_NO_TREE_SMALL")
+    assert depth == depth2 and np.array_equal(perm, perm2)
+    for a, b in zip(levels, levels2):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    if d <= 6:
+        t = oracle.Tree(pts, bw, w)
+        assert depth == t.depth and np.array_equal(perm, t.perm)
+        assert np.allclose(levels[0][0], t.mean[0], rtol=1e-12, atol=1e-12)
+    if d <= 6:   # and a product through it: identical chains either way
+        dens = [(pts, bw), (pts[::-1] * 1.01 + 0.05, bw * 1.3)]
+        a = cb.product_points(dens, (0,) * d, 300, seed=4, ctx=ctx)
+        monkeypatch.setenv("CB2_NO_TREE_SMALL", "1")
+        b = cb.product_points(dens, (0,) * d, 300, seed=4, ctx=ctx)
+        monkeypatch.delenv("CB2_NO_TREE_SMALL")
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
