@@ -471,12 +471,8 @@ def approxConvBatch(convs, seed=0, ctx=None):
         d.n_aux = 0 if aux is None else aux.shape[0]
         d.src = None if src is None else src.ctypes.data
         d.aux = None if aux is None else aux.ctypes.data
-        mean = np.resize(np.asarray(c["mean"], dtype=np.float64), nz)
-        chol = np.asarray(c["chol"], dtype=np.float64).reshape(nz * nz)
-        for i in range(nz):
-            d.mean[i] = mean[i]
-        for i in range(nz * nz):
-            d.chol[i] = chol[i]
+        d.mean[:nz] = np.resize(np.asarray(c["mean"], dtype=np.float64), nz).tolist()
+        d.chol[:nz * nz] = np.asarray(c["chol"], dtype=np.float64).reshape(nz * nz).tolist()
         d.out = out.ctypes.data
     ctx.check(_capi.lib().cb2_approx_conv_batch(ctx._h, descs, B, int(seed)))
     return outs

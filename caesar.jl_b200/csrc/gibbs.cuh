@@ -41,6 +41,7 @@ struct GibbsArgs {
 template <typename T> struct SMeta {
   uint32_t rec_off32[kMaxLev + 1];  // level record offsets in units of 32 elements (validate_and_plan aligns them)
   uint32_t feat_off32;              // leaf feature tiles of the tensor-core path (units of 32 elements) or 0xffffffff
+  uint32_t srec32;                  // SMALL kernels: where this message's records (all levels) sit in shared memory (units of 32 elements)
   long long perm_off;
   T bw2[CB2_MAX_DIM];
   float cmin[CB2_MAX_DIM], cmax[CB2_MAX_DIM];  // range of the stored circular coordinates over all levels
@@ -102,6 +103,13 @@ template <typename T, int DIM> struct ChainsPerThread { static constexpr int val
 // bytes of one TMA stage: 8 KB of FP32 records (twice that in FP64), halved when the CTA has half the threads
 template <typename T, int DIM> __host__ __device__ constexpr int gibbs_tile_bytes() {
   return kTileBytesF32 * (int)(sizeof(T) / 4) / ChainsPerThread<T, DIM>::value;
+}
+
+// dynamic shared memory of the regular kernel: two record stages, chunk sums, selected nodes, barriers, message table (+ the
+// tensor-core pass's coefficient rows, MMA barriers and TMEM slot); SMALL kernels append their record staging area behind it
+template <typename T, int DIM> __host__ __device__ constexpr size_t gibbs_smem_bytes_c() {
+  return 2 * (size_t)gibbs_tile_bytes<T, DIM>() + sizeof(T) * kNCH * kS + sizeof(ind_t) * CB2_MAX_DENS * kS + 16 +
+         sizeof(SMeta<T>) * CB2_MAX_DENS + 64 + ((CB2_GIBBS_TC && DIM == 6 && sizeof(T) == 4) ? (size_t)(16384 + 128 + 64) : 0);
 }
 
 // ---- packed FP32 pairs (fma.rn.f32x2 -> SASS FFMA2 on sm_100a): one issue slot for two lanes of arithmetic; the
@@ -395,7 +403,7 @@ __device__ __forceinline__ void tile_pass(const T* __restrict__ tb, int nt, int 
 }
 
 // pass 2: re-score the selected chunk from global memory until the cumulative sum crosses the target
-template <typename T, int DIM, int MODE, bool PACK>
+template <typename T, int DIM, int MODE, bool PACK, bool SHARED = false>
 __device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, int z1, const ChainConst<T, DIM>& cc,
                                           const PackedConst& pc, uint32_t circ, T m, T cum, T tgt) {
   constexpr int REC = RecLen<DIM, MODE>::value;
@@ -411,7 +419,7 @@ __device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, in
     for (int g = 0; g < PR; ++g) {
       const int zz = min(z + g, z1 - 1);
       RecR<T, REC, PACK> rec;
-      load_recr<false>(lrec + (size_t)zz * REC, rec);
+      load_recr<SHARED>(lrec + (size_t)zz * REC, rec);
       T mul;
       const T e = score_regs<T, DIM, MODE, PACK>(rec, cc, pc, circ, nm, mul);
       p[g] = fast_exp2(e) * mul;
@@ -434,7 +442,7 @@ __device__ __forceinline__ int chunk_pick(const T* __restrict__ lrec, int z0, in
 }
 
 // Gaussian product of the currently selected nodes of all messages except `skip` (skip = -1: all)
-template <typename T, int DIM>
+template <typename T, int DIM, bool SMALL = false>
 __device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta<T>* __restrict__ sm, int D,
                                         const ind_t* __restrict__ ind_s, int tid, int step, int skip, uint32_t circ,
                                         T (&M)[DIM], T (&C)[DIM]) {
@@ -450,12 +458,14 @@ __device__ __forceinline__ void combine(const T* __restrict__ pool, const SMeta<
     const int lev = min(step, dm.depth);
     const int node = ind_s[k * kS + tid];
     T mu[DIM], var[DIM];
+    // SMALL: `pool` is the shared-memory staging area and the message's levels sit at srec32 in the order of the node pool
+    const size_t lbase = SMALL ? (size_t)dm.srec32 * 32 + (dm.rec_off(lev) - dm.rec_off(0)) : dm.rec_off(lev);
     if (lev == dm.depth) {
-      const VecRec<T, RECL> r = *reinterpret_cast<const VecRec<T, RECL>*>(pool + dm.rec_off(lev) + (size_t)node * RECL);
+      const VecRec<T, RECL> r = *reinterpret_cast<const VecRec<T, RECL>*>(pool + lbase + (size_t)node * RECL);
 #pragma unroll
       for (int i = 0; i < DIM; ++i) { mu[i] = r.v[i]; var[i] = dm.bw2[i]; }
     } else {
-      const VecRec<T, RECN> r = *reinterpret_cast<const VecRec<T, RECN>*>(pool + dm.rec_off(lev) + (size_t)node * RECN);
+      const VecRec<T, RECN> r = *reinterpret_cast<const VecRec<T, RECN>*>(pool + lbase + (size_t)node * RECN);
 #pragma unroll
       for (int i = 0; i < DIM; ++i) { mu[i] = r.v[i]; var[i] = r.v[DIM + i]; }
     }
@@ -738,8 +748,13 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
 #define GIBBS_T(slot) do { } while (0)
 #endif
 
-template <typename T, int DIM, uint32_t CIRC>
-__global__ void __launch_bounds__(kS / ChainsPerThread<T, DIM>::value, ChainsPerThread<T, DIM>::value == 2 ? 7 : (sizeof(T) == 4 ? CB2_GIBBS_CTAS : 4))
+// SMALL (small products: every message of the batch has a few hundred points at most, e.g. the 100 particles of an IIF solve): the
+// records of ALL levels of the product's messages are staged in shared memory once, the scoring passes read them in place (no bulk
+// copy to wait for, no CTA barrier per tile), the leave-one-out gathers and the second pass read shared memory instead of L2.  A
+// (level, sweep, message) phase of a 100-point product costs ~1.7 us otherwise, almost all of it memory latency.  Same arithmetic
+// in the same order: bit-identical chains.
+template <typename T, int DIM, uint32_t CIRC, bool SMALL = false>
+__global__ void __launch_bounds__(kS / ChainsPerThread<T, DIM>::value, SMALL ? 1 : (ChainsPerThread<T, DIM>::value == 2 ? 7 : (sizeof(T) == 4 ? CB2_GIBBS_CTAS : 4)))
 gibbs_kernel(const GibbsArgs a) {
   constexpr int RECN = (2 * DIM + 1 + 3) / 4 * 4, RECL = (DIM + 1 + 3) / 4 * 4;
   constexpr int TILE_BYTES = gibbs_tile_bytes<T, DIM>();
@@ -826,6 +841,34 @@ gibbs_kernel(const GibbsArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     tc.tmem = *tmem_slot;
   }
+  // SMALL: every level of every message into shared memory (behind the regular arrays; launch_gibbs_inst sizes the allocation)
+  const T* srec = nullptr;
+  if constexpr (SMALL) {
+    T* stage = reinterpret_cast<T*>(smem_raw + ((gibbs_smem_bytes_c<T, DIM>() + 127) & ~(size_t)127));
+    auto block_elems = [&](const SMeta<T>& m) {  // levels are laid out back to back, each padded to 32 elements (validate_and_plan)
+      return (uint32_t)(m.rec_off(m.depth) - m.rec_off(0)) + (uint32_t)((m.N * RECL + 31) & ~31);
+    };
+    if (tid == 0) {
+      uint32_t o = 0;
+      for (int k = 0; k < D; ++k) { sm[k].srec32 = o >> 5; o += block_elems(sm[k]); }
+    }
+    __syncthreads();
+    constexpr int V = 16 / (int)sizeof(T);
+    for (int k = 0; k < D; ++k) {
+      const uint4* src = reinterpret_cast<const uint4*>(pool + sm[k].rec_off(0));
+      uint4* dst = reinterpret_cast<uint4*>(stage + (size_t)sm[k].srec32 * 32);
+      const int nv = (int)(block_elems(sm[k]) / V);
+      for (int e = tid; e < nv; e += NT) dst[e] = __ldg(src + e);
+    }
+    __syncthreads();
+    srec = stage;
+  }
+  // records of level `lev` of message k: staged copy or node pool
+  auto level_rec = [&](int k, int lev) -> const T* {
+    if constexpr (SMALL) return srec + (size_t)sm[k].srec32 * 32 + (sm[k].rec_off(lev) - sm[k].rec_off(0));
+    else return pool + sm[k].rec_off(lev);
+  };
+  const T* const cpool = SMALL ? srec : pool;   // what combine() indexes
   uint32_t use0 = 0, use1 = 0;  // completed uses of each tile buffer (phase parity)
 #ifdef CB2_GIBBS_PROF
   long long gprof[6] = {0, 0, 0, 0, 0, 0}, glast = clock64();
@@ -840,7 +883,7 @@ gibbs_kernel(const GibbsArgs a) {
       const int depth = sm[k].depth;
       if (step <= depth) {
         const bool toleaf = step == depth;
-        const T* crec = pool + sm[k].rec_off(step);
+        const T* crec = level_rec(k, step);
         const int crl = toleaf ? RECL : RECN, cwo = toleaf ? DIM : 2 * DIM;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -872,9 +915,9 @@ gibbs_kernel(const GibbsArgs a) {
         const bool leaf = lev == dj.depth;
         const int cnt = level_count(dj.N, dj.depth, lev);
         const bool cw = dj.uniform != 0 && (dj.N & (dj.N - 1)) == 0;  // every node of a coarse level weighs the same
-        const T* lrec = pool + dj.rec_off(lev);
+        const T* lrec = level_rec(j, lev);
         const int rec = leaf ? RECL : RECN;
-        const int TN = leaf ? TN_LEAF : TN_NODE;
+        const int TN = SMALL ? cnt : (leaf ? TN_LEAF : TN_NODE);   // SMALL: the whole level is one "tile", read in place
         const int ntiles = (cnt + TN - 1) / TN;
         int CH = kG;
         while (CH * kNCH < cnt) CH <<= 1;
@@ -886,7 +929,7 @@ gibbs_kernel(const GibbsArgs a) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           T M[DIM], C[DIM];
-          if (!single) combine<T, DIM>(pool, sm, D, ind_s, col[r], step, j, circ, M, C);
+          if (!single) combine<T, DIM, SMALL>(cpool, sm, D, ind_s, col[r], step, j, circ, M, C);
           // the wrap is a no-op for this chain if every stored coordinate of message j lies within pi of its mean
           if (circ != 0u && !single) {
 #pragma unroll
@@ -929,23 +972,25 @@ gibbs_kernel(const GibbsArgs a) {
             }
           }
         }
-        if (!done_tc && tid == 0) {
+        if (!SMALL && !done_tc && tid == 0) {
           uint32_t bytes = (uint32_t)(min(TN, cnt) * rec * (int)sizeof(T));
           mbar_expect_tx(&bars[0], bytes);
           tma_load_1d(tile[0], lrec, bytes, &bars[0]);
         }
         for (int t = 0; t < (done_tc ? 0 : ntiles); ++t) {
           const int b = t & 1;
-          if (tid == 0 && t + 1 < ntiles) {
-            int n1 = min(TN, cnt - (t + 1) * TN);
-            uint32_t bytes = (uint32_t)(n1 * rec * (int)sizeof(T));
-            mbar_expect_tx(&bars[b ^ 1], bytes);
-            tma_load_1d(tile[b ^ 1], lrec + (size_t)(t + 1) * TN * rec, bytes, &bars[b ^ 1]);
+          if constexpr (!SMALL) {
+            if (tid == 0 && t + 1 < ntiles) {
+              int n1 = min(TN, cnt - (t + 1) * TN);
+              uint32_t bytes = (uint32_t)(n1 * rec * (int)sizeof(T));
+              mbar_expect_tx(&bars[b ^ 1], bytes);
+              tma_load_1d(tile[b ^ 1], lrec + (size_t)(t + 1) * TN * rec, bytes, &bars[b ^ 1]);
+            }
+            mbar_wait(&bars[b], (b ? use1 : use0) & 1);
+            if (b) ++use1; else ++use0;
           }
-          mbar_wait(&bars[b], (b ? use1 : use0) & 1);
-          if (b) ++use1; else ++use0;
           const int nt = min(TN, cnt - t * TN);
-          const T* tb = reinterpret_cast<const T*>(smem_raw + b * TILE_BYTES);
+          const T* tb = SMALL ? lrec : reinterpret_cast<const T*>(smem_raw + b * TILE_BYTES);
           // with the tensor-core leaf pass compiled in, the packed leaf loops would only serve warp-flat passes of CTAs that are
           // not flat as a whole: they take the wrapped loops instead and the kernel stays smaller (instruction cache)
           if (flat && !(kTC && leaf)) {  // Euclidean arithmetic on every coordinate: same values as the wrapped form, fewer instructions
@@ -962,7 +1007,7 @@ gibbs_kernel(const GibbsArgs a) {
             else if (!dj.uniform) tile_pass<T, DIM, 1, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx, thr);
             else tile_pass<T, DIM, 2, false, R>(tb, nt, t * TN, CH, cc, pc, circ, chunk, tid, m, csum, cidx, thr);
           }
-          __syncthreads();  // everyone is done with tile[b] before it is refilled
+          if constexpr (!SMALL) __syncthreads();  // everyone is done with tile[b] before it is refilled
         }
         if (cnt & (CH - 1)) {
 #pragma unroll
@@ -993,21 +1038,21 @@ gibbs_kernel(const GibbsArgs a) {
           // pass 2 must reproduce the scores of pass 1 bit for bit, so it takes the same (packed or wrapped) scorer
           int pick;
           if (flat && !(kTC && leaf)) {
-            if (!leaf) pick = (kPack && cw) ? chunk_pick<T, DIM, 3, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
-                                            : chunk_pick<T, DIM, 0, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
+            if (!leaf) pick = (kPack && cw) ? chunk_pick<T, DIM, 3, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
+                                            : chunk_pick<T, DIM, 0, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
             else if constexpr (!kTC) {
-              pick = !dj.uniform ? chunk_pick<T, DIM, 1, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
-                                 : chunk_pick<T, DIM, 2, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
+              pick = !dj.uniform ? chunk_pick<T, DIM, 1, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
+                                 : chunk_pick<T, DIM, 2, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
             } else pick = z0;
           } else if (kTC && done_tc) {  // tensor-core leaf pass: the CTA is wrap-free, the packed FP32 leaf scorer applies
             if constexpr (kTC) {
-              pick = !dj.uniform ? chunk_pick<T, DIM, 1, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
-                                 : chunk_pick<T, DIM, 2, kPack>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
+              pick = !dj.uniform ? chunk_pick<T, DIM, 1, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
+                                 : chunk_pick<T, DIM, 2, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
             } else pick = z0;
           } else {
-            pick = !leaf ? chunk_pick<T, DIM, 0, false>(lrec, z0, z1, cc[r], pc[r], circ, m[r], cum, tgt)
-                         : (!dj.uniform ? chunk_pick<T, DIM, 1, false>(lrec, z0, z1, cc[r], pc[r], circ, m[r], cum, tgt)
-                                        : chunk_pick<T, DIM, 2, false>(lrec, z0, z1, cc[r], pc[r], circ, m[r], cum, tgt));
+            pick = !leaf ? chunk_pick<T, DIM, 0, false, SMALL>(lrec, z0, z1, cc[r], pc[r], circ, m[r], cum, tgt)
+                         : (!dj.uniform ? chunk_pick<T, DIM, 1, false, SMALL>(lrec, z0, z1, cc[r], pc[r], circ, m[r], cum, tgt)
+                                        : chunk_pick<T, DIM, 2, false, SMALL>(lrec, z0, z1, cc[r], pc[r], circ, m[r], cum, tgt));
           }
           if (active[r]) ind_s[j * kS + col[r]] = (ind_t)pick;
           GIBBS_T(5);
@@ -1028,7 +1073,7 @@ gibbs_kernel(const GibbsArgs a) {
     if (!active[r]) continue;
     const int s = wk.s0 + col[r];
     T M[DIM], C[DIM];
-    combine<T, DIM>(pool, sm, D, ind_s, col[r], L, -1, circ, M, C);
+    combine<T, DIM, SMALL>(cpool, sm, D, ind_s, col[r], L, -1, circ, M, C);
     uint32_t rnd[4];
     double* out = prp->out;
 #pragma unroll
@@ -1053,8 +1098,4 @@ gibbs_kernel(const GibbsArgs a) {
   }
 }
 
-template <typename T, int DIM> size_t gibbs_smem_bytes() {
-  return 2 * (size_t)gibbs_tile_bytes<T, DIM>() + sizeof(T) * kNCH * kS + sizeof(ind_t) * CB2_MAX_DENS * kS + 16 +
-         sizeof(SMeta<T>) * CB2_MAX_DENS + 64 +
-         ((CB2_GIBBS_TC && DIM == 6 && sizeof(T) == 4) ? (size_t)(16384 + 128 + 64) : 0);  // coefficient rows, MMA barriers, TMEM slot
-}
+template <typename T, int DIM> size_t gibbs_smem_bytes() { return gibbs_smem_bytes_c<T, DIM>(); }

@@ -701,25 +701,32 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 #include "gibbs.cuh"
 
 
-template <typename T, int DIM, uint32_t CIRC>
-int launch_gibbs_inst(cb2_ctx* ctx, int nwork, const GibbsArgs& a) {
+template <typename T, int DIM, uint32_t CIRC, bool SMALL = false>
+int launch_gibbs_inst(cb2_ctx* ctx, int nwork, const GibbsArgs& a, size_t stage_bytes = 0) {
   size_t smem = gibbs_smem_bytes<T, DIM>();
-  cudaError_t e = cudaFuncSetAttribute(gibbs_kernel<T, DIM, CIRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (SMALL) smem = ((smem + 127) & ~(size_t)127) + stage_bytes;
+  cudaError_t e = cudaFuncSetAttribute(gibbs_kernel<T, DIM, CIRC, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(gibbs_kernel<T, DIM, CIRC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(gibbs_kernel<T, DIM, CIRC, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "gibbs smem attribute: %s", cudaGetErrorString(e));
-  gibbs_kernel<T, DIM, CIRC><<<nwork, kS / ChainsPerThread<T, DIM>::value, smem, ctx->stream>>>(a);
+  gibbs_kernel<T, DIM, CIRC, SMALL><<<nwork, kS / ChainsPerThread<T, DIM>::value, smem, ctx->stream>>>(a);
   CB2_CHECK_LAUNCH(ctx, "gibbs_kernel");
   return CB2_OK;
 }
 
+// stage_bytes > 0: every product of the batch is small enough to keep all levels of its messages in shared memory (the SMALL
+// kernels exist for the planar variable types an IIF solve at N ~ 100 spends its time on)
 template <typename T>
-int launch_gibbs(cb2_ctx* ctx, int d, uint32_t mask, int nwork, const GibbsArgs& a) {
+int launch_gibbs(cb2_ctx* ctx, int d, uint32_t mask, int nwork, const GibbsArgs& a, size_t stage_bytes) {
   // the common variable types get compile-time circular masks; anything else takes the run-time mask
 #ifdef CB2_FAST_BUILD  // experiment builds (bench/micro/build_variant.py): the headline instance only, seconds instead of minutes
   if (d == 6 && mask == 0x38u && sizeof(T) == 4) return launch_gibbs_inst<float, 6, 0x38u>(ctx, nwork, a);
   return cb2_fail(ctx, CB2_ERR_UNSUPPORTED, "CB2_FAST_BUILD carries the FP32 Pose3 product kernel only");
 #else
+  if (stage_bytes > 0) {
+    if (d == 2 && mask == 0) return launch_gibbs_inst<T, 2, 0u, true>(ctx, nwork, a, stage_bytes);   // Point2
+    if (d == 3 && mask == 4u) return launch_gibbs_inst<T, 3, 4u, true>(ctx, nwork, a, stage_bytes);  // Pose2
+  }
   if (d == 1 && mask == 0) return launch_gibbs_inst<T, 1, 0u>(ctx, nwork, a);
   if (d == 2 && mask == 0) return launch_gibbs_inst<T, 2, 0u>(ctx, nwork, a);            // Point2
   if (d == 3 && mask == 0) return launch_gibbs_inst<T, 3, 0u>(ctx, nwork, a);            // Point3
@@ -892,7 +899,20 @@ int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const
   ga.metas = lay.metas; ga.prods = lay.prods; ga.work = lay.work; ga.int_pool = lay.int_pool; ga.node_pool = lay.node_pool;
   ga.k0 = (uint32_t)seed; ga.k1 = (uint32_t)(seed >> 32); ga.circ_mask = mask; ga.level_down = ctx->level_down;
   ga.stat = lay.stat; ga.stat_stride = stat_stride;
-  int rc = launch_gibbs<T>(ctx, d, mask, (int)pl.work.size(), ga);
+  size_t stage_bytes = 0;   // largest per-product record block when every product of the batch qualifies for the SMALL kernels
+  if (((d == 2 && mask == 0) || (d == 3 && mask == 4u)) && !getenv("CB2_NO_GIBBS_SMALL")) {
+    const int RECL = recl_of(d);
+    for (const ProdDev& pd : pl.prods) {
+      size_t elems = 0;
+      for (int j = 0; j < pd.D; ++j) {
+        const DensMeta& m = pl.metas[pd.dens[j]];
+        elems += (size_t)(m.rec_off[m.depth] - m.rec_off[0]) + (size_t)(((size_t)m.N * RECL + 31) / 32 * 32);
+      }
+      stage_bytes = std::max(stage_bytes, elems * sizeof(T));
+    }
+    if (stage_bytes > 96 * 1024) stage_bytes = 0;
+  }
+  int rc = launch_gibbs<T>(ctx, d, mask, (int)pl.work.size(), ga, stage_bytes);
   if (rc) return rc;
   CB2_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
   if (lay_out) *lay_out = lay;

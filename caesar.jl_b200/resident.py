@@ -73,6 +73,27 @@ class DeviceBelief:
         return ManifoldKernelDensity(self.manifold, pts, bw)
 
 
+def download_beliefs(beliefs, ctx):
+    """DeviceBelief list -> ManifoldKernelDensity list with ONE device-to-host copy (the address range that holds them all; the
+    beliefs of a finished solve sit next to each other in the slab) instead of two synchronous copies per belief."""
+    from . import ManifoldKernelDensity
+    if not beliefs:
+        return []
+    spans = [(b.pts.ptr, b.N * b.d * 8) for b in beliefs] + [(b.bw_ptr, b.d * 8) for b in beliefs]
+    lo = min(p for p, _ in spans)
+    hi = max(p + n for p, n in spans)
+    if hi - lo > (64 << 20):   # scattered over a large range: not worth one big copy
+        return [b.to_host() for b in beliefs]
+    host = np.empty(hi - lo, dtype=np.uint8)
+    ctx.check(_capi.lib().cb2_download(ctx._h, ptr(host), C.c_void_p(lo), host.nbytes))
+    out = []
+    for b in beliefs:
+        pts = host[b.pts.ptr - lo: b.pts.ptr - lo + b.N * b.d * 8].view(np.float64).reshape(b.N, b.d).copy()
+        bw = host[b.bw_ptr - lo: b.bw_ptr - lo + b.d * 8].view(np.float64).copy()
+        out.append(ManifoldKernelDensity(b.manifold, pts, bw))
+    return out
+
+
 def upload_belief(mkd, slab, ctx):
     """Host ManifoldKernelDensity -> DeviceBelief (two stream-ordered copies)."""
     L = _capi.lib()
@@ -102,12 +123,9 @@ def approxConvBatch_dev(convs, slab, seed=0, ctx=None):
         d.n_aux = 0 if aux is None else aux.N
         d.src = None if src is None else src.ptr
         d.aux = None if aux is None else aux.ptr
-        mean = np.resize(np.asarray(c["mean"], dtype=np.float64), nz)
-        chol = np.asarray(c["chol"], dtype=np.float64).reshape(nz * nz)
-        for i in range(nz):
-            d.mean[i] = mean[i]
-        for i in range(nz * nz):
-            d.chol[i] = chol[i]
+        # (slice assignment fills a ctypes array in one call: the element loop cost more than the kernel it describes)
+        d.mean[:nz] = np.resize(np.asarray(c["mean"], dtype=np.float64), nz).tolist()
+        d.chol[:nz * nz] = np.asarray(c["chol"], dtype=np.float64).reshape(nz * nz).tolist()
         d.out = out.ptr
     ctx.check(_capi.lib().cb2_approx_conv_batch_dev(ctx._h, descs, B, int(seed)))
     return outs

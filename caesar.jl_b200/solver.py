@@ -204,11 +204,20 @@ def _apply_post(out, post):
     return out
 
 
+def _chol(factor):
+    """Cholesky factor of the factor's noise covariance, computed once per factor object."""
+    L = factor.__dict__.get("_chol")
+    if L is None:
+        L = np.linalg.cholesky(factor.cov)
+        factor.__dict__["_chol"] = L
+    return L
+
+
 def conv_desc(fg, labels, factor, target, stream, rng=None):
     """Descriptor of one closed-form convolution for a backend's `approx_conv_batch` (device: `approxConvBatch`)."""
     N = fg.N
     if isinstance(factor, PriorPose2):
-        return dict(kind=0, reverse=False, N=N, mean=factor.mean, chol=np.linalg.cholesky(factor.cov), stream=stream, src=None, aux=None)
+        return dict(kind=0, reverse=False, N=N, mean=factor.mean, chol=_chol(factor), stream=stream, src=None, aux=None)
     if isinstance(factor, PriorPoint2):
         L = np.zeros((3, 3))
         L[:2, :2] = np.linalg.cholesky(factor.cov)
@@ -221,8 +230,7 @@ def conv_desc(fg, labels, factor, target, stream, rng=None):
         return dict(kind=6, reverse=target == labels[0], N=N, mean=[factor.rho, 0.0, 0.0], chol=np.diag([factor.sigma, 0.0, 0.0]),
                     stream=stream, src=src, aux=None)
     if isinstance(factor, Pose2Pose2):
-        return dict(kind=1, reverse=target == labels[0], N=N, mean=factor.mean, chol=np.linalg.cholesky(factor.cov), stream=stream,
-                    src=src, aux=None)
+        return dict(kind=1, reverse=target == labels[0], N=N, mean=factor.mean, chol=_chol(factor), stream=stream, src=src, aux=None)
     if isinstance(factor, Pose2Point2BearingRange):
         rev = target == labels[0]
         return dict(kind=2, reverse=rev, N=N, mean=[factor.bearing[0], factor.range[0], 0.0],
@@ -240,6 +248,13 @@ def _convolve(fg, backend, items, rng, seed, stream0):
         outs = backend.approx_conv_batch(descs, seed)
         return [o if p is None else _apply_post(o, p) for o, p in zip(outs, posts)]
     return [approx_conv(fg, ls, f, t, rng) for ls, f, t in items]
+
+
+class _PointsOnly:
+    """An initialised variable before its bandwidth has been searched (forward initialisation)."""
+
+    def __init__(self, pts):
+        self.pts = pts
 
 
 def _colouring(fg):
@@ -266,6 +281,7 @@ def solveGraph(fg, backend, gibbs_iters=3, seed=0, stats=None):
         backend.begin(fg)
     # forward initialisation (initAll!): a variable is initialised from the first factor whose other end already is
     pending = [v for v in fg.variables if fg.variables[v].belief is None]  # (a re-solve after adding to the graph keeps the rest)
+    fresh = list(pending)
     while pending:
         progressed = False
         for v in list(pending):
@@ -274,12 +290,17 @@ def solveGraph(fg, backend, gibbs_iters=3, seed=0, stats=None):
                 if all(fg.variables[o].belief is not None for o in others) and not (
                         isinstance(f, Pose2Point2BearingRange) and v == ls[0]):
                     pts = _convolve(fg, backend, [(ls, f, v)], rng, seed * 7919 + 1, 900000 + len(pending))[0]
-                    fg.variables[v].belief = backend.manikde_batch(fg.variables[v].vartype, [pts])[0]
+                    fg.variables[v].belief = _PointsOnly(pts)   # the chain of initialisations needs points only
                     pending.remove(v)
                     progressed = True
                     break
         if not progressed:
             raise RuntimeError(f"cannot initialise {pending}")
+    for vartype in ("Pose2", "Point2"):  # the bandwidths of all initial beliefs in one batched search per variable type
+        vs = [v for v in fresh if fg.variables[v].vartype == vartype]
+        if vs:
+            for v, b in zip(vs, backend.manikde_batch(vartype, [fg.variables[v].belief.pts for v in vs])):
+                fg.variables[v].belief = b
     colours = _colouring(fg)
     stream = 0
     conv_stream = 0
@@ -446,6 +467,6 @@ class DeviceResidentBackend:
 
     def finish(self, fg):
         """Downloads every belief (the one synchronisation of the solve)."""
-        for v in fg.variables.values():
-            if hasattr(v.belief, "to_host"):
-                v.belief = v.belief.to_host()
+        vs = [v for v in fg.variables.values() if hasattr(v.belief, "to_host")]
+        for v, b in zip(vs, self.r.download_beliefs([v.belief for v in vs], self.ctx)):
+            v.belief = b

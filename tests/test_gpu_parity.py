@@ -685,3 +685,25 @@ def test_small_tree_build_equals_general_tree_build(cb, ctx, N, d, monkeypatch):
         b = cb.product_points(dens, (0,) * d, 300, seed=4, ctx=ctx)
         monkeypatch.delenv("CB2_NO_TREE_SMALL")
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("manifold,D,N", [("Point2", 2, 2), ("Point2", 3, 100), ("Pose2", 3, 100), ("Pose2", 2, 255), ("Pose2", 5, 77),
+                                           ("Pose2", 3, 300), ("Point2", 8, 128)])
+def test_small_product_kernel_equals_general_kernel(cb, ctx, manifold, D, N, monkeypatch):
+    """Planar products whose records fit in shared memory run the SMALL instance of the Gibbs kernel (all levels staged once, no
+    bulk copies, second pass and leave-one-out gathers from shared memory): identical labels and points."""
+    d = 2 if manifold == "Point2" else 3
+    circ = (0, 0) if d == 2 else (0, 0, 1)
+    rng = np.random.default_rng(11 * N + D)
+    dens = []
+    for j in range(D):
+        pts = rng.normal(size=(N + 3 * j, d)) * rng.uniform(0.5, 1.5, size=d) + rng.normal(size=d) * 0.3
+        if d == 3:
+            pts[:, 2] = (pts[:, 2] * 0.3 + 3.0 + np.pi) % (2 * np.pi) - np.pi   # straddles the cut
+        w = rng.uniform(0.2, 1.0, size=len(pts)) if j % 2 else None
+        dens.append((pts, 1.06 * pts.std(0) * len(pts) ** -0.2) + ((w,) if w is not None else ()))
+    a = cb.product_points(dens, circ, 333, seed=9, ctx=ctx)
+    monkeypatch.setenv("CB2_NO_GIBBS_SMALL", "1")
+    b = cb.product_points(dens, circ, 333, seed=9, ctx=ctx)
+    monkeypatch.delenv("CB2_NO_GIBBS_SMALL")
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
