@@ -708,7 +708,8 @@ loo_tiny_kernel(const LooProblem* __restrict__ probs, const int* __restrict__ id
       if (row < N) {
         T tot = part[row];
         for (int q = 1; q < S; ++q) tot += part[q * NR + row];
-        if constexpr (sizeof(T) == 4) v = (double)(__log2f(fmaxf(tot, 1.17549435e-38f)) * 0.693147180559945309f);
+        // (an empty row -- every neighbour beyond the flush-to-zero radius -- weighs log(DBL_MIN) as in the other kernels)
+        if constexpr (sizeof(T) == 4) v = tot > 0.f ? (double)(__log2f(tot) * 0.693147180559945309f) : -708.3964185322641;
         else v = log(tot > 2.2250738585072014e-308 ? tot : 2.2250738585072014e-308);
       }
       v = warp_sum(v);
