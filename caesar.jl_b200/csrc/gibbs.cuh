@@ -44,7 +44,7 @@ template <typename T> struct SMeta {
   uint32_t srec32;                  // SMALL kernels: where this message's records (all levels) sit in shared memory (units of 32 elements)
   long long perm_off;
   T bw2[CB2_MAX_DIM];
-  float cmin[CB2_MAX_DIM], cmax[CB2_MAX_DIM];  // range of the stored circular coordinates over all levels
+  float cmin[CB2_MAX_DIM], cmax[CB2_MAX_DIM];  // range of the stored coordinates (leaves and node means of every level)
   int N, depth, uniform;
   __device__ __forceinline__ size_t rec_off(int l) const { return (size_t)rec_off32[l] * 32; }
 };
@@ -286,19 +286,44 @@ __device__ __forceinline__ float score_node_rsq(const f32x2 (&q)[8], const Packe
   return e;
 }
 
+// One common denominator over all six coordinates: D = D_x D_y, N = N_x D_y + N_y D_x, p = r exp2(lw - m - N r^2), r = rsqrt(D):
+// two MUFU per candidate instead of three for the same FMA-pipe work.  The six-fold product of variances squares the dynamic range,
+// so a warp takes this form only when every one of its chains can prove from the message's bounds (kernel variance below, half
+// the coordinate range squared + kernel variance above) that D stays inside [1e-30, 1e30] for every node: gibbs_kernel, `one_den`.
+template <bool UW>
+__device__ __forceinline__ float score_node_rsq1(const f32x2 (&q)[8], const PackedConst& c, float nm, float& mul) {
+  const f32x2 sq = pack2(c.nqs, c.nqs);
+  const f32x2 d0 = fma2(q[0], sq, c.a[0]), d1 = fma2(q[1], sq, c.a[1]), d2 = fma2(q[2], sq, c.a[2]);
+  const f32x2 t0 = mul2(d0, d0), t1 = mul2(d1, d1), t2 = mul2(d2, d2);
+  const f32x2 s0 = fma2(q[3], c.cmul, c.b[0]), s1 = fma2(q[4], c.cmul, c.b[1]), s2 = fma2(q[5], c.cmul, c.b[2]);
+  const f32x2 s01 = mul2(s0, s1);
+  const f32x2 num = fma2(s2, fma2(t1, s0, mul2(t0, s1)), mul2(s01, t2));
+  const f32x2 den = mul2(s01, s2);
+  float nx, ny, dx, dy, lw, p1;
+  unpack2(num, nx, ny);
+  unpack2(den, dx, dy);
+  unpack2(q[6], lw, p1);
+  const float r = fast_rsq(dx * dy);
+  const float n6 = fmaf(nx, dy, ny * dx);
+  mul = r;
+  return fmaf(-n6, r * r, UW ? nm : lw + nm);
+}
+
 // MODE 0: coarse level, 1: leaf level with per-kernel weights, 2: leaf level with uniform weights, 3: coarse level whose nodes
-// all weigh the same (packed loops only)
-template <int DIM, int MODE> struct RecLen { static constexpr int value = (MODE == 0 || MODE == 3) ? (2 * DIM + 1 + 3) / 4 * 4 : (DIM + 1 + 3) / 4 * 4; };
+// all weigh the same (packed loops only); 4 / 5: modes 0 / 3 over one common denominator (packed loops only)
+template <int MODE> struct IsCoarse { static constexpr bool value = MODE == 0 || MODE == 3 || MODE == 4 || MODE == 5; };
+template <int DIM, int MODE> struct RecLen { static constexpr int value = IsCoarse<MODE>::value ? (2 * DIM + 1 + 3) / 4 * 4 : (DIM + 1 + 3) / 4 * 4; };
 
 // whether a scoring path returns the probability as mul * exp2(e) (CB2_COARSE_RSQ) instead of exp2(e)
-template <int MODE, bool PACK> struct HasMul { static constexpr bool value = CB2_COARSE_RSQ && PACK && (MODE == 0 || MODE == 3); };
+template <int MODE, bool PACK> struct HasMul { static constexpr bool value = CB2_COARSE_RSQ && PACK && IsCoarse<MODE>::value; };
 
 template <typename T, int DIM, int MODE, bool PACK>
 __device__ __forceinline__ T score_regs(const RecR<T, RecLen<DIM, MODE>::value, PACK>& r, const ChainConst<T, DIM>& c,
                                         const PackedConst& pc, uint32_t circ, T nm, T& mul) {
   mul = T(1);
   if constexpr (PACK) {
-    if constexpr (MODE == 0 || MODE == 3) {
+    if constexpr (MODE == 4 || MODE == 5) return score_node_rsq1<MODE == 5>(r.q, pc, nm, mul);
+    else if constexpr (MODE == 0 || MODE == 3) {
 #if CB2_COARSE_RSQ
       return score_node_rsq<MODE == 3>(r.q, pc, nm, mul);
 #else
@@ -307,7 +332,7 @@ __device__ __forceinline__ T score_regs(const RecR<T, RecLen<DIM, MODE>::value, 
     }
     else return score_leaf_p<MODE == 2>(r.q, pc, nm);
   } else {
-    if constexpr (MODE == 0 || MODE == 3) return score_node<T, DIM>(r.v, c, circ, nm);
+    if constexpr (IsCoarse<MODE>::value) return score_node<T, DIM>(r.v, c, circ, nm);
     else return score_leaf<T, DIM, MODE == 2>(r.v, c, circ, nm);
   }
 }
@@ -954,6 +979,20 @@ gibbs_kernel(const GibbsArgs a) {
         GIBBS_T(1);
         // warp-uniform choice of the scoring loop (all chains of the warp must agree)
         const bool flat = circ == 0u || __all_sync(0xffffffffu, nowrap);
+        bool one_den = false;  // coarse level over one common denominator (score_node_rsq1): every chain of the warp proves the range
+        if constexpr (kPack && CB2_COARSE_RSQ && CB2_ONE_DEN && R == 1) {
+          if (!leaf && !single) {
+            float lo = 1.f, hi = 1.f;
+#pragma unroll
+            for (int i = 0; i < DIM; ++i) {
+              // (circular coordinates: the statistics are taken on the unrotated angles, whose spread is bounded by pi)
+              const float half = (circ >> i & 1) ? 3.1416f : 0.5f * (dj.cmax[i] - dj.cmin[i]);
+              lo *= (float)dj.bw2[i] + (float)cc[0].b[i];
+              hi *= fmaf(half, half, (float)dj.bw2[i]) + (float)cc[0].b[i];
+            }
+            one_den = __all_sync(0xffffffffu, lo > 1e-30f && hi < 1e30f);
+          }
+        }
         // ---- pass 1: chunk partial sums of exp2(e - m), m = running (lazily raised) reference maximum
         T m[R], csum[R], thr[R];
 #pragma unroll
@@ -995,8 +1034,16 @@ gibbs_kernel(const GibbsArgs a) {
           // not flat as a whole: they take the wrapped loops instead and the kernel stays smaller (instruction cache)
           if (flat && !(kTC && leaf)) {  // Euclidean arithmetic on every coordinate: same values as the wrapped form, fewer instructions
             if (!leaf) {
-              if (kPack && cw) tile_pass<T, DIM, 3, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
-              else tile_pass<T, DIM, 0, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
+              if constexpr (kPack && CB2_COARSE_RSQ && CB2_ONE_DEN && R == 1) {
+                if (one_den) {
+                  if (cw) tile_pass<T, DIM, 5, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
+                  else tile_pass<T, DIM, 4, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
+                } else if (cw) tile_pass<T, DIM, 3, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
+                else tile_pass<T, DIM, 0, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
+              } else {
+                if (kPack && cw) tile_pass<T, DIM, 3, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
+                else tile_pass<T, DIM, 0, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
+              }
             }
             else if constexpr (!kTC) {
               if (!dj.uniform) tile_pass<T, DIM, 1, kPack, R>(tb, nt, t * TN, CH, cc, pc, 0u, chunk, tid, m, csum, cidx, thr);
@@ -1038,8 +1085,17 @@ gibbs_kernel(const GibbsArgs a) {
           // pass 2 must reproduce the scores of pass 1 bit for bit, so it takes the same (packed or wrapped) scorer
           int pick;
           if (flat && !(kTC && leaf)) {
-            if (!leaf) pick = (kPack && cw) ? chunk_pick<T, DIM, 3, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
-                                            : chunk_pick<T, DIM, 0, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
+            if (!leaf) {
+              if constexpr (kPack && CB2_COARSE_RSQ && CB2_ONE_DEN && R == 1) {
+                if (one_den) pick = cw ? chunk_pick<T, DIM, 5, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
+                                       : chunk_pick<T, DIM, 4, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
+                else pick = cw ? chunk_pick<T, DIM, 3, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
+                               : chunk_pick<T, DIM, 0, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
+              } else {
+                pick = (kPack && cw) ? chunk_pick<T, DIM, 3, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
+                                     : chunk_pick<T, DIM, 0, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);
+              }
+            }
             else if constexpr (!kTC) {
               pick = !dj.uniform ? chunk_pick<T, DIM, 1, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt)
                                  : chunk_pick<T, DIM, 2, kPack, SMALL>(lrec, z0, z1, cc[r], pc[r], 0u, m[r], cum, tgt);

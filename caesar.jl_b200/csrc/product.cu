@@ -66,6 +66,9 @@ __host__ __device__ inline int node_of(int N, int l, int p) {
 #ifndef CB2_COARSE_RSQ
 #define CB2_COARSE_RSQ 1   // coarse levels of the packed FP32 d = 6 loops: 2 MUFU.RSQ + 1 MUFU.EX2 per candidate (gibbs.cuh)
 #endif
+#ifndef CB2_ONE_DEN
+#define CB2_ONE_DEN 1      // ... over one common denominator (2 MUFU) where the six-fold product of variances stays in range
+#endif
 #ifndef CB2_TC_TILE
 #define CB2_TC_TILE 128
 #endif
@@ -330,8 +333,9 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
   auto lvl_off = [&](int l) { return l < depth ? ((1 << l) - 1) : ((1 << depth) - 1); };
   const int nd = 2 * d + 1;
   const int RECN = recn_of(d), RECL = recl_of(d);
-  // range of the stored circular coordinates over every level: lets a Gibbs chain prove that no candidate of this message
-  // is more than pi away from its current mean, i.e. that the wrap is a no-op (gibbs.cuh, `nowrap`)
+  // range of the stored coordinates over every level: lets a Gibbs chain prove that no candidate of this message is more than
+  // pi away from its current mean, i.e. that the wrap is a no-op (gibbs.cuh, `nowrap`), and bounds every node variance by
+  // (range / 2)^2 + bandwidth^2 (`one_den`)
   double cmn[CB2_MAX_DIM], cmx[CB2_MAX_DIM];
 #pragma unroll
   for (int i = 0; i < CB2_MAX_DIM; ++i) { cmn[i] = 1e300; cmx[i] = -1e300; }
@@ -356,7 +360,7 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
         sl[(size_t)p * nd + d + i] = m.bw[i] * m.bw[i];
         const double rv = (circ_mask >> i & 1) ? wrap_pi(v - cen[i]) : v - cen[i];
         rec[(size_t)p * RECL + i] = (T)rv;
-        if (circ_mask >> i & 1) { cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv); }
+        cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv);
       }
       sl[(size_t)p * nd + 2 * d] = wt;
       for (int i = d; i < RECL; ++i) rec[(size_t)p * RECL + i] = T(0);
@@ -400,7 +404,7 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
         sl[(size_t)k * nd + d + i] = v;
         const double rv = (circ_mask >> i & 1) ? wrap_pi(mm - cen[i]) : mm - cen[i];
         rec[(size_t)k * RECN + i] = (T)rv;
-        if (circ_mask >> i & 1) { cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv); }
+        cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv);
         rec[(size_t)k * RECN + d + i] = (T)v;
       }
       for (int i = 2 * d; i < RECN; ++i) rec[(size_t)k * RECN + i] = T(0);
@@ -536,7 +540,7 @@ tree_build_small_kernel(const DensMeta* __restrict__ metas, int d, int* __restri
         const double c = centre(i);
         const double rv = (circ_mask >> i & 1) ? wrap_pi(v - c) : v - c;
         rec[(size_t)p * RECL + i] = (T)rv;
-        if (circ_mask >> i & 1) { cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv); }
+        cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv);
       }
       sl[p * nd + 2 * d] = wt;
       for (int i = d; i < RECL; ++i) rec[(size_t)p * RECL + i] = T(0);
@@ -577,7 +581,7 @@ tree_build_small_kernel(const DensMeta* __restrict__ metas, int d, int* __restri
         const double c = centre(i);
         const double rv = (circ_mask >> i & 1) ? wrap_pi(mm - c) : mm - c;
         rec[(size_t)k * RECN + i] = (T)rv;
-        if (circ_mask >> i & 1) { cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv); }
+        cmn[i] = fmin(cmn[i], rv); cmx[i] = fmax(cmx[i], rv);
         rec[(size_t)k * RECN + d + i] = (T)v;
       }
       for (int i = 2 * d; i < RECN; ++i) rec[(size_t)k * RECN + i] = T(0);

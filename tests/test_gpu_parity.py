@@ -707,3 +707,26 @@ def test_small_product_kernel_equals_general_kernel(cb, ctx, manifold, D, N, mon
     b = cb.product_points(dens, circ, 333, seed=9, ctx=ctx)
     monkeypatch.delenv("CB2_NO_GIBBS_SMALL")
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
+
+
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 3e4, "mixed"])
+def test_product_fp32_coarse_levels_common_denominator_and_its_range_guard(cb, ctx32, scale):
+    """Coarse levels of the FP32 Pose3 kernel score over ONE common denominator of all six coordinates when a warp can prove that the
+    six-fold product of variances stays inside FP32 range, and over two denominators of three otherwise.  Millimetre / milliradian
+    beliefs (product of variances ~1e-36), kilometre-scale ones (1e+50 without the guard) and mixed scales must all follow the
+    oracle's chains and stay finite."""
+    rng = np.random.default_rng(5)
+    sc = np.array([1e-3, 1e4, 1.0, 1e-3, 0.3, 1e-2]) if scale == "mixed" else np.r_[np.full(3, float(scale)), np.full(3, min(float(scale), 0.3))]
+    circ = (0, 0, 0, 1, 1, 1)
+    dens = []
+    for j, N in enumerate((512, 300, 257, 1024)):
+        pts = rng.normal(size=(N, 6)) * sc * rng.uniform(0.5, 1.0, size=6) + rng.normal(size=6) * 0.3 * sc
+        dens.append((pts, 1.06 * pts.std(0) * N ** -0.2))
+    pts, lab = cb.product_points(dens, circ, 512, seed=13, ctx=ctx32)
+    opts, olab = oracle.product(dens, 512, seed=13, circular=list(circ), ubits=24)
+    assert np.isfinite(pts).all()
+    agree = (lab == olab).all(axis=1)
+    assert agree.mean() > 0.9, (scale, agree.mean())
+    diff = pts[agree] - opts[agree]
+    diff[:, 3:] = (diff[:, 3:] + np.pi) % (2 * np.pi) - np.pi
+    assert np.abs(diff / sc).max() < 1e-3
