@@ -680,6 +680,8 @@ __device__ __forceinline__ void leaf_pass_tc(const float* __restrict__ feat, int
       float gmax = -INFINITY;
       const bool shifted = __any_sync(0xffffffffu, extra != 0.f);  // some chain of the warp has raised its reference in this pass
       const float nx = -extra;
+      // (loading the next block's accumulators while this one is summed -- two blocks of 32 or of 16 registers -- was measured
+      // slower, 181.5 / 178.4 vs 167.7 ms: the other warps of the SM already cover the load latency, the extra registers spill)
 #pragma unroll 1  // one copy of the 32-leaf body: the kernel is large enough to miss in the instruction cache
       for (int c0 = 0; c0 < kTcTile; c0 += 32) {
         const int z0 = t * kTcTile + c0;
