@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 D_MSG, N_KER, DIM, N_OUT = 8, 4096, 6, 4096
 CIRC = (0, 0, 0, 1, 1, 1)
 VARS_PER_GPU = 256
-TRAFFIC_NCU = {256: 1959.6e6}  # dram bytes (read + write) of one gibbs_kernel launch, ncu --set full (profiles/r02_ncu_full_summary.csv), by variables per launch
+TRAFFIC_NCU = {256: 1975.0e6}  # dram bytes (read + write) of one gibbs_kernel launch, ncu --set full (profiles/r02_ncu_full_summary.csv), by variables per launch
 FP32_FLOPS_PER_EVAL = 4 * DIM + 3  # product kernel-eval ~ (4d+3) flops + 1 SFU
 
 
@@ -293,9 +293,9 @@ def main():
                                     "frac": b / (gibbs_ms * 1e-3) / 1e9 / pk, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks
                                     else "B200_PROFILING.md fallback"})(
             V * (3.146e6 + D_MSG * N_KER * 128 + D_MSG * N_KER * 4 + N_OUT * (DIM * 8 + D_MSG * 4)), float(peaks.get("hbm_gbs", 6550.0))) if gibbs_ms > 0 else None,
-        "ncu": {"issue_active_pct": 57.9, "pipe_fma_cycles_pct": 51.9, "pipe_xu_pct": 51.7, "lsu_wavefronts_pct": 54.2,
-                "warp_instructions": 1.08e11, "registers": 126, "launch_ms": 172.0,
-                "source": "profiles/r02_ncu_full_summary.csv (r02_gibbs_final, 256 variables); launch shares: profiles/r02_launch_summary.csv"},
+        "ncu": {"issue_active_pct": 58.3, "pipe_fma_cycles_pct": 52.5, "pipe_xu_pct": 43.5, "lsu_wavefronts_pct": 55.7,
+                "warp_instructions": 1.06e11, "registers": 128, "launch_ms": 167.7,
+                "source": "profiles/r02_ncu_full_summary.csv (r02_gibbs_final2, 256 variables); launch shares: profiles/r02_launch_summary.csv"},
         "phases_under_full_load": {"pass1_coarse": 0.59, "pass1_leaf_tensor_core": 0.226, "pass2": 0.083, "combine": 0.062, "cdf": 0.029, "other": 0.01,
                                    "source": "in-kernel clock64 profile of a CTA from the middle of the grid (-DCB2_GIBBS_PROF) of the 182.9 ms build, before the reference moved into the MMA coefficient row; DESIGN.md sec. 4"},
     }
