@@ -49,9 +49,21 @@ struct cb2_ctx {
   cudaEvent_t copy_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::map<int64_t, cb2_pending> pending;
   int64_t next_ticket = 1;
+  std::map<const void*, size_t> smem_attr;  // kernels whose dynamic shared-memory limit has been raised, and to what (cb2_func_smem)
 };
 
 typedef std::lock_guard<std::recursive_mutex> cb2_lock;
+
+// Raises the dynamic shared-memory limit of a kernel once per context (again only for a larger request): the attribute call is a
+// driver round trip of a few microseconds, which small batches pay on every launch otherwise.  Caller holds ctx->mu.
+inline cudaError_t cb2_func_smem(cb2_ctx* ctx, const void* fn, size_t bytes, bool max_carveout = false) {
+  auto it = ctx->smem_attr.find(fn);
+  if (it != ctx->smem_attr.end() && it->second >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && max_carveout) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess) ctx->smem_attr[fn] = bytes;
+  return e;
+}
 
 int cb2_fail(cb2_ctx* ctx, int code, const char* fmt, ...);
 

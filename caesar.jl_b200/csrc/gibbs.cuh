@@ -10,7 +10,7 @@
 //                   f32x2 registers (FFMA2 / FMUL2), the two groups of three coordinates over common denominators D_x, D_y,
 //                   p = r_x r_y exp2(.. - N_x r_x^2 - N_y r_y^2) with r = rsqrt(D) (one denominator D_x D_y and one rsqrt where a
 //                   warp can bound the product, score_node_rsq1): 15 packed + 8 scalar FMA-pipe
-//                   instructions, 3 MUFU and 3 LDS.128 per candidate.  Measured under full load: 60 clk per candidate and
+//                   instructions, 2 - 3 MUFU and 3 LDS.128 per candidate.  Measured under full load: 60 clk per candidate and
 //                   SM sub-partition against 37 clk of FMA pipe and 29 clk-equivalents of the SM-wide shared-memory pipe (a
 //                   warp-broadcast LDS.128 costs 2.4 clk of it, bench/micro/lds_bcast.cu) -- both pipes are near their limit there.
 // Circular coordinates are stored wrapped to [-pi, pi] (tree_build_kernel) and the chain mean comes out of atan2,

@@ -794,24 +794,28 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
   char* base = (char*)scratch;
   size_t off = 0;
   auto take = [&](size_t bytes) { void* p = base + off; off += cb2_align(bytes); return p; };
+  // uploaded tables first and back to back (problems, CTA map, small / tiny ids): one copy
   LooProblem* probs_dev = (LooProblem*)take(sizeof(LooProblem) * P);
-  LooState* st_dev = (LooState*)take(sizeof(LooState) * P);
   int2* map_dev = (int2*)take(sizeof(int2) * (cta_map.size() + 1));
   int* small_dev = (int*)take(sizeof(int) * (small_ids.size() + tiny_ids.size() + 1));
   int* tiny_dev = small_dev + small_ids.size();
+  const size_t tab_bytes = (size_t)((char*)(small_dev + small_ids.size() + tiny_ids.size()) - base);
+  LooState* st_dev = (LooState*)take(sizeof(LooState) * P);
   double* partial = (double*)take(sizeof(double) * P);
   int* counters = (int*)take(sizeof(int) * 64);
   double* xs_dev = (double*)take(sizeof(double) * (size_t)xs_elems);
   void* rowsum = take(tsz * (size_t)xs_elems);
   void* colpart = take(tsz * (size_t)cp_elems);
-  CB2_CUDA(ctx, cudaMemcpyAsync(probs_dev, probs.data(), sizeof(LooProblem) * P, cudaMemcpyHostToDevice, ctx->stream));
-  if (!cta_map.empty())
-    CB2_CUDA(ctx, cudaMemcpyAsync(map_dev, cta_map.data(), sizeof(int2) * cta_map.size(), cudaMemcpyHostToDevice, ctx->stream));
-  if (!small_ids.empty())
-    CB2_CUDA(ctx, cudaMemcpyAsync(small_dev, small_ids.data(), sizeof(int) * small_ids.size(), cudaMemcpyHostToDevice, ctx->stream));
+  {
+    std::vector<char> tab(tab_bytes);
+    memcpy(tab.data() + ((char*)probs_dev - base), probs.data(), sizeof(LooProblem) * P);
+    if (!cta_map.empty()) memcpy(tab.data() + ((char*)map_dev - base), cta_map.data(), sizeof(int2) * cta_map.size());
+    if (!small_ids.empty()) memcpy(tab.data() + ((char*)small_dev - base), small_ids.data(), sizeof(int) * small_ids.size());
+    if (!tiny_ids.empty()) memcpy(tab.data() + ((char*)tiny_dev - base), tiny_ids.data(), sizeof(int) * tiny_ids.size());
+    CB2_CUDA(ctx, cudaMemcpyAsync(base, tab.data(), tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
   const bool all_tiny = (int)tiny_ids.size() == P;   // then the kernel writes the bandwidths itself and nothing else is launched
   if (!tiny_ids.empty()) {
-    CB2_CUDA(ctx, cudaMemcpyAsync(tiny_dev, tiny_ids.data(), sizeof(int) * tiny_ids.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (f64) loo_tiny_kernel<double><<<(int)tiny_ids.size(), kThreads, 0, ctx->stream>>>(probs_dev, tiny_dev, st_dev, all_tiny ? sigma_out_dev : nullptr);
     else loo_tiny_kernel<float><<<(int)tiny_ids.size(), kThreads, 0, ctx->stream>>>(probs_dev, tiny_dev, st_dev, all_tiny ? sigma_out_dev : nullptr);
     CB2_CHECK_LAUNCH(ctx, "loo_tiny_kernel");
@@ -838,13 +842,12 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
   int P2 = 1;
   while (P2 < maxN) P2 <<= 1;
   size_t sort_smem = sizeof(double) * P2;
-  cudaError_t e = cudaFuncSetAttribute(loo_sort_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
+  cudaError_t e = cb2_func_smem(ctx, (const void*)loo_sort_init_kernel, sort_smem);
   if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "loo sort smem attribute: %s", cudaGetErrorString(e));
   loo_sort_init_kernel<<<P, kSortThreads, sort_smem, ctx->stream>>>(probs_dev, st_dev, xs_dev);
   CB2_CHECK_LAUNCH(ctx, "loo_sort_init_kernel");
   const size_t rows_smem = tsz * (size_t)kCT * (1 + kThreads / 32);
-  e = f64 ? cudaFuncSetAttribute(loo_rows_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem)
-          : cudaFuncSetAttribute(loo_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem);
+  e = f64 ? cb2_func_smem(ctx, (const void*)loo_rows_kernel<double>, rows_smem) : cb2_func_smem(ctx, (const void*)loo_rows_kernel<float>, rows_smem);
   if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "loo rows smem attribute: %s", cudaGetErrorString(e));
   const int max_iter = 64, check_every = 8;
   for (int it = 0; it < max_iter; ++it) {

@@ -709,9 +709,7 @@ template <typename T, int DIM, uint32_t CIRC, bool SMALL = false>
 int launch_gibbs_inst(cb2_ctx* ctx, int nwork, const GibbsArgs& a, size_t stage_bytes = 0) {
   size_t smem = gibbs_smem_bytes<T, DIM>();
   if (SMALL) smem = ((smem + 127) & ~(size_t)127) + stage_bytes;
-  cudaError_t e = cudaFuncSetAttribute(gibbs_kernel<T, DIM, CIRC, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(gibbs_kernel<T, DIM, CIRC, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaError_t e = cb2_func_smem(ctx, (const void*)gibbs_kernel<T, DIM, CIRC, SMALL>, smem, true);
   if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "gibbs smem attribute: %s", cudaGetErrorString(e));
   gibbs_kernel<T, DIM, CIRC, SMALL><<<nwork, kS / ChainsPerThread<T, DIM>::value, smem, ctx->stream>>>(a);
   CB2_CHECK_LAUNCH(ctx, "gibbs_kernel");
@@ -855,9 +853,14 @@ int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const
     pl.prods[b].out = descs[b].pts_out;
     pl.prods[b].labels = descs[b].labels_out;
   }
-  CB2_CUDA(ctx, cudaMemcpyAsync(lay.metas, pl.metas.data(), sizeof(DensMeta) * pl.metas.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CB2_CUDA(ctx, cudaMemcpyAsync(lay.prods, pl.prods.data(), sizeof(ProdDev) * pl.prods.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CB2_CUDA(ctx, cudaMemcpyAsync(lay.work, pl.work.data(), sizeof(Work) * pl.work.size(), cudaMemcpyHostToDevice, ctx->stream));
+  {  // the three tables sit back to back at the start of the layout: one upload (each copy from pageable memory costs ~5 us of host time)
+    const size_t tab_bytes = o_work + sizeof(Work) * pl.work.size();
+    std::vector<char> tab(tab_bytes);
+    memcpy(tab.data() + o_metas, pl.metas.data(), sizeof(DensMeta) * pl.metas.size());
+    memcpy(tab.data() + o_prods, pl.prods.data(), sizeof(ProdDev) * pl.prods.size());
+    memcpy(tab.data() + o_work, pl.work.data(), sizeof(Work) * pl.work.size());
+    CB2_CUDA(ctx, cudaMemcpyAsync(base, tab.data(), tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
   if (bw_ptrs_dev) {
     fill_meta_bw_kernel<<<(int)((pl.metas.size() + 127) / 128), 128, 0, ctx->stream>>>(lay.metas, bw_ptrs_dev, (int)pl.metas.size(), d);
     CB2_CHECK_LAUNCH(ctx, "fill_meta_bw_kernel");
@@ -870,8 +873,8 @@ int product_batch_core(cb2_ctx* ctx, const cb2_product_desc* descs, int B, const
   const size_t small_smem = tree_small_smem(tree_maxN, pl.max_nodes, d);
   // launches whose messages all hold at most kTreeSmallN points take the latency-oriented kernel
   const bool tree_small = tree_maxN <= kTreeSmallN && small_smem <= 160 * 1024 && !getenv("CB2_NO_TREE_SMALL");
-  cudaError_t e = tree_small ? cudaFuncSetAttribute(tree_build_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem)
-                             : cudaFuncSetAttribute(tree_build_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem);
+  cudaError_t e = tree_small ? cb2_func_smem(ctx, (const void*)tree_build_small_kernel<T>, small_smem)
+                             : cb2_func_smem(ctx, (const void*)tree_build_kernel<T>, tree_smem);
   if (e != cudaSuccess) return cb2_fail(ctx, CB2_ERR_CUDA, "tree smem attribute (%zu bytes): %s", tree_small ? small_smem : tree_smem, cudaGetErrorString(e));
   if (chunks && !chunks->msg_end.empty()) {  // build the trees of every chunk as soon as its arrays have landed
     int m0 = 0;
