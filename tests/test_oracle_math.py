@@ -235,3 +235,37 @@ def test_icp_restatement_recovers_a_known_rigid_transform():
         assert np.abs(Hk[k] - H[0] @ Tp).max() < 1.5e-2, k
     with pytest.raises(ValueError):
         oracle.icp_align(fix, mov, correspondences=5)
+
+
+def test_point2_convolutions_prior_and_range_ring():
+    """PriorPoint2 and Point2Point2Range (the factors of R:test/ICRA2022_tests/insufficient_data.jl:104-134): a Gaussian, and a ring
+    of radius ~ N(rho, sigma) around the known point with a uniform direction, the same in both directions of the factor."""
+    L = np.zeros((3, 3))
+    L[:2, :2] = np.linalg.cholesky(np.array([[2.0, 0.6], [0.6, 1.0]]))
+    pr = oracle.approx_conv(5, False, 20000, [10.0, 30.0, 0.0], L, seed=3, stream=1)
+    assert pr.shape == (20000, 2)
+    assert np.allclose(pr.mean(0), [10.0, 30.0], atol=0.05) and np.allclose(np.cov(pr.T), [[2.0, 0.6], [0.6, 1.0]], atol=0.06)
+    src = np.array([[10.0, 30.0], [10.5, 29.0], [9.0, 31.0]])
+    for reverse in (False, True):
+        ring = oracle.approx_conv(6, reverse, 6000, [31.6, 0, 0], np.diag([2.0, 0, 0]), seed=4, stream=2, src=src)
+        rel = ring - src[np.arange(6000) % 3]
+        r, th = np.hypot(*rel.T), np.arctan2(rel[:, 1], rel[:, 0])
+        assert abs(r.mean() - 31.6) < 0.1 and abs(r.std() - 2.0) < 0.1
+        assert np.histogram(th, bins=8, range=(-np.pi, np.pi))[0].min() > 0.8 * 6000 / 8   # uniform direction
+    # same counters, same draws: the reverse flag does not change a symmetric factor
+    a = oracle.approx_conv(6, False, 50, [5.0, 0, 0], np.diag([0.1, 0, 0]), seed=9, stream=0, src=src)
+    b = oracle.approx_conv(6, True, 50, [5.0, 0, 0], np.diag([0.1, 0, 0]), seed=9, stream=0, src=src)
+    assert np.array_equal(a, b)
+
+
+def test_heatmap_grid_density_counterpart_places_mass_where_the_image_has_it():
+    x, y = np.linspace(-5, 5, 41), np.linspace(-3, 3, 25)
+    gx, gy = np.meshgrid(x, y, indexing="ij")
+    img = np.exp(-0.5 * ((gx - 2.0) ** 2 + (gy + 1.0) ** 2) / 0.3) - 0.05   # negative background carries no mass
+    pts, bw = oracle.heatmap_grid_density(img, (x, y), 2000, seed=1)
+    assert pts.shape == (2000, 2) and bw.shape == (2,) and (bw > 0).all()
+    assert np.allclose(pts.mean(0), [2.0, -1.0], atol=0.05)
+    assert np.all(np.hypot(pts[:, 0] - 2.0, pts[:, 1] + 1.0) < 2.5)
+    # reproducible: the Philox stream is keyed by the seed alone
+    p2, _ = oracle.heatmap_grid_density(img, (x, y), 2000, seed=1)
+    assert np.array_equal(pts, p2)
