@@ -437,11 +437,13 @@ def product_points(dens, circular, Nout, seed=0, niter=1, stream=0, sample_offse
 
 
 FACTOR_PRIOR_POSE2, FACTOR_POSE2POSE2, FACTOR_POSE2POINT2_BEARINGRANGE, FACTOR_PRIOR_POSE3, FACTOR_POSE3POSE3 = 0, 1, 2, 3, 4
-FACTOR_PRIOR_POINT2, FACTOR_POINT2POINT2_RANGE = 5, 6
+FACTOR_PRIOR_POINT2, FACTOR_POINT2POINT2_RANGE, FACTOR_LINEAR_SAMPLES = 5, 6, 7
 
 
-def _conv_dims(kind, rev):
+def _conv_dims(kind, rev, mean=None):
     """(coordinates of the noise / mean, coordinates of the target) of a closed-form convolution."""
+    if kind == FACTOR_LINEAR_SAMPLES:
+        return 3, int(np.asarray(mean, dtype=np.float64).ravel()[0])
     if kind in (FACTOR_PRIOR_POSE3, FACTOR_POSE3POSE3):
         return 6, 6
     if kind in (FACTOR_PRIOR_POINT2, FACTOR_POINT2POINT2_RANGE):
@@ -459,7 +461,7 @@ def approxConvBatch(convs, seed=0, ctx=None):
     keep, outs = [], []
     for b, c in enumerate(convs):
         kind, rev = int(c["kind"]), int(bool(c.get("reverse", False)))
-        nz, dt = _conv_dims(kind, rev)
+        nz, dt = _conv_dims(kind, rev, c.get("mean"))
         out = np.zeros((int(c["N"]), dt))
         src = None if c.get("src") is None else f64(c["src"])
         aux = None if c.get("aux") is None else f64(c["aux"])

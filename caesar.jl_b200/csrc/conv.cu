@@ -126,6 +126,15 @@ __global__ void approx_conv_kernel(const ConvDev* __restrict__ descs, uint32_t k
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.N) return;
   if (is_pose3(c.kind)) { conv_pose3(c, i, k0, k1); return; }
+  if (c.kind == CB2_FACTOR_LINEAR_SAMPLES) {  // the caller's noise samples: x_j = x_i + z, x_i = x_j - z, or x = z without a source
+    const int dd = (int)c.mean[0];
+    const double* zz = c.aux + (size_t)(i % c.n_aux) * dd;
+    for (int k = 0; k < dd; ++k) {
+      const double base = c.n_src > 0 ? c.src[(size_t)(i % c.n_src) * dd + k] : 0.0;
+      c.out[(size_t)i * dd + k] = c.reverse ? base - zz[k] : base + zz[k];
+    }
+    return;
+  }
   double z[3], nz[3];
   normal3((uint32_t)i, c.stream, k0, k1, z);
   for (int r = 0; r < 3; ++r) nz[r] = c.mean[r] + c.chol[r * 3] * z[0] + c.chol[r * 3 + 1] * z[1] + c.chol[r * 3 + 2] * z[2];
@@ -177,17 +186,24 @@ __global__ void approx_conv_kernel(const ConvDev* __restrict__ descs, uint32_t k
 
 inline bool is_point2(int kind) { return kind == CB2_FACTOR_PRIOR_POINT2 || kind == CB2_FACTOR_POINT2POINT2_RANGE; }
 inline int out_dim(const cb2_conv_desc& c) {
+  if (c.kind == CB2_FACTOR_LINEAR_SAMPLES) return (int)c.mean[0];
   if (is_pose3(c.kind)) return 6;
   if (is_point2(c.kind)) return 2;
   return (c.kind == CB2_FACTOR_POSE2POINT2_BEARINGRANGE && !c.reverse) ? 2 : 3;
 }
+inline int aux_dim(const cb2_conv_desc& c) { return c.kind == CB2_FACTOR_LINEAR_SAMPLES ? (int)c.mean[0] : 3; }
 inline int src_dim(const cb2_conv_desc& c) {
+  if (c.kind == CB2_FACTOR_LINEAR_SAMPLES) return (int)c.mean[0];
   if (is_pose3(c.kind)) return 6;
   if (is_point2(c.kind)) return 2;
   return (c.kind == CB2_FACTOR_POSE2POINT2_BEARINGRANGE && c.reverse) ? 2 : 3;
 }
 inline bool is_prior(const cb2_conv_desc& c) {
-  return c.kind == CB2_FACTOR_PRIOR_POSE2 || c.kind == CB2_FACTOR_PRIOR_POSE3 || c.kind == CB2_FACTOR_PRIOR_POINT2;
+  return c.kind == CB2_FACTOR_PRIOR_POSE2 || c.kind == CB2_FACTOR_PRIOR_POSE3 || c.kind == CB2_FACTOR_PRIOR_POINT2 ||
+         (c.kind == CB2_FACTOR_LINEAR_SAMPLES && c.n_src == 0);
+}
+inline bool needs_aux(const cb2_conv_desc& c) {
+  return c.kind == CB2_FACTOR_LINEAR_SAMPLES || (c.kind == CB2_FACTOR_POSE2POINT2_BEARINGRANGE && c.reverse);
 }
 
 // residual of the relative-pose factors (ScatterAlignPose2/3, Pose2Pose2, Pose3Pose3): one thread per particle
@@ -224,13 +240,13 @@ extern "C" int cb2_approx_conv_batch(cb2_ctx* ctx, const cb2_conv_desc* descs, i
   int maxN = 0;
   for (int b = 0; b < B; ++b) {
     const cb2_conv_desc& c = descs[b];
-    CB2_REQUIRE(ctx, c.kind >= 0 && c.kind <= CB2_FACTOR_POINT2POINT2_RANGE, "convolution %d: unknown factor kind %d", b, c.kind);
+    CB2_REQUIRE(ctx, c.kind >= 0 && c.kind <= CB2_FACTOR_LINEAR_SAMPLES, "convolution %d: unknown factor kind %d", b, c.kind);
     CB2_REQUIRE(ctx, c.N > 0 && c.out, "convolution %d: N <= 0 or null out", b);
     if (!is_prior(c)) CB2_REQUIRE(ctx, c.src && c.n_src > 0, "convolution %d: missing source samples", b);
-    if (c.kind == CB2_FACTOR_POSE2POINT2_BEARINGRANGE && c.reverse)
-      CB2_REQUIRE(ctx, c.aux && c.n_aux > 0, "convolution %d: reverse bearing-range needs the pose's current samples", b);
+    if (needs_aux(c)) CB2_REQUIRE(ctx, c.aux && c.n_aux > 0, "convolution %d: missing aux samples (pose samples of a reverse bearing-range / noise of LINEAR_SAMPLES)", b);
+    if (c.kind == CB2_FACTOR_LINEAR_SAMPLES) CB2_REQUIRE(ctx, c.mean[0] >= 1 && c.mean[0] <= 3, "convolution %d: LINEAR_SAMPLES needs mean[0] = d in 1..3", b);
     if (!is_prior(c)) total += cb2_align(sizeof(double) * (size_t)c.n_src * src_dim(c));
-    if (c.aux) total += cb2_align(sizeof(double) * (size_t)c.n_aux * 3);
+    if (needs_aux(c)) total += cb2_align(sizeof(double) * (size_t)c.n_aux * aux_dim(c));
     total += cb2_align(sizeof(double) * (size_t)c.N * out_dim(c));
     if (c.N > maxN) maxN = c.N;
   }
@@ -253,8 +269,8 @@ extern "C" int cb2_approx_conv_batch(cb2_ctx* ctx, const cb2_conv_desc* descs, i
       d.src = (const double*)(p + off);
       off += cb2_align(nb);
     }
-    if (c.aux && c.kind == CB2_FACTOR_POSE2POINT2_BEARINGRANGE && c.reverse) {
-      size_t nb = sizeof(double) * (size_t)c.n_aux * 3;
+    if (needs_aux(c)) {
+      size_t nb = sizeof(double) * (size_t)c.n_aux * aux_dim(c);
       memcpy(stage + off, c.aux, nb);
       d.aux = (const double*)(p + off);
       off += cb2_align(nb);
@@ -289,11 +305,11 @@ extern "C" int cb2_approx_conv_batch_dev(cb2_ctx* ctx, const cb2_conv_desc* desc
   int maxN = 0;
   for (int b = 0; b < B; ++b) {
     const cb2_conv_desc& c = descs[b];
-    CB2_REQUIRE(ctx, c.kind >= 0 && c.kind <= CB2_FACTOR_POINT2POINT2_RANGE, "convolution %d: unknown factor kind %d", b, c.kind);
+    CB2_REQUIRE(ctx, c.kind >= 0 && c.kind <= CB2_FACTOR_LINEAR_SAMPLES, "convolution %d: unknown factor kind %d", b, c.kind);
     CB2_REQUIRE(ctx, c.N > 0 && c.out, "convolution %d: N <= 0 or null out", b);
     if (!is_prior(c)) CB2_REQUIRE(ctx, c.src && c.n_src > 0, "convolution %d: missing source samples", b);
-    if (c.kind == CB2_FACTOR_POSE2POINT2_BEARINGRANGE && c.reverse)
-      CB2_REQUIRE(ctx, c.aux && c.n_aux > 0, "convolution %d: reverse bearing-range needs the pose's current samples", b);
+    if (needs_aux(c)) CB2_REQUIRE(ctx, c.aux && c.n_aux > 0, "convolution %d: missing aux samples (pose samples of a reverse bearing-range / noise of LINEAR_SAMPLES)", b);
+    if (c.kind == CB2_FACTOR_LINEAR_SAMPLES) CB2_REQUIRE(ctx, c.mean[0] >= 1 && c.mean[0] <= 3, "convolution %d: LINEAR_SAMPLES needs mean[0] = d in 1..3", b);
     ConvDev& d = dd[b];
     d.kind = c.kind; d.reverse = c.reverse; d.N = c.N; d.n_src = c.n_src; d.n_aux = c.n_aux; d.stream = c.stream;
     memcpy(d.mean, c.mean, sizeof(d.mean)); memcpy(d.chol, c.chol, sizeof(d.chol));

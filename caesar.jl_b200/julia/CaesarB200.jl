@@ -232,7 +232,7 @@ end
 
 # ------------------------------------------------------------------------------------------------ approxConv (closed form)
 # Proposals of closed-form relative factors (kinds 0 PriorPose2, 1 Pose2Pose2, 2 Pose2Point2BearingRange, 3 PriorPose3, 4 Pose3Pose3,
-# 5 PriorPoint2, 6 Point2Point2Range), all factors of a Gibbs colour in one launch; hook: IIF.approxConvBelief / sampleFactor for
+# 5 PriorPoint2, 6 Point2Point2Range, 7 Prior / LinearRelative with caller-sampled noise in `aux`), all factors of a Gibbs colour in one launch; hook: IIF.approxConvBelief / sampleFactor for
 # these factor types.
 struct CB2ConvDesc
   kind::Int32

@@ -94,6 +94,14 @@ def download_beliefs(beliefs, ctx):
     return out
 
 
+def upload_array(arr, slab, ctx):
+    """Host N x d Float64 samples -> DeviceArray (one stream-ordered copy)."""
+    a = f64(np.atleast_2d(arr))
+    p = slab.take(a.nbytes)
+    ctx.check(_capi.lib().cb2_upload(ctx._h, C.c_void_p(p), ptr(a), a.nbytes))
+    return DeviceArray(p, a.shape[0], a.shape[1])
+
+
 def upload_belief(mkd, slab, ctx):
     """Host ManifoldKernelDensity -> DeviceBelief (two stream-ordered copies)."""
     L = _capi.lib()
@@ -112,7 +120,7 @@ def approxConvBatch_dev(convs, slab, seed=0, ctx=None):
     outs = []
     for b, c in enumerate(convs):
         kind, rev = int(c["kind"]), int(bool(c.get("reverse", False)))
-        nz, dt = _conv_dims(kind, rev)
+        nz, dt = _conv_dims(kind, rev, c.get("mean"))
         N = int(c["N"])
         out = DeviceArray(slab.take(N * dt * 8), N, dt)
         outs.append(out)

@@ -17,6 +17,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 TWO_PI = 2.0 * np.pi
+VARTYPES = ("Pose2", "Point2", "ContinuousScalar")
 
 
 def _wrap(a):
@@ -66,6 +67,45 @@ class Point2Point2Range:
     points; R:test/ICRA2022_tests/insufficient_data.jl:70-85,126-142)."""
     rho: float
     sigma: float
+
+
+# ---- scalar factors with arbitrary noise (IIF.Prior / LinearRelative / Mixture on ContinuousScalar: the graph of the ICRA tutorial 2
+# test R:test/ICRA2022_tests/nongaussian_mixture.jl:18-51).  A distribution is a sampler `(rng, N) -> N values`; the factor's own
+# `getSample` stays on the host (as upstream's stays in Julia), the solve x_j = x_i + z is convolution kind 7 of the library.
+def Normal(mu, sigma):
+    return lambda rng, N: mu + sigma * rng.standard_normal(N)
+
+
+def Rayleigh(sigma):
+    return lambda rng, N: rng.rayleigh(sigma, size=N)
+
+
+def Uniform(a, b):
+    return lambda rng, N: rng.uniform(a, b, size=N)
+
+
+def MixtureDist(components, weights):
+    """`Mixture(LinearRelative, (a = .., b = ..), [w_a; w_b])`: every particle draws its component with the given probabilities."""
+    w = np.asarray(weights, dtype=np.float64)
+
+    def draw(rng, N):
+        pick = rng.choice(len(w), size=N, p=w / w.sum())
+        out = np.empty(N)
+        for k, c in enumerate(components):
+            sel = np.flatnonzero(pick == k)
+            out[sel] = c(rng, len(sel))
+        return out
+    return draw
+
+
+@dataclass
+class Prior:
+    dist: object
+
+
+@dataclass
+class LinearRelative:
+    dist: object
 
 
 @dataclass
@@ -127,8 +167,13 @@ def approx_conv(fg, labels, factor, target, rng):
         return x
     if isinstance(factor, PriorPoint2):
         return rng.multivariate_normal(factor.mean, factor.cov, size=N)
+    if isinstance(factor, Prior):
+        return factor.dist(rng, N)[:, None]
     other = labels[0] if labels[1] == target else labels[1]
     src = _resample(fg.variables[other].belief.pts, N, rng)
+    if isinstance(factor, LinearRelative):
+        z = factor.dist(rng, N)[:, None]
+        return src + z if target == labels[1] else src - z
     if isinstance(factor, Point2Point2Range):
         r = factor.rho + factor.sigma * rng.standard_normal(N)
         th = rng.uniform(-np.pi, np.pi, size=N)
@@ -222,10 +267,16 @@ def conv_desc(fg, labels, factor, target, stream, rng=None):
         L = np.zeros((3, 3))
         L[:2, :2] = np.linalg.cholesky(factor.cov)
         return dict(kind=5, reverse=False, N=N, mean=[factor.mean[0], factor.mean[1], 0.0], chol=L, stream=stream, src=None, aux=None)
+    if isinstance(factor, Prior):
+        return dict(kind=7, reverse=False, N=N, mean=[1.0, 0.0, 0.0], chol=np.zeros((3, 3)), stream=stream, src=None,
+                    aux=factor.dist(rng, N)[:, None])
     if isinstance(factor, Pose2Pose2) and (factor.multihypo is not None or factor.nullhypo > 0):
         return _hypo_desc(fg, labels, factor, target, stream, rng)
     other = labels[0] if labels[1] == target else labels[1]
     src = fg.variables[other].belief.pts
+    if isinstance(factor, LinearRelative):
+        return dict(kind=7, reverse=target == labels[0], N=N, mean=[1.0, 0.0, 0.0], chol=np.zeros((3, 3)), stream=stream, src=src,
+                    aux=factor.dist(rng, N)[:, None])
     if isinstance(factor, Point2Point2Range):
         return dict(kind=6, reverse=target == labels[0], N=N, mean=[factor.rho, 0.0, 0.0], chol=np.diag([factor.sigma, 0.0, 0.0]),
                     stream=stream, src=src, aux=None)
@@ -296,7 +347,7 @@ def solveGraph(fg, backend, gibbs_iters=3, seed=0, stats=None):
                     break
         if not progressed:
             raise RuntimeError(f"cannot initialise {pending}")
-    for vartype in ("Pose2", "Point2"):  # the bandwidths of all initial beliefs in one batched search per variable type
+    for vartype in VARTYPES:  # the bandwidths of all initial beliefs in one batched search per variable type
         vs = [v for v in fresh if fg.variables[v].vartype == vartype]
         if vs:
             for v, b in zip(vs, backend.manikde_batch(vartype, [fg.variables[v].belief.pts for v in vs])):
@@ -306,7 +357,7 @@ def solveGraph(fg, backend, gibbs_iters=3, seed=0, stats=None):
     conv_stream = 0
     for it in range(gibbs_iters):
         for group in colours:
-            for vartype in ("Pose2", "Point2"):
+            for vartype in VARTYPES:
                 vs = [v for v in group if fg.variables[v].vartype == vartype]
                 if not vs:
                     continue
@@ -457,6 +508,10 @@ class DeviceResidentBackend:
         return self.r.manifoldProducts_dev(groups, vartype, N, self.slab, Niter=1, seed=seed, streams=streams, ctx=self.ctx)
 
     def approx_conv_batch(self, convs, seed):
+        for c in convs:  # noise samples the host drew (convolution kind 7) travel to the device first
+            for k in ("src", "aux"):
+                if isinstance(c.get(k), np.ndarray):
+                    c[k] = self.r.upload_array(c[k], self.slab, self.ctx)
         return self.r.approxConvBatch_dev(convs, self.slab, seed=seed, ctx=self.ctx)
 
     def begin(self, fg):

@@ -199,9 +199,13 @@ typedef enum {
   CB2_FACTOR_PRIOR_POSE3 = 3,               /* Pose3 coordinates [t; rotation vector]: t = mean_t + n_t, R = Exp(mean_w) Exp(n_w) */
   CB2_FACTOR_POSE3POSE3 = 4,                /* forward: x_j = x_i o exp(z) on SE(3);  reverse: x_i = x_j o exp(z)^-1 */
   CB2_FACTOR_PRIOR_POINT2 = 5,              /* target ~ N(mean[0..1], L L^T), L = chol[0], chol[3], chol[4] (3 x 3 layout), no source */
-  CB2_FACTOR_POINT2POINT2_RANGE = 6         /* range-only (R:test/ICRA2022_tests/insufficient_data.jl:70-85): x_j = x_i + rho (cos t, sin t),
+  CB2_FACTOR_POINT2POINT2_RANGE = 6,        /* range-only (R:test/ICRA2022_tests/insufficient_data.jl:70-85): x_j = x_i + rho (cos t, sin t),
                                                rho ~ N(mean[0], chol[0]^2), t uniform on the circle -- one constraint on two coordinates,
                                                the same in both directions */
+  CB2_FACTOR_LINEAR_SAMPLES = 7             /* Prior / LinearRelative on a Euclidean variable of d = mean[0] coordinates (1..3) whose noise the
+                                               CALLER sampled (any distribution: Rayleigh, Uniform, Mixture ..., as the factors of
+                                               R:test/ICRA2022_tests/nongaussian_mixture.jl:24-51): aux = d x n_aux samples z;
+                                               forward x_j = x_i + z, reverse x_i = x_j - z, no source (n_src = 0): x = z */
 } cb2_factor_kind;
 
 typedef struct {
@@ -210,7 +214,7 @@ typedef struct {
   int32_t N;           /* particles to produce */
   int32_t n_src;       /* samples available in src (particle i uses src[i % n_src]) */
   const double* src;   /* d_src x n_src samples of the known variable; NULL for a prior */
-  const double* aux;   /* reverse bearing-range only: 3 x n_aux current samples of the target pose (heading is kept) */
+  const double* aux;   /* reverse bearing-range: 3 x n_aux current samples of the target pose (heading is kept); LINEAR_SAMPLES: the noise */
   int32_t n_aux;
   uint32_t stream;     /* Philox stream id of this convolution */
   double mean[6];      /* Pose2 prior / Pose2Pose2: [x, y, theta]; bearing-range: [bearing, range, 0]; Pose3 kinds: [t; rotation vector] */

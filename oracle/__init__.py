@@ -243,13 +243,17 @@ def se_residual(dim, X, p, q):
 
 def approx_conv(kind, reverse, N, mean, chol, seed, stream=0, src=None, aux=None):
     """Closed-form approxConv (kind 0 Pose2 prior, 1 Pose2Pose2, 2 Pose2Point2BearingRange, 3 Pose3 prior, 4 Pose3Pose3, 5 Point2 prior,
-    6 Point2Point2Range);
+    6 Point2Point2Range, 7 Prior / LinearRelative with caller-sampled noise in `aux`);
     returns N x d_tgt."""
     n = 6 if kind in (3, 4) else 3
     mean, chol = _f64(np.resize(np.asarray(mean, dtype=np.float64), n)), _f64(np.asarray(chol, dtype=np.float64).reshape(n * n))
     src = None if src is None else _f64(src)
     aux = None if aux is None else _f64(aux)
     dt = 6 if kind in (3, 4) else (2 if (kind in (5, 6) or (kind == 2 and not reverse)) else 3)
+    if kind == 7:   # linear relative / prior with the caller's noise samples (aux): d = mean[0]
+        dt = int(mean[0])
+        aux = _f64(np.reshape(aux, (-1, dt)))
+        src = None if src is None else _f64(np.reshape(src, (-1, dt)))
     out = np.zeros((N, dt))
     rc = lib().cb2o_approx_conv(kind, int(reverse), N, _p(src), 0 if src is None else src.shape[0], _p(aux),
                                 0 if aux is None else aux.shape[0], stream, _p(mean), _p(chol), C.c_uint64(seed), _p(out))

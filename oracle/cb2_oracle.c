@@ -648,7 +648,17 @@ int cb2o_se_residual(int dim, const double* X, const double* p, const double* q,
 
 int cb2o_approx_conv(int kind, int reverse, int N, const double* src, int n_src, const double* aux, int n_aux,
                      uint32_t stream, const double* mean, const double* chol, uint64_t seed, double* out) {
-  if (kind < 0 || kind > 6 || N <= 0) return -1;
+  if (kind < 0 || kind > 7 || N <= 0) return -1;
+  if (kind == 7) { /* Prior / LinearRelative with the caller's noise samples (factors of R:test/ICRA2022_tests/nongaussian_mixture.jl:24-51) */
+    const int dd = (int)mean[0];
+    if (dd < 1 || dd > 3 || !aux || n_aux <= 0) return -1;
+    for (int i = 0; i < N; ++i)
+      for (int k = 0; k < dd; ++k) {
+        double base = n_src > 0 ? src[(size_t)(i % n_src) * dd + k] : 0.0, z = aux[(size_t)(i % n_aux) * dd + k];
+        out[(size_t)i * dd + k] = reverse ? base - z : base + z;
+      }
+    return 0;
+  }
   if (kind == 3 || kind == 4) { approx_conv_pose3(kind, reverse, N, src, n_src, stream, mean, chol, seed, out); return 0; }
   for (int i = 0; i < N; ++i) {
     double z[3], nz[3];

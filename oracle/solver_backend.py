@@ -3,7 +3,7 @@ import numpy as np
 
 import oracle
 
-TOPO = {"Pose2": [0, 0, 1], "Point2": [0, 0]}
+TOPO = {"Pose2": [0, 0, 1], "Point2": [0, 0], "ContinuousScalar": [0]}
 
 
 class _Belief:
