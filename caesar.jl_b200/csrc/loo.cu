@@ -495,9 +495,10 @@ loo_small_kernel(const LooProblem* __restrict__ probs, const int* __restrict__ i
 // every peer's slot, one cluster barrier per step, slots double-buffered by step parity) and advance identical copies of the
 // search state.  Each CTA sorts its own copy (the bracket needs the smallest neighbour gap).
 constexpr int kLooCluster = 8;
-constexpr int kLooClusterThreads = kSmallN / kLooCluster;  // one row per thread
+constexpr int kLooClusterThreads = kSmallN / kLooCluster;  // row slots per CTA: one row per slot
+constexpr int kLooClusterCta = 2 * kLooClusterThreads;     // threads per CTA: every row is split into two column segments
 template <typename T>
-__global__ void __cluster_dims__(kLooCluster, 1, 1) __launch_bounds__(kLooClusterThreads)
+__global__ void __cluster_dims__(kLooCluster, 1, 1) __launch_bounds__(kLooClusterCta)
 loo_cluster_kernel(const LooProblem* __restrict__ probs, const int* __restrict__ ids, LooState* __restrict__ st) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -506,17 +507,18 @@ loo_cluster_kernel(const LooProblem* __restrict__ probs, const int* __restrict__
   const LooProblem pr = probs[p];
   const int N = pr.N, tid = threadIdx.x;
   __shared__ double sk[kSmallN];
-  __shared__ T sxs[kSmallN];
-  __shared__ double sred[kLooClusterThreads / 32];
+  __shared__ __align__(16) T sxs[kSmallN + 4];
+  __shared__ T part[kLooClusterCta];
+  __shared__ double sred[kLooClusterCta / 32];
   __shared__ double slots[2][kLooCluster];
   __shared__ LooState ss;
   int P2 = 1;
   while (P2 < N) P2 <<= 1;
-  for (int i = tid; i < P2; i += kLooClusterThreads) sk[i] = i < N ? pr.x[(size_t)i * pr.stride] : 1.7976931348623157e308;
+  for (int i = tid; i < P2; i += kLooClusterCta) sk[i] = i < N ? pr.x[(size_t)i * pr.stride] : 1.7976931348623157e308;
   __syncthreads();
   for (int k = 2; k <= P2; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < P2; i += kLooClusterThreads) {
+      for (int i = tid; i < P2; i += kLooClusterCta) {
         int ixj = i ^ j;
         if (ixj > i) {
           double a = sk[i], b = sk[ixj];
@@ -526,13 +528,13 @@ loo_cluster_kernel(const LooProblem* __restrict__ probs, const int* __restrict__
       __syncthreads();
     }
   double mn = 1e300;
-  for (int i = tid; i + 1 < N; i += kLooClusterThreads) mn = fmin(mn, sk[i + 1] - sk[i]);
+  for (int i = tid; i + 1 < N; i += kLooClusterCta) mn = fmin(mn, sk[i + 1] - sk[i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
   if ((tid & 31) == 0) sred[tid >> 5] = mn;
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < kLooClusterThreads / 32; ++w) mn = fmin(mn, sred[w]);
+    for (int w = 1; w < kLooClusterCta / 32; ++w) mn = fmin(mn, sred[w]);
     LooState s0;
     loo_bracket(s0, mn, sk[N - 1] - sk[0]);
     ss = s0;
@@ -541,50 +543,87 @@ loo_cluster_kernel(const LooProblem* __restrict__ probs, const int* __restrict__
   const double x_mid = circ ? 0.0 : sk[N >> 1];
   const bool wraps = circ && !(sk[0] >= -CB2_PI && sk[N - 1] <= CB2_PI && sk[N - 1] - sk[0] <= CB2_PI);
   const int rows = (N + kLooCluster - 1) / kLooCluster;   // rows of this problem per CTA (<= kLooClusterThreads)
-  const int row = rank * rows + tid;
-  const bool mine = tid < rows && row < N;
-  const int n8 = N & ~7;
+  // (row slot, column segment): with one thread per row a scheduler holds ONE warp and every dependent step of a pair
+  // (load, subtract, square, exponential, add) is exposed -- 24.7 k clk per golden-section step at N = 1000 against 8 k clk of
+  // exponentials; two segments per row give every scheduler a second warp, and the FP32 loop reads four columns per LDS.128 and
+  // squares them as packed pairs
+  const int rl = tid & (kLooClusterThreads - 1), seg = tid / kLooClusterThreads;
+  const int row = rank * rows + rl;
+  const bool mine = rl < rows && row < N;
+  const int half = (((N + 1) >> 1) + 3) & ~3;              // first column of the second segment: a multiple of four
+  const int c0 = seg ? min(N, half) : 0, c1 = seg ? N : min(N, half);
+  const int c1p = (c1 + 3) & ~3;                           // the last block of four may run into the padding behind N
+  const int npad = (N + 3) & ~3;
+#ifdef CB2_LOO_PROF
+  long long cp[5] = {0, 0, 0, 0, 0}, cl = clock64();
+  int csteps = 0;
+#define LOOC_T(k) do { long long t_ = clock64(); cp[k] += t_ - cl; cl = t_; } while (0)
+#else
+#define LOOC_T(k) do { } while (0)
+#endif
   for (int it = 0; it < 96; ++it) {
     __syncthreads();
     if (ss.phase == 3) break;  // identical in every CTA of the cluster: all leave together
+    LOOC_T(4);
     const double h = ss.h_eval;
     const double sc = sqrt(0.5 * CB2_LOG2E) / h;
     const T period = (T)(CB2_TWO_PI * sc);
-    for (int j = tid; j < N; j += kLooClusterThreads) sxs[j] = (T)(((circ ? wrap_pi(sk[j]) : sk[j]) - x_mid) * sc);
+    for (int j = tid; j < npad; j += kLooClusterCta) sxs[j] = j < N ? (T)(((circ ? wrap_pi(sk[j]) : sk[j]) - x_mid) * sc) : T(1e18);
     __syncthreads();
-    double v = 0;
-    if (mine) {
+    LOOC_T(0);
+    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+    if (mine && c1 > c0) {
       const T xi = sxs[row];
-      T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
       if (wraps) {
-        for (int j = 0; j < N; ++j) {
+        for (int j = c0; j < c1; ++j) {
           T ad = fabs(xi - sxs[j]);
           T df = fmin(ad, period - ad);
           a0 += (j == row) ? T(0) : fast_exp2(-(df * df));
         }
       } else {
-        for (int j = 0; j < n8; j += 8) {  // the self term (exp2(0) = 1) is summed and taken out below
-#pragma unroll
-          for (int u = 0; u < 8; u += 4) {
-            const T d0 = xi - sxs[j + u], d1 = xi - sxs[j + u + 1], d2 = xi - sxs[j + u + 2], d3 = xi - sxs[j + u + 3];
+        if constexpr (sizeof(T) == 4) {
+          const f32x2 nx = pack2(-(float)xi, -(float)xi);
+#pragma unroll 4
+          for (int j = c0; j < c1p; j += 4) {   // the self term (exp2(0) = 1) is summed and taken out below
+            f32x2 q01, q23;
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(q01), "=l"(q23) : "r"((uint32_t)__cvta_generic_to_shared(&sxs[j])));
+            const f32x2 d01 = add2(q01, nx), d23 = add2(q23, nx);
+            float s0, s1, s2, s3;
+            unpack2(mul2(d01, d01), s0, s1);
+            unpack2(mul2(d23, d23), s2, s3);
+            a0 += fast_exp2(-s0); a1 += fast_exp2(-s1); a2 += fast_exp2(-s2); a3 += fast_exp2(-s3);
+          }
+        } else {
+#pragma unroll 2
+          for (int j = c0; j < c1p; j += 4) {
+            const T d0 = xi - sxs[j], d1 = xi - sxs[j + 1], d2 = xi - sxs[j + 2], d3 = xi - sxs[j + 3];
             a0 += fast_exp2(-(d0 * d0)); a1 += fast_exp2(-(d1 * d1)); a2 += fast_exp2(-(d2 * d2)); a3 += fast_exp2(-(d3 * d3));
           }
         }
-        for (int j = n8; j < N; ++j) { const T d0 = xi - sxs[j]; a0 += fast_exp2(-(d0 * d0)); }
-        a0 -= T(1);
+        if (row >= c0 && row < c1) a0 -= T(1);
       }
-      const double a = (double)((a0 + a1) + (a2 + a3));
-      v = log(a > 2.2250738585072014e-308 ? a : 2.2250738585072014e-308);
     }
-    v = warp_sum(v);
-    if ((tid & 31) == 0) sred[tid >> 5] = v;
+    part[tid] = (a0 + a1) + (a2 + a3);
+    LOOC_T(1);
     __syncthreads();
+    if (seg == 0) {
+      double v = 0;
+      if (mine) {
+        const double a = (double)(part[rl] + part[kLooClusterThreads + rl]);
+        v = log(a > 2.2250738585072014e-308 ? a : 2.2250738585072014e-308);
+      }
+      v = warp_sum(v);
+      if ((tid & 31) == 0) sred[tid >> 5] = v;
+    }
+    __syncthreads();
+    LOOC_T(2);
     if (tid == 0) {
       double t = 0;
       for (int w = 0; w < kLooClusterThreads / 32; ++w) t += sred[w];
       for (int r = 0; r < kLooCluster; ++r) cluster.map_shared_rank(&slots[it & 1][0], r)[rank] = t;  // my partial into every peer
     }
     cluster.sync();
+    LOOC_T(3);
     if (tid == 0) {
       double t = 0;
       for (int r = 0; r < kLooCluster; ++r) t += slots[it & 1][r];  // fixed order: every CTA computes the same total
@@ -592,7 +631,15 @@ loo_cluster_kernel(const LooProblem* __restrict__ probs, const int* __restrict__
       golden_advance(s1, loo_objective(t, N, h));
       ss = s1;
     }
+#ifdef CB2_LOO_PROF
+    ++csteps;
+#endif
   }
+#ifdef CB2_LOO_PROF
+  if (blockIdx.x == 0 && (tid == 0 || tid == 200))
+    printf("loo cluster prof tid %d N %d steps %d clk/step: fill %lld pairs %lld owner %lld exchange %lld advance+barrier %lld\n", tid, N, csteps,
+           cp[0] / max(csteps, 1), cp[1] / max(csteps, 1), cp[2] / max(csteps, 1), cp[3] / max(csteps, 1), cp[4] / max(csteps, 1));
+#endif
   __syncthreads();
   if (tid == 0 && rank == 0) {
     LooState s1 = ss;
@@ -829,8 +876,8 @@ int cb2_bw_loo_dev_core(cb2_ctx* ctx, const double* const* mu_dev, const int32_t
     for (int id : small_ids) minN = std::min(minN, probs[id].N);
     const bool use_cluster = !getenv("CB2_NO_LOO_CLUSTER") && minN >= 192 && (int)small_ids.size() * kLooCluster <= 2 * ctx->sm_count;
     if (use_cluster) {
-      if (f64) loo_cluster_kernel<double><<<(int)small_ids.size() * kLooCluster, kLooClusterThreads, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
-      else loo_cluster_kernel<float><<<(int)small_ids.size() * kLooCluster, kLooClusterThreads, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
+      if (f64) loo_cluster_kernel<double><<<(int)small_ids.size() * kLooCluster, kLooClusterCta, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
+      else loo_cluster_kernel<float><<<(int)small_ids.size() * kLooCluster, kLooClusterCta, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
       CB2_CHECK_LAUNCH(ctx, "loo_cluster_kernel");
     } else {
       if (f64) loo_small_kernel<double><<<(int)small_ids.size(), kThreads, 0, ctx->stream>>>(probs_dev, small_dev, st_dev);
