@@ -279,6 +279,35 @@ tree_build_kernel(const DensMeta* __restrict__ metas, int d, int* __restrict__ i
     }
     __syncthreads();
     TREE_T(1);
+    if (!pow2 && N <= 2 * kTreeThreads && (N + cnt - 1) / cnt <= 128) {
+      // ragged N, small nodes: the bitonic network below would sort all P2 keys again on every level (55 rounds at N = 1000)
+      // although the elements already sit in their nodes; counting ranks inside the node gives the same (node, value, position)
+      // order in at most 128 compares per element
+      int dst[2] = {0, 0}, val[2] = {0, 0};
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int p = tid + c * kTreeThreads;
+        if (p < N) {
+          const unsigned long long op = ord[p];
+          const uint32_t tp = tag[p];
+          int lo, n, rank = 0;
+          node_range(N, l, (int)(tp >> 14), lo, n);
+#pragma unroll 4
+          for (int q = lo; q < lo + n; ++q) rank += (ord[q] < op || (ord[q] == op && tag[q] < tp)) ? 1 : 0;
+          dst[c] = lo + rank;
+          val[c] = perm[p];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int p = tid + c * kTreeThreads;
+        if (p < N) perm[dst[c]] = val[c];
+      }
+      __syncthreads();
+      TREE_T(2);
+      continue;
+    }
     // bitonic sort; when N is a power of two the nodes are aligned blocks of N>>l, sort inside blocks only
     const int kmax = pow2 ? (N >> l) : P2;
     // one compare-exchange per thread and round: pair q = (i, i | j)
